@@ -1,0 +1,226 @@
+// C-ABI plumbing: context, batch upload, pinned memory, depth-cap pre-pass.
+#include <algorithm>
+#include <queue>
+
+#include "ls_common.cuh"
+
+extern "C" int ls_abi_version(void) { return LS_ABI_VERSION; }
+
+extern "C" int ls_ctx_create(int device, ls_ctx **out) {
+  if (!out) return LS_E_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    fprintf(stderr, "longsom_b200: no CUDA device (%s); there is no CPU fallback\n", cudaGetErrorString(e));
+    return LS_E_CUDA;
+  }
+  if (device < 0 || device >= ndev) return LS_E_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return LS_E_CUDA;
+  ls_ctx *ctx = new ls_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return LS_E_CUDA;
+  }
+  for (auto &ev : ctx->ev)
+    if (cudaEventCreate(&ev) != cudaSuccess) {
+      delete ctx;
+      return LS_E_CUDA;
+    }
+  *out = ctx;
+  return LS_OK;
+}
+
+extern "C" int ls_ctx_destroy(ls_ctx *ctx) {
+  if (!ctx) return LS_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DBuf *bufs[] = {&ctx->tid,       &ctx->pos,       &ctx->flag,      &ctx->mapq,       &ctx->cell,     &ctx->cigar_off,
+                  &ctx->cigar,     &ctx->base_off,  &ctx->lq,        &ctx->seq4,       &ctx->qual,     &ctx->wtid,
+                  &ctx->wstart,    &ctx->wend,      &ctx->wref_off,  &ctx->ref,        &ctx->wtile_base, &ctx->nseg,
+                  &ctx->seg_off,   &ctx->segs,      &ctx->keys_a,    &ctx->keys_b,     &ctx->vals_a,   &ctx->vals_b,
+                  &ctx->rs_hist,   &ctx->scan_tmp,  &ctx->counters,  &ctx->tile_flag,  &ctx->tile_rank, &ctx->slot_tile,
+                  &ctx->slot_lo,   &ctx->slot_out,  &ctx->slot_mask, &ctx->slot_npass, &ctx->slot_off, &ctx->drop_keys,
+                  &ctx->out_tid,   &ctx->out_pos,   &ctx->out_ref,   &ctx->out_counts, &ctx->l2_scratch, &ctx->g_a,
+                  &ctx->g_b,       &ctx->g_c,       &ctx->g_d,       &ctx->g_e,        &ctx->rend,     &ctx->wcount};
+  for (DBuf *b : bufs) b->release();
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return LS_OK;
+}
+
+extern "C" const char *ls_last_error(const ls_ctx *ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int ls_host_alloc(size_t bytes, void **ptr) {
+  if (!ptr) return LS_E_ARG;
+  *ptr = nullptr;
+  if (bytes == 0) bytes = 1;
+  return cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) == cudaSuccess ? LS_OK : LS_E_CUDA;
+}
+extern "C" int ls_host_free(void *ptr) {
+  if (!ptr) return LS_OK;
+  return cudaFreeHost(ptr) == cudaSuccess ? LS_OK : LS_E_CUDA;
+}
+
+extern "C" int ls_device_synchronize(ls_ctx *ctx) {
+  if (!ctx) return LS_E_ARG;
+  LS_CK(cudaSetDevice(ctx->device));
+  LS_CK(cudaStreamSynchronize(ctx->stream));
+  return LS_OK;
+}
+
+__global__ void l2_flush_kernel(uint4 *p, size_t n, uint32_t v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = make_uint4(v, v, v, v);
+}
+
+extern "C" int ls_flush_l2(ls_ctx *ctx) {
+  if (!ctx) return LS_E_ARG;
+  LS_CK(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)256 << 20;  // 2x the 126 MB L2
+  LS_CK(ctx->l2_scratch.ensure(bytes));
+  static uint32_t v = 0;
+  l2_flush_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(ctx->l2_scratch.as<uint4>(), bytes / 16, ++v);
+  LS_CK(cudaGetLastError());
+  return LS_OK;
+}
+
+#define UP(buf, src, bytes)                                                                   \
+  do {                                                                                        \
+    LS_CK(ctx->buf.ensure((bytes) ? (bytes) : 16));                                           \
+    if (bytes) LS_CK(cudaMemcpyAsync(ctx->buf.p, (src), (bytes), cudaMemcpyHostToDevice, st)); \
+  } while (0)
+
+extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_windows *w) {
+  if (!ctx) return LS_E_ARG;
+  if (!b) LS_FAIL(LS_E_ARG, "ls_pileup_upload: batch is null");
+  ctx->have_batch = false;
+  ctx->have_run = false;
+  const int64_t n = b->n_reads;
+  if (n < 0 || b->n_cigar < 0 || b->n_bases < 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: negative size");
+  if (n >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_pileup_upload: more than 2^32-1 reads per batch");
+  if (n > 0 && (!b->tid || !b->pos || !b->flag || !b->mapq || !b->cell || !b->cigar_off || !b->base_off || !b->l_qseq))
+    LS_FAIL(LS_E_ARG, "ls_pileup_upload: null per-read array");
+  if (b->n_cigar > 0 && !b->cigar) LS_FAIL(LS_E_ARG, "ls_pileup_upload: null cigar");
+  if (b->n_bases > 0 && (!b->seq4 || !b->qual)) LS_FAIL(LS_E_ARG, "ls_pileup_upload: null seq4/qual");
+  int32_t max_cell = -1;
+  for (int64_t i = 0; i < n; ++i) {
+    if (i > 0 && (b->tid[i] < b->tid[i - 1] || (b->tid[i] == b->tid[i - 1] && b->pos[i] < b->pos[i - 1])))
+      LS_FAIL(LS_E_ARG, "ls_pileup_upload: reads are not sorted by (tid, pos)");
+    if (b->cigar_off[i + 1] < b->cigar_off[i] || (int64_t)b->cigar_off[i + 1] > b->n_cigar)
+      LS_FAIL(LS_E_ARG, "ls_pileup_upload: bad cigar_off");
+    if (b->base_off[i] % LS_BASE_ALIGN != 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: base_off not aligned");
+    if (b->l_qseq[i] < 0 || b->base_off[i] + (uint64_t)b->l_qseq[i] > (uint64_t)b->n_bases)
+      LS_FAIL(LS_E_ARG, "ls_pileup_upload: read bases exceed n_bases");
+    if (b->cell[i] > max_cell) max_cell = b->cell[i];
+  }
+  if (max_cell >= 0x7ffffffe) LS_FAIL(LS_E_ARG, "ls_pileup_upload: cell id too large");
+  const int64_t nw = w ? w->n_windows : 0;
+  if (nw < 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: negative n_windows");
+  if (nw > 0 && (!w->tid || !w->start || !w->end || !w->ref_off || !w->ref))
+    LS_FAIL(LS_E_ARG, "ls_pileup_upload: null window array");
+  const int T = ls_tile_size();
+  ctx->h_wtid.assign(nw ? w->tid : nullptr, nw ? w->tid + nw : nullptr);
+  ctx->h_wstart.assign(nw ? w->start : nullptr, nw ? w->start + nw : nullptr);
+  ctx->h_wend.assign(nw ? w->end : nullptr, nw ? w->end + nw : nullptr);
+  ctx->h_wtile_base.assign((size_t)nw + 1, 0);
+  for (int64_t i = 0; i < nw; ++i) {
+    if (w->end[i] < w->start[i] || w->start[i] < 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: bad window");
+    if (i > 0 && (w->tid[i] < w->tid[i - 1] || (w->tid[i] == w->tid[i - 1] && w->start[i] < w->end[i - 1])))
+      LS_FAIL(LS_E_ARG, "ls_pileup_upload: windows must be sorted by (tid, start) and disjoint");
+    if (w->ref_off[i + 1] - w->ref_off[i] != (uint64_t)(w->end[i] - w->start[i]))
+      LS_FAIL(LS_E_ARG, "ls_pileup_upload: ref_off does not match window length");
+    ctx->h_wtile_base[i + 1] = ctx->h_wtile_base[i] + (w->end[i] - w->start[i] + T - 1) / T;
+  }
+  ctx->n_tiles_total = ctx->h_wtile_base[nw];
+
+  LS_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  UP(tid, b->tid, (size_t)n * 4);
+  UP(pos, b->pos, (size_t)n * 4);
+  UP(flag, b->flag, (size_t)n * 2);
+  UP(mapq, b->mapq, (size_t)n);
+  UP(cell, b->cell, (size_t)n * 4);
+  UP(cigar_off, b->cigar_off, (size_t)(n + 1) * 4);
+  UP(cigar, b->cigar, (size_t)b->n_cigar * 4);
+  UP(base_off, b->base_off, (size_t)(n + 1) * 8);
+  UP(lq, b->l_qseq, (size_t)n * 4);
+  UP(seq4, b->seq4, (size_t)(b->n_bases + 1) / 2);
+  UP(qual, b->qual, (size_t)b->n_bases);
+  UP(wtid, w ? w->tid : nullptr, (size_t)nw * 4);
+  UP(wstart, w ? w->start : nullptr, (size_t)nw * 4);
+  UP(wend, w ? w->end : nullptr, (size_t)nw * 4);
+  UP(wref_off, w ? w->ref_off : nullptr, (size_t)(nw + 1) * 8);
+  UP(ref, w ? w->ref : nullptr, (size_t)(nw ? w->ref_off[nw] : 0));
+  UP(wtile_base, ctx->h_wtile_base.data(), (size_t)(nw + 1) * 8);
+  LS_CK(cudaStreamSynchronize(st));
+  ctx->n_reads = n;
+  ctx->n_cigar = b->n_cigar;
+  ctx->n_bases = b->n_bases;
+  ctx->n_windows = nw;
+  ctx->max_cell = max_cell;
+  ctx->n_drop = 0;
+  ctx->have_batch = true;
+  return LS_OK;
+}
+
+// ---- pileup max_depth -------------------------------------------------------------------------
+// htslib bam_plp_push drops a record iff its start equals the engine's current column and more
+// than maxcnt records are buffered.  Equivalent, per pileup() call
+// (= per window): the first kept record at a start position P is always accepted; a later
+// record at P is dropped iff 1 + #{accepted records of this call with end >= P} > maxcnt.
+// Only windows that fetch more than max_depth records can ever drop, so the common case
+// costs one device-side count (done inside seg_count_kernel) and nothing here.
+int ls_depth_cap_host(ls_ctx *ctx, int min_mq, int max_depth, const std::vector<uint32_t> &wcount) {
+  const int64_t n = ctx->n_reads, nw = ctx->n_windows;
+  std::vector<int32_t> tid(n), pos(n), rend(n);
+  std::vector<uint16_t> flag(n);
+  std::vector<uint8_t> mapq(n);
+  LS_CK(cudaMemcpy(tid.data(), ctx->tid.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  LS_CK(cudaMemcpy(pos.data(), ctx->pos.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  LS_CK(cudaMemcpy(rend.data(), ctx->rend.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  LS_CK(cudaMemcpy(flag.data(), ctx->flag.p, (size_t)n * 2, cudaMemcpyDeviceToHost));
+  LS_CK(cudaMemcpy(mapq.data(), ctx->mapq.p, (size_t)n, cudaMemcpyDeviceToHost));
+  std::vector<uint64_t> drops;
+  for (int64_t w = 0; w < nw; ++w) {
+    if ((int64_t)wcount[w] <= (int64_t)max_depth) continue;
+    const int32_t wt = ctx->h_wtid[w], ws = ctx->h_wstart[w], we = ctx->h_wend[w];
+    // first read of this contig
+    int64_t r0 = std::lower_bound(tid.begin(), tid.end(), wt) - tid.begin();
+    std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> live;
+    int32_t last_p = -1;
+    bool any_at_p = false;
+    for (int64_t r = r0; r < n && tid[r] == wt && pos[r] < we; ++r) {
+      uint32_t f = flag[r];
+      if (f & LS_FLAG_FILTER) continue;
+      if ((int)mapq[r] < min_mq) continue;
+      if ((f & LS_FLAG_PAIRED) && !(f & LS_FLAG_PROPER)) continue;
+      int32_t e = rend[r] > pos[r] ? rend[r] : pos[r] + 1;  // fetch overlap uses bam_endpos
+      if (e <= ws) continue;
+      const int32_t P = pos[r];
+      if (P != last_p) {
+        last_p = P;
+        any_at_p = false;
+      }
+      while (!live.empty() && live.top() < P) live.pop();
+      if (any_at_p && (int64_t)1 + (int64_t)live.size() > (int64_t)max_depth) {
+        drops.push_back(((uint64_t)w << 32) | (uint64_t)r);
+        continue;
+      }
+      any_at_p = true;
+      live.push(rend[r]);
+    }
+  }
+  std::sort(drops.begin(), drops.end());
+  ctx->n_drop = (int64_t)drops.size();
+  LS_CK(ctx->drop_keys.ensure(drops.size() * 8 + 16));
+  if (!drops.empty())
+    LS_CK(cudaMemcpy(ctx->drop_keys.p, drops.data(), drops.size() * 8, cudaMemcpyHostToDevice));
+  return LS_OK;
+}

@@ -1,0 +1,123 @@
+// K2: fp64 beta-binomial upper tails, p = scipy.stats.betabinom.sf(k - eps, n, a, b).
+//
+// Replaces the scalar scipy calls of BaseCellCalling.step1.py:196,201,329-330,427-428 and
+// SingleCellGenotype.py:204 / HCCVSingleCellGenotype.py:204.  scipy evaluates
+//   sf = clip(1 - np.sum(exp(logpmf(arange(0, k)))), 0, 1)
+// with logpmf built from cephes lbeta (ls_cephes.h) and np.sum's pairwise order
+// (ls_pairwise.h); both are restated exactly so that only libm-level (<= 1-2 ulp) differences
+// remain.  Compiled with -fmad=false: the reference arithmetic has no fused multiply-adds.
+//
+// Work decomposition: one thread per pmf TERM (balanced however skewed k is), terms staged
+// in an HBM scratch in query-major order, then one thread per query replays numpy's
+// pairwise reduction over its slice.
+#include <algorithm>
+
+#include "ls_common.cuh"
+#include "ls_pairwise.h"
+
+__global__ void bb_const_kernel(double a, double b, double *out) { out[0] = ls_lbeta(a, b); }
+
+__global__ void __launch_bounds__(256) bb_terms_kernel(const int32_t *__restrict__ k, const int32_t *__restrict__ n,
+                                                       const uint64_t *__restrict__ off, int64_t m, uint64_t total,
+                                                       double a, double b, const double *__restrict__ lab_p,
+                                                       double *__restrict__ terms) {
+  const double lab = lab_p[0];
+  for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    // query q with off[q] <= t < off[q+1]
+    int64_t lo = 0, hi = m;
+    while (hi - lo > 1) {
+      int64_t mid = (lo + hi) >> 1;
+      if (off[mid] <= t)
+        lo = mid;
+      else
+        hi = mid;
+    }
+    const double nn = (double)n[lo];
+    const double i = (double)(t - off[lo]);
+    const double lnp1 = log(nn + 1.0);
+    terms[t] = exp(ls_betabinom_logpmf(i, nn, a, b, lnp1, lab));
+  }
+}
+
+__global__ void __launch_bounds__(128) bb_sum_kernel(const int32_t *__restrict__ k, const int32_t *__restrict__ n,
+                                                     const uint64_t *__restrict__ off, int64_t m,
+                                                     const double *__restrict__ terms, double *__restrict__ p) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const uint64_t lo = off[q], hi = off[q + 1];
+  double cdf = 0.0;
+  if (hi > lo) cdf = ls_pairwise_sum(terms + lo, (long)(hi - lo));
+  p[q] = ls_sf_finish(k[q], n[q], cdf);
+}
+
+extern "C" int ls_betabinom_sf(ls_ctx *ctx, const int32_t *k, const int32_t *n, double a, double b, double *p,
+                               int64_t m, ls_run_stats *stats) {
+  if (!ctx) return LS_E_ARG;
+  if (m < 0 || (m > 0 && (!k || !n || !p))) LS_FAIL(LS_E_ARG, "ls_betabinom_sf: null array");
+  if (!(a > 0.0) || !(b > 0.0)) LS_FAIL(LS_E_ARG, "ls_betabinom_sf: a and b must be > 0");
+  LS_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  ls_run_stats S;
+  memset(&S, 0, sizeof S);
+  if (m == 0) {
+    if (stats) *stats = S;
+    return LS_OK;
+  }
+  const uint64_t CAP = (uint64_t)1 << 26;  // pmf terms staged per chunk (512 MB of doubles)
+  LS_CK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
+  LS_CK(ctx->g_e.ensure(64));
+  bb_const_kernel<<<1, 1, 0, st>>>(a, b, ctx->g_e.as<double>());
+  int launches = 1;
+  float ms_total = 0.f;
+  std::vector<uint64_t> off;
+  int64_t q0 = 0;
+  while (q0 < m) {
+    off.clear();
+    off.push_back(0);
+    int64_t q1 = q0;
+    uint64_t tot = 0;
+    while (q1 < m) {
+      uint64_t t = (n[q1] >= 0 && k[q1] > 0 && k[q1] <= n[q1]) ? (uint64_t)k[q1] : 0;
+      if (q1 > q0 && tot + t > CAP) break;
+      tot += t;
+      off.push_back(tot);
+      ++q1;
+    }
+    const int64_t mc = q1 - q0;
+    LS_CK(ctx->g_a.ensure((size_t)mc * 4));
+    LS_CK(ctx->g_b.ensure((size_t)mc * 4));
+    LS_CK(ctx->g_c.ensure((size_t)(mc + 1) * 8));
+    LS_CK(ctx->g_d.ensure((size_t)mc * 8));
+    LS_CK(ctx->scan_tmp.ensure((size_t)(tot ? tot : 1) * 8));
+    LS_CK(cudaMemcpyAsync(ctx->g_a.p, k + q0, (size_t)mc * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaMemcpyAsync(ctx->g_b.p, n + q0, (size_t)mc * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaMemcpyAsync(ctx->g_c.p, off.data(), (size_t)(mc + 1) * 8, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaEventRecord(ctx->ev[0], st));
+    if (tot) {
+      uint64_t nb = (tot + 255) / 256;
+      unsigned grid = (unsigned)std::min<uint64_t>(nb, (uint64_t)ctx->num_sms * 32);
+      bb_terms_kernel<<<grid, 256, 0, st>>>(ctx->g_a.as<int32_t>(), ctx->g_b.as<int32_t>(), ctx->g_c.as<uint64_t>(), mc,
+                                            tot, a, b, ctx->g_e.as<double>(), ctx->scan_tmp.as<double>());
+      ++launches;
+    }
+    bb_sum_kernel<<<(unsigned)((mc + 127) / 128), 128, 0, st>>>(ctx->g_a.as<int32_t>(), ctx->g_b.as<int32_t>(),
+                                                                ctx->g_c.as<uint64_t>(), mc, ctx->scan_tmp.as<double>(),
+                                                                ctx->g_d.as<double>());
+    ++launches;
+    LS_CK(cudaGetLastError());
+    LS_CK(cudaEventRecord(ctx->ev[1], st));
+    LS_CK(cudaMemcpyAsync(p + q0, ctx->g_d.p, (size_t)mc * 8, cudaMemcpyDeviceToHost, st));
+    LS_CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    LS_CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ms_total += ms;
+    S.n_events += (int64_t)tot;
+    q0 = q1;
+  }
+  S.ms_count = ms_total;
+  S.ms_total = ms_total;
+  S.count_launches = launches;
+  if (stats) *stats = S;
+  return LS_OK;
+}

@@ -1,0 +1,298 @@
+// K1': pileup at candidate sites, per (site, cell) Dp / Alt.
+//
+// Replaces the pileup loop of SingleCellGenotype.run_interval (SingleCellGenotype.py:114-178)
+// and HCCVSingleCellGenotype.run_interval (:112-176): for every candidate site, every read
+// entry whose class is in {A,C,T,G,I,D,N} (--alt_flag All) or equals ALT_expected
+// (--alt_flag Alt), whose barcode is in --meta, and that is not secondary / duplicate /
+// supplementary, adds 1 to Dp[site, cell] and, if its class equals ALT_expected, to Alt.
+//
+// Design: candidate sites are sparse (<= 2e5) while reads are dense, so the scan is
+// read-major: one thread walks one read's CIGAR, binary-searches the sorted site table for
+// sites inside each reference-consuming op and scatters with global atomics into the dense
+// [site][cell] tensors (one int32 add per hit; hits are ~depth x sites, tiny next to HBM).
+// Bases that cover no candidate site are never loaded.
+#include <algorithm>
+#include <queue>
+
+#include "ls_common.cuh"
+
+struct GenoArgs {
+  int64_t n_reads;
+  const int32_t *tid, *pos, *cell, *lq;
+  const uint16_t *flag;
+  const uint8_t *mapq;
+  const uint32_t *cigar_off, *cigar;
+  const uint64_t *base_off;
+  const uint8_t *seq4, *qual;
+  const uint64_t *site_key;  // tid<<32 | pos, sorted
+  const uint8_t *alt_class;
+  const uint32_t *site_bin;  // index of the pileup() call (50 kb bin) of each site
+  int64_t n_sites;
+  int32_t n_cells;
+  int min_bq, min_mq, alt_only;
+  const uint64_t *drop_keys;  // (bin<<32 | read) removed by the depth cap
+  int64_t n_drop;
+  int32_t *dp, *alt;
+  unsigned long long *n_events;
+};
+
+__device__ __forceinline__ int64_t lower_site(const GenoArgs &a, uint64_t key) {
+  int64_t lo = 0, hi = a.n_sites;
+  while (lo < hi) {
+    int64_t m = (lo + hi) >> 1;
+    if (a.site_key[m] < key)
+      lo = m + 1;
+    else
+      hi = m;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ bool geno_dropped(const GenoArgs &a, uint32_t bin, uint32_t r) {
+  if (a.n_drop == 0) return false;
+  uint64_t key = ((uint64_t)bin << 32) | r;
+  int64_t lo = 0, hi = a.n_drop;
+  while (lo < hi) {
+    int64_t m = (lo + hi) >> 1;
+    if (a.drop_keys[m] < key)
+      lo = m + 1;
+    else
+      hi = m;
+  }
+  return lo < a.n_drop && a.drop_keys[lo] == key;
+}
+
+__global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long nev = 0;
+  if (r < a.n_reads) {
+    const uint32_t flag = a.flag[r];
+    const int32_t cell = a.cell[r];
+    const int32_t tid = a.tid[r];
+    if (tid >= 0 && read_passes_engine(flag, a.mapq[r], a.min_mq) && !(flag & LS_FLAG_SUPPL) && cell >= 0 &&
+        cell < a.n_cells) {
+      const uint32_t k0 = a.cigar_off[r], kend = a.cigar_off[r + 1];
+      int32_t x = a.pos[r];
+      uint32_t y = 0;
+      const uint64_t boff = a.base_off[r];
+      const uint32_t lq = (uint32_t)a.lq[r];
+      int64_t s = lower_site(a, ((uint64_t)(uint32_t)tid << 32) | (uint32_t)x);
+      for (uint32_t k = k0; k < kend && s < a.n_sites; ++k) {
+        const uint32_t c = a.cigar[k];
+        const uint32_t op = c & 15u;
+        const int32_t len = (int32_t)(c >> 4);
+        const bool match = op_is_match(op);
+        if ((match || op == OP_D || op == OP_N) && len > 0) {
+          const uint64_t kend_key = ((uint64_t)(uint32_t)tid << 32) | (uint32_t)(x + len);
+          while (s < a.n_sites && a.site_key[s] < kend_key) {
+            const int32_t sp = (int32_t)(a.site_key[s] & 0xffffffffu);
+            // site_key[s] >= (tid, x) holds because s only moves forward with x
+            const int32_t j = sp - x;
+            const uint32_t qpos = match ? y + (uint32_t)j : y;
+            const uint32_t q = qpos < lq ? a.qual[boff + qpos] : 0u;
+            if ((int)q >= a.min_bq && !geno_dropped(a, a.site_bin[s], (uint32_t)r)) {
+              int ind = (j == len - 1) ? indel_after(a.cigar, k, kend, op) : 0;
+              int cls;
+              if (ind < 0)
+                cls = LS_CLASS_D;
+              else if (ind > 0)
+                cls = LS_CLASS_I;
+              else if (match) {
+                uint32_t code = 15u;
+                if (qpos < lq) {
+                  uint32_t bb = a.seq4[(boff + qpos) >> 1];
+                  code = (qpos & 1u) ? (bb & 15u) : (bb >> 4);
+                }
+                cls = class_of_code(code);
+              } else
+                cls = (op == OP_D) ? LS_CLASS_O : LS_CLASS_NA;
+              const int ac = a.alt_class[s];
+              const bool use = a.alt_only ? (cls == ac && cls != LS_CLASS_NA) : (cls != LS_CLASS_NA && cls != LS_CLASS_O);
+              if (use) {
+                atomicAdd(&a.dp[(size_t)s * a.n_cells + cell], 1);
+                if (cls == ac) atomicAdd(&a.alt[(size_t)s * a.n_cells + cell], 1);
+                ++nev;
+              }
+            }
+            ++s;
+          }
+        }
+        if (match) {
+          x += len;
+          y += (uint32_t)len;
+        } else if (op == OP_D || op == OP_N) {
+          x += len;
+        } else if (op == OP_I || op == OP_S) {
+          y += (uint32_t)len;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nev += __shfl_xor_sync(0xffffffffu, nev, o);
+  if ((threadIdx.x & 31) == 0 && nev) atomicAdd(a.n_events, nev);
+}
+
+// read end (exclusive) per read, for the depth-cap pre-pass
+__global__ void __launch_bounds__(256) read_end_kernel(int64_t n, const int32_t *__restrict__ pos,
+                                                       const uint32_t *__restrict__ cigar_off,
+                                                       const uint32_t *__restrict__ cigar, int32_t *__restrict__ rend) {
+  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  int32_t x = pos[r];
+  for (uint32_t k = cigar_off[r]; k < cigar_off[r + 1]; ++k) {
+    uint32_t op = cigar[k] & 15u;
+    if (op_consumes_ref(op)) x += (int32_t)(cigar[k] >> 4);
+  }
+  rend[r] = x;
+}
+
+// Depth cap per pileup() call of the genotype scripts: one call per 50 kb bin of candidate sites
+// over [min-1, max+1) (SingleCellGenotype.py:110-124).  Same rule as ls_depth_cap_host.
+static int geno_depth_cap(ls_ctx *ctx, const std::vector<int32_t> &btid, const std::vector<int32_t> &bstart,
+                          const std::vector<int32_t> &bend, int min_mq, int max_depth) {
+  const int64_t n = ctx->n_reads;
+  ctx->n_drop = 0;
+  if (max_depth <= 0 || n <= (int64_t)max_depth) return LS_OK;
+  cudaStream_t st = ctx->stream;
+  LS_CK(ctx->rend.ensure((size_t)n * 4));
+  read_end_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ctx->pos.as<int32_t>(), ctx->cigar_off.as<uint32_t>(),
+                                                               ctx->cigar.as<uint32_t>(), ctx->rend.as<int32_t>());
+  std::vector<int32_t> tid(n), pos(n), rend(n);
+  std::vector<uint16_t> flag(n);
+  std::vector<uint8_t> mapq(n);
+  LS_CK(cudaMemcpyAsync(rend.data(), ctx->rend.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(tid.data(), ctx->tid.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(pos.data(), ctx->pos.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(flag.data(), ctx->flag.p, (size_t)n * 2, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(mapq.data(), ctx->mapq.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaStreamSynchronize(st));
+  std::vector<uint64_t> drops;
+  for (size_t w = 0; w < btid.size(); ++w) {
+    const int32_t wt = btid[w], ws = bstart[w], we = bend[w];
+    int64_t r0 = std::lower_bound(tid.begin(), tid.end(), wt) - tid.begin();
+    std::priority_queue<int32_t, std::vector<int32_t>, std::greater<int32_t>> live;
+    int32_t last_p = -1;
+    bool any_at_p = false;
+    for (int64_t r = r0; r < n && tid[r] == wt && pos[r] < we; ++r) {
+      uint32_t f = flag[r];
+      if (f & LS_FLAG_FILTER) continue;
+      if ((int)mapq[r] < min_mq) continue;
+      if ((f & LS_FLAG_PAIRED) && !(f & LS_FLAG_PROPER)) continue;
+      int32_t e = rend[r] > pos[r] ? rend[r] : pos[r] + 1;
+      if (e <= ws) continue;
+      const int32_t P = pos[r];
+      if (P != last_p) {
+        last_p = P;
+        any_at_p = false;
+      }
+      while (!live.empty() && live.top() < P) live.pop();
+      if (any_at_p && (int64_t)1 + (int64_t)live.size() > (int64_t)max_depth) {
+        drops.push_back(((uint64_t)w << 32) | (uint64_t)r);
+        continue;
+      }
+      any_at_p = true;
+      live.push(rend[r]);
+    }
+  }
+  std::sort(drops.begin(), drops.end());
+  ctx->n_drop = (int64_t)drops.size();
+  LS_CK(ctx->drop_keys.ensure(drops.size() * 8 + 16));
+  if (!drops.empty()) LS_CK(cudaMemcpy(ctx->drop_keys.p, drops.data(), drops.size() * 8, cudaMemcpyHostToDevice));
+  return LS_OK;
+}
+
+extern "C" int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int32_t *site_pos,
+                                 const uint8_t *alt_class, int64_t n_sites, int32_t n_cells,
+                                 const ls_geno_params *params, int32_t *dp, int32_t *alt, ls_run_stats *stats) {
+  if (!ctx) return LS_E_ARG;
+  if (!params) LS_FAIL(LS_E_ARG, "ls_genotype_count: params is null");
+  if (!ctx->have_batch) LS_FAIL(LS_E_STATE, "ls_genotype_count: no batch uploaded");
+  if (n_sites < 0 || n_cells < 0) LS_FAIL(LS_E_ARG, "ls_genotype_count: negative size");
+  ls_run_stats S;
+  memset(&S, 0, sizeof S);
+  if (n_sites == 0 || n_cells == 0) {
+    if (stats) *stats = S;
+    return LS_OK;
+  }
+  if (!site_tid || !site_pos || !alt_class || !dp || !alt) LS_FAIL(LS_E_ARG, "ls_genotype_count: null array");
+  const int32_t bin = params->bin_size > 0 ? params->bin_size : 50000;
+  std::vector<uint64_t> keys((size_t)n_sites);
+  std::vector<uint32_t> sbin((size_t)n_sites);
+  std::vector<int32_t> btid, bstart, bend;
+  for (int64_t i = 0; i < n_sites; ++i) {
+    if (site_tid[i] < 0 || site_pos[i] < 0) LS_FAIL(LS_E_ARG, "ls_genotype_count: negative site coordinate");
+    keys[i] = ((uint64_t)(uint32_t)site_tid[i] << 32) | (uint32_t)site_pos[i];
+    if (i > 0 && keys[i] <= keys[i - 1]) LS_FAIL(LS_E_ARG, "ls_genotype_count: sites must be sorted and unique");
+    // build_dict_variants: CHROM_floor(POS / bin) with the 1-based POS of the TSV (:253-274)
+    const int64_t code = ((int64_t)site_pos[i] + 1) / bin;
+    if (i == 0 || site_tid[i] != site_tid[i - 1] || code != ((int64_t)site_pos[i - 1] + 1) / bin) {
+      btid.push_back(site_tid[i]);
+      bstart.push_back(site_pos[i] - 1 < 0 ? 0 : site_pos[i] - 1);
+      bend.push_back(site_pos[i] + 1);
+    } else {
+      bend.back() = site_pos[i] + 1;
+    }
+    sbin[i] = (uint32_t)(btid.size() - 1);
+  }
+  LS_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  int rc = geno_depth_cap(ctx, btid, bstart, bend, params->min_mq, params->max_depth);
+  if (rc != LS_OK) return rc;
+  const size_t cells = (size_t)n_sites * (size_t)n_cells;
+  LS_CK(ctx->g_a.ensure((size_t)n_sites * 8));
+  LS_CK(ctx->g_b.ensure((size_t)n_sites));
+  LS_CK(ctx->g_c.ensure(cells * 4));
+  LS_CK(ctx->g_d.ensure(cells * 4));
+  LS_CK(ctx->g_e.ensure((size_t)n_sites * 4));
+  LS_CK(ctx->counters.ensure(64));
+  LS_CK(cudaMemcpyAsync(ctx->g_a.p, keys.data(), (size_t)n_sites * 8, cudaMemcpyHostToDevice, st));
+  LS_CK(cudaMemcpyAsync(ctx->g_b.p, alt_class, (size_t)n_sites, cudaMemcpyHostToDevice, st));
+  LS_CK(cudaMemcpyAsync(ctx->g_e.p, sbin.data(), (size_t)n_sites * 4, cudaMemcpyHostToDevice, st));
+  LS_CK(cudaEventRecord(ctx->ev[0], st));
+  LS_CK(cudaMemsetAsync(ctx->g_c.p, 0, cells * 4, st));
+  LS_CK(cudaMemsetAsync(ctx->g_d.p, 0, cells * 4, st));
+  LS_CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+  GenoArgs a;
+  a.n_reads = ctx->n_reads;
+  a.tid = ctx->tid.as<int32_t>();
+  a.pos = ctx->pos.as<int32_t>();
+  a.cell = ctx->cell.as<int32_t>();
+  a.lq = ctx->lq.as<int32_t>();
+  a.flag = ctx->flag.as<uint16_t>();
+  a.mapq = ctx->mapq.as<uint8_t>();
+  a.cigar_off = ctx->cigar_off.as<uint32_t>();
+  a.cigar = ctx->cigar.as<uint32_t>();
+  a.base_off = ctx->base_off.as<uint64_t>();
+  a.seq4 = ctx->seq4.as<uint8_t>();
+  a.qual = ctx->qual.as<uint8_t>();
+  a.site_key = ctx->g_a.as<uint64_t>();
+  a.alt_class = ctx->g_b.as<uint8_t>();
+  a.site_bin = ctx->g_e.as<uint32_t>();
+  a.n_sites = n_sites;
+  a.n_cells = n_cells;
+  a.min_bq = params->min_bq;
+  a.min_mq = params->min_mq;
+  a.alt_only = params->alt_only;
+  a.drop_keys = ctx->drop_keys.as<uint64_t>();
+  a.n_drop = ctx->n_drop;
+  a.dp = ctx->g_c.as<int32_t>();
+  a.alt = ctx->g_d.as<int32_t>();
+  a.n_events = ctx->counters.as<unsigned long long>();
+  LS_CK(cudaEventRecord(ctx->ev[1], st));
+  if (ctx->n_reads > 0) genotype_kernel<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, st>>>(a);
+  LS_CK(cudaGetLastError());
+  LS_CK(cudaEventRecord(ctx->ev[2], st));
+  LS_CK(cudaMemcpyAsync(dp, ctx->g_c.p, cells * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(alt, ctx->g_d.p, cells * 4, cudaMemcpyDeviceToHost, st));
+  unsigned long long nev = 0;
+  LS_CK(cudaMemcpyAsync(&nev, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaStreamSynchronize(st));
+  LS_CK(cudaEventElapsedTime(&S.ms_count, ctx->ev[1], ctx->ev[2]));
+  LS_CK(cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[2]));
+  S.n_events = (int64_t)nev;
+  S.count_launches = 1;
+  ctx->n_drop = 0;
+  if (stats) *stats = S;
+  return LS_OK;
+}

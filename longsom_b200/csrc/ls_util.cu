@@ -1,0 +1,260 @@
+// Device-wide exclusive scan and stable LSD radix sort (hand-written; no CUB / Thrust).
+// Both are plumbing for the pileup path: the scan turns per-read segment counts into
+// offsets, the sort groups (read, tile) segments by (tile, cell).
+#include "ls_common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread over the block; returns exclusive prefix, total in *total
+template <int THREADS>
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total, uint32_t *smem /*THREADS/32+1*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  uint32_t inc = warp_incl_scan(v, lane);
+  if (lane == 31) smem[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    uint32_t s = (lane < THREADS / 32) ? smem[lane] : 0u;
+    uint32_t si = warp_incl_scan(s, lane);
+    if (lane < THREADS / 32) smem[lane] = si - s;
+    if (lane == THREADS / 32 - 1) smem[THREADS / 32] = si;
+  }
+  __syncthreads();
+  uint32_t r = smem[w] + inc - v;
+  *total = smem[THREADS / 32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials(const uint32_t *__restrict__ in, int64_t n,
+                                                              uint32_t *__restrict__ partial) {
+  __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK;
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + (int64_t)i * SCAN_THREADS + threadIdx.x;
+    if (idx < n) s += in[idx];
+  }
+  uint32_t tot;
+  block_excl_scan<SCAN_THREADS>(s, &tot, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) scan_of_partials(uint32_t *__restrict__ partial, int64_t nb,
+                                                         uint64_t *__restrict__ total) {
+  __shared__ uint32_t sm[1024 / 32 + 1];
+  __shared__ uint64_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int64_t base = 0; base < nb; base += 1024) {
+    int64_t idx = base + threadIdx.x;
+    uint32_t v = idx < nb ? partial[idx] : 0u;
+    uint32_t tot;
+    uint32_t ex = block_excl_scan<1024>(v, &tot, sm);
+    uint64_t carry = carry_s;
+    if (idx < nb) partial[idx] = (uint32_t)(carry + ex);
+    __syncthreads();
+    if (threadIdx.x == 0) carry_s = carry + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                           int64_t n, const uint32_t *__restrict__ partial) {
+  __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
+  int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t v[SCAN_ITEMS];
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    v[i] = idx < n ? in[idx] : 0u;
+    s += v[i];
+  }
+  uint32_t tot;
+  uint32_t ex = block_excl_scan<SCAN_THREADS>(s, &tot, sm) + partial[blockIdx.x];
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; ++i) {
+    int64_t idx = base + i;
+    if (idx < n) out[idx] = ex;
+    ex += v[i];
+  }
+}
+
+// ---------------- radix sort ------------------------------------------------------------
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ROUNDS = 8;                       // items per thread per chunk
+constexpr int RS_CHUNK = RS_THREADS * RS_ROUNDS;   // 2048
+
+__global__ void __launch_bounds__(RS_THREADS) rs_hist(const uint64_t *__restrict__ keys, int64_t n, int64_t per_block,
+                                                      int shift, uint32_t *__restrict__ hist, int G) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  int64_t lo = (int64_t)blockIdx.x * per_block;
+  int64_t hi = lo + per_block < n ? lo + per_block : n;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += RS_THREADS) {
+    uint32_t d = (uint32_t)(keys[i] >> shift) & 255u;
+    atomicAdd(&h[d], 1u);
+  }
+  __syncthreads();
+  hist[(int64_t)threadIdx.x * G + blockIdx.x] = h[threadIdx.x];
+}
+
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restrict__ keys_in,
+                                                         const uint32_t *__restrict__ vals_in,
+                                                         uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                         int64_t n, int64_t per_block, int shift,
+                                                         const uint32_t *__restrict__ hist_scanned, int G, int first_pass) {
+  __shared__ uint32_t base[256];
+  __shared__ uint32_t wcnt[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * G + blockIdx.x];
+  int64_t lo = (int64_t)blockIdx.x * per_block;
+  int64_t hi = lo + per_block < n ? lo + per_block : n;
+  for (int64_t chunk = lo; chunk < hi; chunk += RS_CHUNK) {
+    for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    uint64_t key[RS_ROUNDS];
+    uint32_t val[RS_ROUNDS];
+    uint32_t rank[RS_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+      int64_t idx = chunk + (int64_t)w * (32 * RS_ROUNDS) + r * 32 + lane;
+      bool valid = idx < hi;
+      key[r] = valid ? keys_in[idx] : 0ull;
+      if (HAS_VALS) val[r] = valid ? (first_pass ? (uint32_t)idx : vals_in[idx]) : 0u;
+      uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;
+      uint32_t peers = __match_any_sync(0xffffffffu, d);
+      uint32_t before = __popc(peers & lt);
+      uint32_t cur = valid ? wcnt[w][d] : 0u;
+      rank[r] = cur + before;
+      __syncwarp();
+      if (valid && before == 0) wcnt[w][d] = cur + __popc(peers);
+      __syncwarp();
+    }
+    __syncthreads();
+    {  // exclusive scan across warps per digit, fold in the running block base
+      int d = threadIdx.x;
+      uint32_t run = base[d];
+#pragma unroll
+      for (int ww = 0; ww < RS_WARPS; ++ww) {
+        uint32_t t = wcnt[ww][d];
+        wcnt[ww][d] = run;
+        run += t;
+      }
+      base[d] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+      int64_t idx = chunk + (int64_t)w * (32 * RS_ROUNDS) + r * 32 + lane;
+      if (idx < hi) {
+        uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
+        uint32_t p = wcnt[w][d] + rank[r];
+        keys_out[p] = key[r];
+        if (HAS_VALS) vals_out[p] = val[r];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(1024) rs_scan_hist(uint32_t *__restrict__ hist, int total) {
+  // exclusive scan over `total` entries (digit-major, block-minor), single block
+  __shared__ uint32_t sm[1024 / 32 + 1];
+  int per = (total + 1023) / 1024;
+  int lo = threadIdx.x * per;
+  int hi = lo + per < total ? lo + per : total;
+  uint32_t s = 0;
+  for (int i = lo; i < hi; ++i) s += hist[i];
+  uint32_t tot;
+  uint32_t ex = block_excl_scan<1024>(s, &tot, sm);
+  for (int i = lo; i < hi; ++i) {
+    uint32_t t = hist[i];
+    hist[i] = ex;
+    ex += t;
+  }
+}
+
+template <bool HAS_VALS>
+cudaError_t radix_sort_impl(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n,
+                            int key_bits, DBuf &hist, uint64_t **sorted_keys, uint32_t **sorted_vals, int num_sms,
+                            cudaStream_t st, int *launches) {
+  *sorted_keys = keys_a;
+  if (sorted_vals) *sorted_vals = vals_a;
+  if (n <= 0) return cudaSuccess;
+  int passes = (key_bits + 7) / 8;
+  if (passes < 1) passes = 1;
+  int64_t nchunks = (n + RS_CHUNK - 1) / RS_CHUNK;
+  int G = (int)(nchunks < (int64_t)num_sms * 4 ? nchunks : (int64_t)num_sms * 4);
+  int64_t per_block = ((nchunks + G - 1) / G) * RS_CHUNK;
+  cudaError_t e = hist.ensure((size_t)256 * G * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  uint64_t *kin = keys_a, *kout = keys_b;
+  uint32_t *vin = vals_a, *vout = vals_b;
+  for (int p = 0; p < passes; ++p) {
+    int shift = p * 8;
+    rs_hist<<<G, RS_THREADS, 0, st>>>(kin, n, per_block, shift, hist.as<uint32_t>(), G);
+    rs_scan_hist<<<1, 1024, 0, st>>>(hist.as<uint32_t>(), 256 * G);
+    rs_scatter<HAS_VALS><<<G, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, per_block, shift, hist.as<uint32_t>(), G,
+                                                   p == 0 ? 1 : 0);
+    if (launches) *launches += 3;
+    uint64_t *tk = kin;
+    kin = kout;
+    kout = tk;
+    uint32_t *tv = vin;
+    vin = vout;
+    vout = tv;
+  }
+  *sorted_keys = kin;
+  if (sorted_vals) *sorted_vals = vin;
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t ls_scan_exclusive_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total, DBuf &tmp,
+                                  cudaStream_t st) {
+  if (n <= 0) {
+    if (d_total) return cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
+    return cudaSuccess;
+  }
+  int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  cudaError_t e = tmp.ensure((size_t)nb * sizeof(uint32_t));
+  if (e != cudaSuccess) return e;
+  scan_partials<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, n, tmp.as<uint32_t>());
+  scan_of_partials<<<1, 1024, 0, st>>>(tmp.as<uint32_t>(), nb, d_total);
+  scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, tmp.as<uint32_t>());
+  return cudaGetLastError();
+}
+
+cudaError_t ls_radix_sort_pairs(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n,
+                                int key_bits, DBuf &hist, uint64_t **sorted_keys, uint32_t **sorted_vals, int num_sms,
+                                cudaStream_t st, int *launches) {
+  return radix_sort_impl<true>(keys_a, keys_b, vals_a, vals_b, n, key_bits, hist, sorted_keys, sorted_vals, num_sms,
+                               st, launches);
+}
+
+cudaError_t ls_radix_sort_keys(uint64_t *keys_a, uint64_t *keys_b, int64_t n, int key_bits, DBuf &hist,
+                               uint64_t **sorted_keys, int num_sms, cudaStream_t st, int *launches) {
+  return radix_sort_impl<false>(keys_a, keys_b, nullptr, nullptr, n, key_bits, hist, sorted_keys, nullptr, num_sms,
+                                st, launches);
+}

@@ -1,0 +1,90 @@
+"""CPU-only checks: ABI surface, host restatement of the special functions vs scipy,
+oracle vs hand-built pileup cases (SURVEY Appendix A corner cases)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol(built):
+    from longsom_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "longsom_b200.h")).read()
+    declared = set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"ls_ctx"}
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.ABI_SYMBOLS)
+    assert lib.ls_abi_version() == 1
+
+
+def test_no_cuda_device_fails_loudly(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from longsom_b200._lib import LongSomError
+    from longsom_b200.engine import Engine
+    with pytest.raises(LongSomError):
+        Engine(0)
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never route through oracle/ (no CPU fallback)."""
+    bad = []
+    for base in ("longsom_b200", "workflow"):
+        for dp, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".c", ".cpp")):
+                    src = open(os.path.join(dp, f), errors="ignore").read()
+                    if re.search(r"^\s*(import|from)\s+oracle\b", src, re.M) or "liboracle" in src:
+                        bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+@pytest.fixture(scope="module")
+def cephes(built):
+    so = os.path.join(ROOT, "tests", "support", "libcephes_host.so")
+    src = os.path.join(ROOT, "tests", "support", "cephes_host.c")
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", so, src, "-lm"])
+    lib = C.CDLL(so)
+    for f in ("h_lbeta", "h_lgam", "h_Gamma"):
+        getattr(lib, f).restype = C.c_double
+    lib.h_lbeta.argtypes = [C.c_double] * 2
+    lib.h_lgam.argtypes = [C.c_double]
+    lib.h_Gamma.argtypes = [C.c_double]
+    lib.h_betabinom_sf.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p]
+    return lib
+
+
+def test_cephes_restatement_matches_scipy(cephes):
+    import scipy.special as sp
+    rng = np.random.default_rng(0)
+    xs = np.concatenate([rng.uniform(0.01, 200, 5000), rng.uniform(100, 3e5, 5000), np.arange(1, 400, dtype=float)])
+    g = np.array([cephes.h_lgam(x) for x in xs])
+    assert np.array_equal(g, sp.gammaln(xs))
+    xs2 = xs[xs < 171]
+    assert np.array_equal(np.array([cephes.h_Gamma(x) for x in xs2]), sp.gamma(xs2))
+    A = np.concatenate([rng.uniform(0.01, 300, 5000), rng.uniform(1, 2e5, 5000)])
+    B = np.concatenate([rng.uniform(0.01, 300, 5000), rng.uniform(0.01, 2e5, 5000)])
+    g = np.array([cephes.h_lbeta(a, b) for a, b in zip(A, B)])
+    r = sp.betaln(A, B)
+    assert np.max(np.abs(g - r) / np.maximum(1.0, np.abs(r))) < 5e-16
+
+
+def test_host_sf_matches_scipy(cephes):
+    from scipy.stats import betabinom
+    rng = np.random.default_rng(1)
+    n = np.concatenate([rng.integers(1, 300, 1500), rng.integers(300, 20000, 200), rng.integers(20000, 200000, 20)]).astype(np.int32)
+    k = np.minimum((rng.random(len(n)) ** 3 * np.minimum(n, 3000)).astype(np.int32) + rng.integers(0, 3, len(n)).astype(np.int32), n + 1).astype(np.int32)
+    p = np.zeros(len(n))
+    scratch = np.zeros(300000)
+    for a, b in [(0.260288007167716, 173.94711910763732), (0.08354121346569514, 103.47683488327257)]:
+        cephes.h_betabinom_sf(k.ctypes.data, n.ctypes.data, a, b, p.ctypes.data, len(n), scratch.ctypes.data)
+        ref = betabinom.sf(k - 0.1, n, a, b)
+        assert np.max(np.abs(p - ref)) < 1e-14
+        assert np.array_equal(np.round(p, 4), np.round(ref, 4))

@@ -1,0 +1,95 @@
+"""K1 parity: CUDA pileup-count (through the C-ABI) vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+from longsom_b200 import synth
+from longsom_b200.batch import ReadBatch, Windows, make_windows
+from longsom_b200.engine import CountParams
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(got, want):
+    assert got.n_sites == want.n_sites, (got.n_sites, want.n_sites)
+    assert np.array_equal(got.tid, want.tid)
+    assert np.array_equal(got.pos, want.pos)
+    assert np.array_equal(got.ref, want.ref)
+    if not np.array_equal(got.counts, want.counts):
+        bad = np.nonzero((got.counts != want.counts).any(axis=1))[0]
+        i = bad[0]
+        raise AssertionError("counts differ at %d sites; first tid=%d pos=%d\n got=%s\nwant=%s" % (
+            len(bad), got.tid[i], got.pos[i], got.counts[i], want.counts[i]))
+
+
+CASES = [
+    dict(seed=1, contig_lens=[300000, 16600], chrm=True, n_genes=12, n_reads=20000, n_cells=200),
+    dict(seed=2, contig_lens=[120000, 90000, 70000], n_genes=30, n_reads=8000, n_cells=50),
+    dict(seed=3, contig_lens=[200000], n_genes=6, n_reads=30000, n_cells=1000, n_hot_genes=2, hot_fraction=0.9),
+    dict(seed=4, contig_lens=[100000], n_genes=5, n_reads=300, n_cells=20),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("prm", [dict(min_bq=20, min_mq=60), dict(min_bq=30, min_mq=0, min_dp=1, min_cc=1),
+                                 dict(min_bq=0, min_mq=255, min_dp=3, min_cc=2),
+                                 dict(min_bq=20, min_mq=60, min_ac=2)])
+def test_synth_parity(engine, case, prm):
+    import oracle
+    d = synth.generate(**CASES[case])
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    p = CountParams(**prm)
+    got = engine.pileup_count(d.batch, w, p)
+    want, nal = oracle.pileup_count(d.batch, w, p, threads=4)
+    _compare(got, want)
+    assert engine.last_stats["n_aligned"] == nal == d.batch.aligned_bases()
+    if prm.get("min_dp", 5) == 5:
+        assert got.n_sites > 0
+
+
+def test_odd_windows(engine):
+    """Windows that are not on the 50 kb grid, with gaps (the --bed / --bed_out case)."""
+    import oracle
+    d = synth.generate(seed=9, contig_lens=[150000, 80000], n_genes=14, n_reads=12000, n_cells=80)
+    iv = [(0, 1, 777), (0, 777, 40001), (0, 52000, 52001), (0, 60000, 149999), (1, 5, 33333), (1, 40000, 80000)]
+    w = Windows.from_intervals(iv, d.contig_seqs())
+    p = CountParams(min_bq=20, min_mq=60, min_dp=2, min_cc=2)
+    _compare(engine.pileup_count(d.batch, w, p), oracle.pileup_count(d.batch, w, p)[0])
+
+
+def test_depth_cap(engine):
+    """pileup max_depth: small cap so that the drop rule fires."""
+    import oracle
+    d = synth.generate(seed=5, contig_lens=[120000], n_genes=4, n_reads=20000, n_cells=300, n_hot_genes=1,
+                       hot_fraction=0.8)
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    for cap in (50, 500, 3000):
+        p = CountParams(min_bq=20, min_mq=60, max_depth=cap)
+        got = engine.pileup_count(d.batch, w, p)
+        want = oracle.pileup_count(d.batch, w, p)[0]
+        _compare(got, want)
+    uncapped = oracle.pileup_count(d.batch, w, CountParams(min_bq=20, min_mq=60, max_depth=0))[0]
+    assert not np.array_equal(uncapped.counts[:, 0].sum(), want.counts[:, 0].sum())
+
+
+def test_empty_and_tiny(engine):
+    d = synth.generate(seed=6, contig_lens=[60000], n_genes=4, n_reads=200, n_cells=10)
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    p = CountParams(min_bq=20, min_mq=60)
+    empty = d.batch.select(np.zeros(0, np.int64))
+    got = engine.pileup_count(empty, w, p)
+    assert got.n_sites == 0
+    w0 = Windows.from_intervals([], d.contig_seqs())
+    assert engine.pileup_count(d.batch, w0, p).n_sites == 0
+    # everything filtered by MAPQ
+    assert engine.pileup_count(d.batch, w, CountParams(min_bq=20, min_mq=61)).n_sites == 0
+
+
+def test_rejects_bad_input(engine):
+    from longsom_b200._lib import LongSomError
+    d = synth.generate(seed=6, contig_lens=[60000], n_genes=4, n_reads=200, n_cells=10)
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    b = d.batch
+    bad = ReadBatch(b.tid, b.pos[::-1].copy(), b.flag, b.mapq, b.cell, b.cigar_off, b.cigar, b.base_off, b.l_qseq,
+                    b.seq4, b.qual)
+    with pytest.raises(LongSomError):
+        engine.pileup_count(bad, w, CountParams())
