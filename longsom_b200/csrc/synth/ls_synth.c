@@ -183,7 +183,7 @@ static void read_body(const synth_plan *pl, const rhead *h, int mode, int32_t *n
                                  qual[y] = (uint8_t)(q); } ++y; } while (0)
 #define DRAW_Q() (qd = rng_f(&r), qd < 0.90 ? 40 : (qd < 0.95 ? 93 : 2 + (int)rng_int(&r, 28)))
   double qd;
-  for (int i = 0; i < h->clip5; ++i) { int q = DRAW_Q(); PUT_BASE(code_of(BASES[rng_int(&r, 4)]), q); }
+  for (int i = 0; i < h->clip5; ++i) { int q = DRAW_Q(); int cd = code_of(BASES[rng_int(&r, 4)]); PUT_BASE(cd, q); }
   PUSH_OP(4, h->clip5);
   /* walk the transcript interval [tstart, tstart+tlen) exon by exon */
   int e = 0;
@@ -209,7 +209,7 @@ static void read_body(const synth_plan *pl, const rhead *h, int mode, int32_t *n
       } else if (next_ins <= 0 && !first_base && run_m > 0 && t + 2 < stop) {
         int32_t il = 1 + (int32_t)rng_geom(&r, 0.7); if (il > 30) il = 30;
         PUSH_OP(0, run_m); run_m = 0; PUSH_OP(1, il);
-        for (int i = 0; i < il; ++i) { int q = DRAW_Q(); PUT_BASE(code_of(BASES[rng_int(&r, 4)]), q); }
+        for (int i = 0; i < il; ++i) { int q = DRAW_Q(); int cd = code_of(BASES[rng_int(&r, 4)]); PUT_BASE(cd, q); }
         next_ins = rng_geom(&r, p->p_ins);
       }
       --next_del; --next_ins;
@@ -227,7 +227,8 @@ static void read_body(const synth_plan *pl, const rhead *h, int mode, int32_t *n
       }
       if (rng_f(&r) < p->p_mismatch) b = BASES[rng_int(&r, 4)];
       int q = DRAW_Q();
-      PUT_BASE(code_of(b), q);
+      int cd = code_of(b);
+      PUT_BASE(cd, q);
       ++run_m; ++t; first_base = 0;
     }
     if (t < tend) { /* intron */
@@ -238,7 +239,7 @@ static void read_body(const synth_plan *pl, const rhead *h, int mode, int32_t *n
     }
   }
   PUSH_OP(0, run_m);
-  for (int i = 0; i < h->clip3; ++i) { int q = DRAW_Q(); PUT_BASE(code_of(BASES[rng_int(&r, 4)]), q); }
+  for (int i = 0; i < h->clip3; ++i) { int q = DRAW_Q(); int cd = code_of(BASES[rng_int(&r, 4)]); PUT_BASE(cd, q); }
   PUSH_OP(4, h->clip3);
   *n_cigar_o = nc; *lq_o = y;
 #undef PUSH_OP
