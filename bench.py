@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py -- LongSom SNV hot path on B200: aligned bases counted / s (pileup).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  CPU arm (oracle port, all host threads)
+
+Workload (BASELINE.json configs[1]/[2]): whole-transcriptome synthetic PacBio-Kinnex-style
+batch, 5M reads x ~1.5 kb, 5k cells; at N > 1 the SAME batch is sharded by coverage-balanced
+genomic bins across the GPUs (strong scaling, no collective on the data path).
+A "step" is one pass of the hot path over the resident batch: segment build -> (tile, cell)
+sort -> pileup-count kernel -> per-tile site tables in HBM.  `value` is device-resident
+throughput, `e2e` is the same metric through the single C-ABI call ls_pileup_count() with
+pinned HOST buffers (H2D of the batch and D2H of the compacted site table inside the timing).
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "aligned bases counted/sec (pileup)"
+UNIT = "aligned_bases/s"
+PARAMS = dict(min_bq=20, min_mq=60, min_dp=5, min_cc=5, min_ac=0, max_depth=200000)  # workflow values
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ---------------------------------------------------------------------------------------------
+def build_workload(scale, rank, world, sample_bases=None):
+    """Returns dict(batch, windows, owned_aligned, total_reads, ...) for this rank's shard, or, when
+    sample_bases is given, a bounded sample (a run of consecutive windows) for the CPU arm."""
+    from longsom_b200 import synth
+    from longsom_b200.batch import Windows, make_windows
+    from longsom_b200.sharding import balanced_window_shards, reads_for_windows, window_weights
+    cfg = synth.config("C2", scale=scale)
+    t0 = time.time()
+    plan = synth.Plan(**cfg)
+    tid, pos, gend, tlen = plan.headers()
+    iv = make_windows(plan.contig_lens, 50000)
+    wt = np.array([i[0] for i in iv], np.int32)
+    ws = np.array([i[1] for i in iv], np.int32)
+    we = np.array([i[2] for i in iv], np.int32)
+    weights = window_weights(wt, ws, we, tid, pos, tlen)
+    if sample_bases is not None:
+        # densest run of consecutive windows holding ~sample_bases aligned bases
+        cum = np.concatenate([[0.0], np.cumsum(weights)])
+        start = int(np.argmax(weights > 0))
+        end = int(np.searchsorted(cum, cum[start] + sample_bases, side="left"))
+        w_lo, w_hi = start, max(start + 1, min(end, len(iv)))
+    else:
+        w_lo, w_hi = balanced_window_shards(weights, world)[rank]
+    sel = reads_for_windows(wt, ws, we, w_lo, w_hi, tid, pos, gend)
+    batch = plan.materialize(sel)
+    # windows of the shard that can see a read at all (empty windows produce no output)
+    keep = [j for j in range(w_lo, w_hi) if weights[j] > 0 or True]
+    contig = {t: plan.ref[int(plan.contig_off[t]):int(plan.contig_off[t + 1])] for t in range(len(plan.contig_lens))}
+    # drop windows no read overlaps: they cannot emit a site and only cost reference upload
+    if len(sel):
+        rkey_lo = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
+        rkey_hi = (batch.tid.astype(np.int64) << 32) | gend[sel].astype(np.int64)
+        wkey_lo = (wt[w_lo:w_hi].astype(np.int64) << 32) | ws[w_lo:w_hi].astype(np.int64)
+        wkey_hi = (wt[w_lo:w_hi].astype(np.int64) << 32) | we[w_lo:w_hi].astype(np.int64)
+        # a window is covered if some read starts before its end and the running max end passes its start
+        order_max_end = np.maximum.accumulate(rkey_hi)
+        n_before_end = np.searchsorted(rkey_lo, wkey_hi, side="left")
+        covered = (n_before_end > 0) & (order_max_end[np.maximum(n_before_end - 1, 0)] > wkey_lo)
+        keep = [w_lo + j for j in np.nonzero(covered)[0]]
+    windows = Windows.from_intervals([iv[j] for j in keep], contig)
+    # reads "owned" by this shard: start inside [first window start, last window end)
+    if w_hi > w_lo:
+        lo_key = (int(wt[w_lo]) << 32) | (int(ws[w_lo]) if w_lo > 0 and wt[w_lo - 1] == wt[w_lo] else 0)
+        hi_key = (int(wt[w_hi - 1]) << 32) | (int(we[w_hi - 1]) if w_hi < len(iv) and wt[w_hi] == wt[w_hi - 1] else (1 << 31))
+        rk = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
+        owned = (rk >= lo_key) & (rk < hi_key)
+    else:
+        owned = np.zeros(batch.n_reads, bool)
+    op = batch.cigar & 15
+    ln = np.where((op == 0) | (op == 7) | (op == 8), batch.cigar >> 4, 0).astype(np.int64)
+    per_read = np.add.reduceat(ln, batch.cigar_off[:-1].astype(np.int64)) if batch.n_reads else np.zeros(0, np.int64)
+    if batch.n_reads:
+        per_read[batch.cigar_off[1:] == batch.cigar_off[:-1]] = 0
+    owned_aligned = int(per_read[owned].sum())
+    info = dict(cfg=cfg, n_reads_total=plan.n_reads, n_cells=plan.n_cells, windows_total=len(iv),
+                shard=(w_lo, w_hi), gen_s=time.time() - t0, batch_aligned=int(per_read.sum()))
+    plan.close()
+    return dict(batch=batch, windows=windows, owned_aligned=owned_aligned, info=info)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(batch, n_tiles, tile, n_sites):
+    """B_K1 of DESIGN.md: 1.5 B per query base (4-bit base + quality), 4 B per CIGAR op, 19 B per
+    read (pos 4, flag 2, mapq 1, cell 4, two offsets 8), 1 B of reference per tile position,
+    104 B (26 words) per emitted site."""
+    qbases = int(batch.l_qseq.astype(np.int64).sum())
+    return 1.5 * qbases + 4.0 * batch.cigar.shape[0] + 19.0 * batch.n_reads + 1.0 * n_tiles * tile + 104.0 * n_sites
+
+
+def cpu_oracle_rate(sample, threads, steps=1):
+    """Oracle port (plain C, OpenMP over windows) on a bounded sample; aligned bases / s."""
+    import oracle
+    from longsom_b200.engine import CountParams
+    prm = CountParams(**PARAMS)
+    best = None
+    n_sites = 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        sc, nal = oracle.pileup_count(sample["batch"], sample["windows"], prm, threads=threads)
+        dt = time.perf_counter() - t0
+        n_sites = sc.n_sites
+        best = dt if best is None or dt < best else best
+    return sample["owned_aligned"] / best, best, n_sites
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    g.build()
+    cores = os.cpu_count() or 1
+    scale = args.scale
+    # size the per-step sample so that (steps + warmup) steps take ~2 minutes: probe first
+    probe = build_workload(scale, 0, 1, sample_bases=2e7)
+    rate, dt, _ = cpu_oracle_rate(probe, cores)
+    budget = 100.0 / max(1, args.steps + args.warmup)
+    target = float(min(max(rate * min(budget, 25.0), 2e7), 2e9))
+    sample = build_workload(scale, 0, 1, sample_bases=target)
+    for _ in range(args.warmup):
+        cpu_oracle_rate(sample, cores)
+    times = []
+    for _ in range(args.steps):
+        r, dt, ns = cpu_oracle_rate(sample, cores)
+        times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = sample["owned_aligned"] / (ms / 1e3)
+    desc = "%d reads / %d aligned bases (windows %d..%d of the C2 batch)" % (
+        sample["batch"].n_reads, sample["owned_aligned"], sample["info"]["shard"][0], sample["info"]["shard"][1])
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": workload_config(sample["info"], scale, l2="n/a (CPU)"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "oracle port (oracle/pileup_oracle.c, OpenMP over 50 kb windows) of BaseCellCounter.run_interval; "
+                "the reference's own Python/pysam path cannot run here (pysam absent, SURVEY.md 8c)",
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(info, scale, l2):
+    cfg = info["cfg"]
+    return {"workload": "C2 whole-transcriptome synthetic PacBio Kinnex-style batch (BASELINE.json configs[1]); "
+                        "%d reads x ~1.5 kb, %d cells, %d contigs" % (cfg["n_reads"], cfg["n_cells"],
+                                                                      len(cfg["contig_lens"])),
+            "scale": scale, "reads": cfg["n_reads"], "cells": cfg["n_cells"], "genes": cfg["n_genes"],
+            "params": PARAMS, "partition": "coverage-balanced 50 kb-window bins, one shard per GPU, no collective",
+            "l2": l2}
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import __graft_entry__ as g
+    if rank == 0:
+        g.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    else:
+        torch.cuda.set_device(local_rank)
+    from longsom_b200.batch import ReadBatch, SiteCounts
+    from longsom_b200.engine import CountParams, Engine
+    from longsom_b200 import _lib
+    scale = args.scale
+    wl = build_workload(scale, rank, world)
+    batch, windows, info = wl["batch"], wl["windows"], wl["info"]
+    log("[rank %d] shard windows %s: %d reads, %.3f GB batch, generated in %.1f s" % (
+        rank, info["shard"], batch.n_reads, batch.nbytes() / 1e9, info["gen_s"]))
+    prm = CountParams(**PARAMS)
+    eng = Engine(local_rank)
+    tile = _lib.load().ls_pileup_tile_size()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce_max(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    total_units = reduce_sum(float(wl["owned_aligned"]))
+
+    # ---- device-resident steps ---------------------------------------------------------------
+    eng.upload(batch, windows)
+    n_sites = 0
+    for _ in range(args.warmup):
+        n_sites = eng.run(prm)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    t0 = time.perf_counter()
+    ms_count, ms_total, launches = [], [], 0
+    for _ in range(args.steps):
+        n_sites = eng.run(prm)
+        st = eng.last_stats
+        ms_count.append(st["ms_count"])
+        ms_total.append(st["ms_total"])
+        launches += st["count_launches"]
+    barrier()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    dt = reduce_max(dt)
+    ms_per_step = 1e3 * dt / args.steps
+    value = total_units / (dt / args.steps)
+    st = eng.last_stats
+
+    # ---- roofline of the dominant kernel (pileup_count_kernel), live CUDA-event timing ---------
+    peak, peak_src = measured_peak()
+    alg = algorithmic_bytes(batch, st["n_tiles"], tile, n_sites)
+    k_ms = float(np.mean(ms_count))
+    achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "pileup_count_kernel", "kernel_ms": k_ms,
+                "algorithmic_bytes_per_launch": alg, "bytes_per_aligned_base": alg / max(1, info["batch_aligned"]),
+                "peak_source": peak_src, "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None}
+
+    # ---- end to end through the C-ABI with pinned host buffers ---------------------------------
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        return t.pin_memory().numpy() if t.numel() else a
+    pb = ReadBatch(*[pin(getattr(batch, f)) for f in ("tid", "pos", "flag", "mapq", "cell", "cigar_off", "cigar",
+                                                      "base_off", "l_qseq", "seq4", "qual")])
+    from longsom_b200.batch import Windows
+    pw = Windows(*[pin(getattr(windows, f)) for f in ("tid", "start", "end", "ref_off", "ref")])
+    cap = max(int(n_sites), 1)
+    out = SiteCounts(pin(np.zeros(cap, np.int32)), pin(np.zeros(cap, np.int32)), pin(np.zeros(cap, np.uint8)),
+                     pin(np.zeros((cap, 26), np.uint32)))
+    e2e_steps = max(1, min(args.steps, 3))
+    eng.pileup_count_e2e(pb, pw, prm, out)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ns = eng.pileup_count_e2e(pb, pw, prm, out)
+        launches_e2e = eng.last_stats["count_launches"] + 1
+    barrier()
+    dte = reduce_max(time.perf_counter() - t0)
+    h2d = batch.nbytes() + sum(getattr(windows, f).nbytes for f in ("tid", "start", "end", "ref_off", "ref"))
+    d2h = int(ns) * (4 + 4 + 1 + 104)
+    e2e = {"value": total_units / (dte / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(reduce_sum(float(h2d))),
+           "d2h_bytes_per_step": int(reduce_sum(float(d2h))), "steps": e2e_steps, "ms_per_step": 1e3 * dte / e2e_steps,
+           "api": "ls_pileup_count (C-ABI, pinned host buffers)"}
+
+    # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        probe = build_workload(scale, 0, 1, sample_bases=2e7)
+        rate, _, _ = cpu_oracle_rate(probe, cores)
+        sample = build_workload(scale, 0, 1, sample_bases=float(min(max(rate * 15.0, 2e7), 2e9)))
+        rate, dtc, _ = cpu_oracle_rate(sample, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d reads / %d aligned bases (windows %d..%d of the C2 batch), %.1f s" % (
+                   sample["batch"].n_reads, sample["owned_aligned"], sample["info"]["shard"][0],
+                   sample["info"]["shard"][1], dtc)}
+    if rank == 0:
+        res = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u32", "data": "synthetic",
+            "config": workload_config(info, scale, l2="inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
+                                      % (batch.nbytes() / 1e9)),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches),
+            "stats": {"n_segments": st["n_segments"], "n_tiles": st["n_tiles"], "n_sites": int(n_sites),
+                      "n_events": st["n_events"], "ms_segments": st["ms_segments"], "ms_sort": st["ms_sort"],
+                      "ms_count": k_ms, "ms_device_total": float(np.mean(ms_total)), "tile": tile,
+                      "aligned_bases_total": total_units},
+        }
+        print(json.dumps(res), flush=True)
+    eng.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("LS_BENCH_SCALE", "1.0")),
+                    help="fraction of the C2 workload (1.0 = 5M reads); only for local debugging")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world != args.gpus and world > 1:
+        log("warning: WORLD_SIZE=%d but --gpus %d" % (world, args.gpus))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,479 @@
+// K1 pileup-count kernel (second generation) + host orchestration.  Included by ls_pileup.cu.
+//
+// Unit of work: a PART = up to K1_PART_SEGS consecutive (tile, cell)-sorted segments of one
+// tile.  Most tiles are one part; deep tiles (chrM, hotspot genes: >1e5 reads per locus) are
+// split so that no CTA owns more than ~4e5 pileup entries -- the skew that made the first
+// version's tail 70 ms long.  Same-cell runs never straddle parts (a run belongs to the part /
+// chunk that holds its first segment), so NC / CC stay exact and every output word is additive
+// across parts; multi-part tiles add into their HBM slot and the last part to finish applies
+// the reference's gates.
+//
+// Inside a part (CTA of 16 warps, tile accumulators in shared memory):
+//   * a warp grabs a chunk of <= 32 segments; lane j loads segment j's record and read
+//     metadata (one global-latency for the whole chunk instead of one per segment);
+//   * per segment the lanes fetch the next 32 CIGAR ops at once, then walk them warp-uniformly;
+//   * a match op is consumed 128 query bases per step: lane L loads one aligned 32-bit word of
+//     qualities and one 16-bit word of 4-bit bases (vectorised, coalesced), classifies its 4
+//     bases and issues ONE packed shared atomic per visible base (count<<20 | quality);
+//   * the site index is swizzled so that the 4-bases-per-lane pattern is bank-conflict free.
+#pragma once
+
+constexpr int K1_THREADS = 512;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_PART_SEGS = 2048;       // nominal segments per part
+constexpr int K1_MAX_RUN_PACKED = 2039;  // packed counters (12-bit) need: part segs + run extension <= 4095
+constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
+
+static_assert(LS_TILE % 128 == 0 && LS_TILE == K1_THREADS, "epilogue maps one thread to one site");
+
+__host__ __device__ __forceinline__ int swz(int s) { return (s & ~127) | ((s & 3) << 5) | ((s >> 2) & 31); }
+
+struct CountArgs {
+  const uint16_t *flag;
+  const uint32_t *cigar_off, *cigar;
+  const uint64_t *base_off;
+  const int32_t *lq;
+  const uint8_t *seq4, *qual;
+  const Segment *segs;
+  const uint64_t *keys;
+  const uint32_t *vals;
+  const int64_t *slot_tile;
+  const uint32_t *slot_lo;
+  const uint32_t *part_slot, *part_k, *slot_nparts;
+  uint32_t *slot_done;
+  const uint32_t *n_parts;
+  int64_t n_windows;
+  const int32_t *wstart, *wend;
+  const int64_t *wtile_base;
+  const uint64_t *wref_off;
+  const uint8_t *ref;
+  uint32_t *out;    // [n_slots][LS_SITE_WORDS][LS_TILE]
+  uint32_t *acbuf;  // [n_slots][LS_TILE], only when min_ac > 0
+  uint32_t *mask;   // [n_slots][LS_TILE/32]
+  uint32_t *npass;  // [n_slots]
+  unsigned long long *n_events;
+  int cell_bits;
+  uint32_t uncounted_key;
+  int min_bq, min_dp, min_cc, min_ac;
+};
+
+template <bool PACKED>
+struct TileSmemT {
+  uint32_t hist[PACKED ? 16 : 32][LS_TILE];  // PACKED: [cls*2+strand] = cnt<<20|bq ; else [0..15] cnt, [16..31] bq
+  uint32_t dupcc[6][LS_TILE];                // entries whose (cell, class) was already seen at the site
+  uint32_t dupnc[LS_TILE];                   // entries whose cell was already seen at the site (any class)
+  uint32_t acx[LS_TILE];                     // alt entries of visible-but-uncounted reads (--min_ac > 0)
+  uint8_t seen[K1_WARPS][LS_TILE];
+  uint8_t ref[LS_TILE];
+  uint32_t next, npass, ticket;
+};
+
+__device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t tile) {
+  int64_t lo = 0, hi = a.n_windows;  // last w with wtile_base[w] <= tile
+  while (hi - lo > 1) {
+    int64_t m = (lo + hi) >> 1;
+    if (a.wtile_base[m] <= tile)
+      lo = m;
+    else
+      hi = m;
+  }
+  return lo;
+}
+
+template <bool PACKED, bool SEEN>
+__device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint8_t *seen, int sidx, int cls, uint32_t q,
+                                          int strand) {
+  if (PACKED) {
+    atomicAdd(&sm.hist[cls * 2 + strand][sidx], (1u << K1_CNT_SHIFT) | q);
+  } else {
+    atomicAdd(&sm.hist[cls * 2 + strand][sidx], 1u);
+    atomicAdd(&sm.hist[16 + cls * 2 + strand][sidx], q);
+  }
+  if (SEEN) {
+    const uint32_t old = seen[sidx];
+    const uint32_t bit = 1u << cls;
+    if ((old & bit) && cls < 6) atomicAdd(&sm.dupcc[cls][sidx], 1u);
+    if (old) atomicAdd(&sm.dupnc[sidx], 1u);
+    seen[sidx] = (uint8_t)(old | bit);
+  }
+}
+
+template <bool PACKED>
+__device__ __forceinline__ void add_uncounted(TileSmemT<PACKED> &sm, int s, int cls) {
+  // AC pre-gate of BaseCellCounter.py:165-174,221 for reads the counts ignore (no CB / supplementary)
+  const bool alt = (cls == LS_CLASS_D || cls == LS_CLASS_I) || (cls != LS_CLASS_O && class_letter(cls) != sm.ref[s]);
+  if (alt) atomicAdd(&sm.acx[swz(s)], 1u);
+}
+
+// nibble code -> class id, 4 bits per entry: 1->A(0) 2->C(1) 4->G(3) 8->T(2) 15->N(6), else NA(8)
+#define K1_CLASS_LUT 0x6888888288838108ull
+
+struct SegMeta {
+  uint32_t cig, kend, y0, lq;
+  int32_t x0;
+  uint64_t boff;
+  int strand;
+};
+
+// One segment = the part of one read inside the tile; warp-cooperative.
+template <bool PACKED, bool SEEN>
+__device__ __forceinline__ uint32_t process_segment(const CountArgs &a, TileSmemT<PACKED> &sm, uint8_t *seen,
+                                                    const SegMeta m, int32_t tile_start, int32_t tile_end,
+                                                    bool counted, int lane) {
+  const uint8_t *__restrict__ qual = a.qual + m.boff;
+  const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
+  const int strand = m.strand;
+  const uint32_t lq = m.lq;
+  int32_t x = m.x0;
+  uint32_t y = m.y0;
+  uint32_t nev = 0;
+  uint32_t k = m.cig;
+  while (k < m.kend && x < tile_end) {
+    // the next (up to) 32 ops in one coalesced load; op k+1 alongside for the indel peek
+    const uint32_t kk = k + (uint32_t)lane;
+    const uint32_t c_l = kk < m.kend ? a.cigar[kk] : 0xfu;
+    const uint32_t c_n = kk + 1 < m.kend ? a.cigar[kk + 1] : 0xfu;
+    const int nwin = (int)((m.kend - k) < 32u ? (m.kend - k) : 32u);
+    for (int t = 0; t < nwin && x < tile_end; ++t) {
+      const uint32_t c = __shfl_sync(0xffffffffu, c_l, t);
+      const uint32_t cn = __shfl_sync(0xffffffffu, c_n, t);
+      const uint32_t op = c & 15u;
+      const int32_t len = (int32_t)(c >> 4);
+      const bool match = op_is_match(op);
+      if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
+        const int32_t last = x + len - 1;
+        int ind = 0;
+        if (last >= tile_start && last < tile_end) {
+          const uint32_t op2 = cn & 15u;
+          if (op2 == OP_D && op != OP_D)
+            ind = -1;
+          else if (op2 == OP_I)
+            ind = 1;
+          else if (op2 == OP_P)
+            ind = indel_after(a.cigar, k + (uint32_t)t, m.kend, op);
+        }
+        if (op == OP_N) {
+          if (ind != 0 && lane == 0) {
+            const uint32_t q = y < lq ? qual[y] : 0u;
+            if ((int)q >= a.min_bq) {
+              const int cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
+              const int s = last - tile_start;
+              if (counted) {
+                add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, q, strand);
+                ++nev;
+              } else {
+                add_uncounted<PACKED>(sm, s, cls);
+              }
+            }
+          }
+        } else if (!match) {  // deletion: every column carries the quality of the next query base
+          const int32_t lo = x > tile_start ? x : tile_start;
+          const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
+          const uint32_t q = y < lq ? qual[y] : 0u;
+          if ((int)q >= a.min_bq) {
+            for (int32_t p = lo + lane; p < hi; p += 32) {
+              const int cls = (p == last && ind != 0) ? (ind < 0 ? LS_CLASS_D : LS_CLASS_I) : LS_CLASS_O;
+              const int s = p - tile_start;
+              if (counted) {
+                add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, q, strand);
+                ++nev;
+              } else {
+                add_uncounted<PACKED>(sm, s, cls);
+              }
+            }
+          }
+        } else {
+          const int32_t lo = x > tile_start ? x : tile_start;
+          const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
+          const uint32_t ya = y + (uint32_t)(lo - x), yb = y + (uint32_t)(hi - x);  // query range inside the tile
+          const uint32_t ybl = yb < lq ? yb : lq;                                    // bases that exist
+          const int sbase = lo - tile_start;
+          const uint32_t ylast = (ind != 0) ? (y + (uint32_t)len - 1u) : 0xffffffffu;
+          for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < ybl; g += 128u) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
+            const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t qp = g + (uint32_t)j;
+              const uint32_t q = (w >> (8 * j)) & 255u;
+              if (qp >= ya && qp < ybl && (int)q >= a.min_bq) {
+                const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
+                int cls = (int)((K1_CLASS_LUT >> (4 * code)) & 15ull);
+                if (qp == ylast) cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
+                if (cls != LS_CLASS_NA) {
+                  const int s = sbase + (int)(qp - ya);
+                  if (counted) {
+                    add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, q, strand);
+                    ++nev;
+                  } else {
+                    add_uncounted<PACKED>(sm, s, cls);
+                  }
+                }
+              }
+            }
+          }
+          // query positions past the stored sequence (malformed record): base 'N', quality 0
+          if (yb > lq && a.min_bq <= 0) {
+            for (uint32_t qp = (ya > lq ? ya : lq) + (uint32_t)lane; qp < yb; qp += 32u) {
+              const int cls = (qp == ylast) ? (ind < 0 ? LS_CLASS_D : LS_CLASS_I) : LS_CLASS_N;
+              const int s = sbase + (int)(qp - ya);
+              if (counted) {
+                add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, 0u, strand);
+                ++nev;
+              } else {
+                add_uncounted<PACKED>(sm, s, cls);
+              }
+            }
+          }
+        }
+        if (SEEN) __syncwarp();
+      }
+      if (match) {
+        x += len;
+        y += (uint32_t)len;
+      } else if (op == OP_D || op == OP_N) {
+        x += len;
+      } else if (op == OP_I || op == OP_S) {
+        y += (uint32_t)len;
+      }
+    }
+    k += (uint32_t)nwin;
+  }
+  return nev;
+}
+
+__device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
+  const Segment sg = a.segs[a.vals[i]];
+  SegMeta m;
+  m.cig = sg.cig;
+  m.x0 = sg.x0;
+  m.y0 = sg.y0;
+  m.kend = a.cigar_off[sg.read + 1];
+  m.boff = a.base_off[sg.read];
+  m.lq = (uint32_t)a.lq[sg.read];
+  m.strand = (a.flag[sg.read] & LS_FLAG_REVERSE) ? 1 : 0;
+  return m;
+}
+
+__device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
+  SegMeta r;
+  r.cig = __shfl_sync(0xffffffffu, m.cig, j);
+  r.kend = __shfl_sync(0xffffffffu, m.kend, j);
+  r.y0 = __shfl_sync(0xffffffffu, m.y0, j);
+  r.lq = __shfl_sync(0xffffffffu, m.lq, j);
+  r.x0 = __shfl_sync(0xffffffffu, m.x0, j);
+  r.boff = __shfl_sync(0xffffffffu, m.boff, j);
+  r.strand = __shfl_sync(0xffffffffu, m.strand, j);
+  return r;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(K1_THREADS, 2) pileup_count_kernel(CountArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
+  const uint32_t part = blockIdx.x;
+  if (part >= *a.n_parts) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t slot = a.part_slot[part];
+  const uint32_t pk = a.part_k[part];
+  const uint32_t nparts = a.slot_nparts[slot];
+  const int64_t tile = a.slot_tile[slot];
+  const uint32_t slot_lo = a.slot_lo[slot], slot_hi = a.slot_lo[slot + 1];
+  const uint32_t my_lo = slot_lo + pk * K1_PART_SEGS;
+  const uint32_t my_hi = (my_lo + K1_PART_SEGS) < slot_hi ? (my_lo + K1_PART_SEGS) : slot_hi;
+  const int64_t w = window_of_tile(a, tile);
+  const int32_t tile_start = a.wstart[w] + (int32_t)(tile - a.wtile_base[w]) * LS_TILE;
+  const int32_t tile_end = (tile_start + LS_TILE) < a.wend[w] ? (tile_start + LS_TILE) : a.wend[w];
+  const uint64_t ref_base = a.wref_off[w] + (uint64_t)(tile_start - a.wstart[w]);
+
+  {  // zero the accumulators, stage the reference bases
+    uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
+    constexpr int NZ = ((PACKED ? 16 : 32) + 6 + 1 + 1) * LS_TILE;
+    for (int i = threadIdx.x; i < NZ; i += K1_THREADS) z[i] = 0u;
+    for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS)
+      sm.ref[i] = (tile_start + i < tile_end) ? upper_ascii(a.ref[ref_base + i]) : (uint8_t)'N';
+    if (threadIdx.x == 0) {
+      sm.next = 0;
+      sm.npass = 0;
+      sm.ticket = 0;
+    }
+  }
+  __syncthreads();
+
+  const uint64_t cmask = (1ull << a.cell_bits) - 1ull;
+  const uint64_t unc = (uint64_t)a.uncounted_key;
+  uint8_t *seen = sm.seen[warp];
+  uint32_t nev = 0;
+  const uint32_t nmine = my_hi - my_lo;
+  uint32_t chunk = (nmine + K1_WARPS - 1) / K1_WARPS;
+  chunk = chunk < 4u ? 4u : (chunk > 32u ? 32u : chunk);
+  for (;;) {
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(&sm.next, chunk);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g >= nmine) break;
+    const uint32_t ca = my_lo + g;
+    const uint32_t cb = (ca + chunk) < my_hi ? (ca + chunk) : my_hi;
+    const int n = (int)(cb - ca);
+    // lane j < n owns segment ca + j: key, "starts a run" flag, record + read metadata
+    uint64_t ck = ~0ull;
+    bool start = false;
+    SegMeta mm = {};
+    if (lane < n) {
+      const uint32_t i = ca + (uint32_t)lane;
+      ck = a.keys[i] & cmask;
+      start = (i == slot_lo) || ck == unc || (a.keys[i - 1] & cmask) != ck;
+      mm = load_meta(a, i);
+    }
+    const uint32_t startmask = __ballot_sync(0xffffffffu, start);
+    uint32_t rem = startmask;
+    while (rem) {
+      const int j0 = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const int j1 = rem ? (__ffs(rem) - 1) : n;
+      const uint64_t rk = __shfl_sync(0xffffffffu, ck, j0);
+      const bool counted = rk != unc;
+      // a run that reaches the end of the chunk continues into the following segments of the tile
+      uint32_t ext = 0;
+      if (j1 == n && counted) {
+        while (cb + ext < slot_hi && (a.keys[cb + ext] & cmask) == rk) ++ext;
+      }
+      const uint32_t runlen = (uint32_t)(j1 - j0) + ext;
+      if (runlen == 1) {
+        nev += process_segment<PACKED, false>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, counted, lane);
+      } else {
+        uint32_t *s4 = reinterpret_cast<uint32_t *>(seen);
+        for (int q = lane; q < LS_TILE / 4; q += 32) s4[q] = 0u;
+        __syncwarp();
+        for (int j = j0; j < j1; ++j)
+          nev += process_segment<PACKED, true>(a, sm, seen, shfl_meta(mm, j), tile_start, tile_end, true, lane);
+        for (uint32_t e = 0; e < ext; ++e)
+          nev += process_segment<PACKED, true>(a, sm, seen, load_meta(a, cb + e), tile_start, tile_end, true, lane);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- site epilogue: gates of BaseCellCounter.py:211,220-222,282,294 -------------------
+  uint32_t *out = a.out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
+  const int s = threadIdx.x;  // one site per thread
+  const int sidx = swz(s);
+  uint32_t f[8], r[8], bq[6];
+  uint32_t dp = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (PACKED) {
+      const uint32_t hf = sm.hist[k * 2][sidx], hr = sm.hist[k * 2 + 1][sidx];
+      f[k] = hf >> K1_CNT_SHIFT;
+      r[k] = hr >> K1_CNT_SHIFT;
+      if (k < 6) bq[k] = (hf & ((1u << K1_CNT_SHIFT) - 1u)) + (hr & ((1u << K1_CNT_SHIFT) - 1u));
+    } else {
+      f[k] = sm.hist[k * 2][sidx];
+      r[k] = sm.hist[k * 2 + 1][sidx];
+      if (k < 6) bq[k] = sm.hist[16 + k * 2][sidx] + sm.hist[16 + k * 2 + 1][sidx];
+    }
+    dp += f[k] + r[k];
+  }
+  const uint8_t rb = sm.ref[s];
+  uint32_t nc = dp - sm.dupnc[sidx];
+  uint32_t cc[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) cc[k] = f[k] + r[k] - sm.dupcc[k][sidx];
+  uint32_t ac = 0;
+  if (a.min_ac > 0) {
+    ac = sm.acx[sidx] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
+    const int base_cls[5] = {LS_CLASS_A, LS_CLASS_C, LS_CLASS_T, LS_CLASS_G, LS_CLASS_N};
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (class_letter(base_cls[j]) != rb) ac += f[base_cls[j]] + r[base_cls[j]];
+  }
+  bool last_part = true;
+  if (nparts > 1) {
+    // additive merge of this part's words into the tile's HBM slot; the last part applies the gates
+    if (dp) atomicAdd(&out[LS_SITE_DP * LS_TILE + s], dp);
+    if (nc) atomicAdd(&out[LS_SITE_NC * LS_TILE + s], nc);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (cc[k]) atomicAdd(&out[(LS_SITE_CC + k) * LS_TILE + s], cc[k]);
+      if (f[k]) atomicAdd(&out[(LS_SITE_BCF + k) * LS_TILE + s], f[k]);
+      if (r[k]) atomicAdd(&out[(LS_SITE_BCR + k) * LS_TILE + s], r[k]);
+      if (bq[k]) atomicAdd(&out[(LS_SITE_BQ + k) * LS_TILE + s], bq[k]);
+    }
+    if (a.min_ac > 0 && ac) atomicAdd(&a.acbuf[(size_t)slot * LS_TILE + s], ac);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) sm.ticket = atomicAdd(&a.slot_done[slot], 1u);
+    __syncthreads();
+    last_part = sm.ticket == nparts - 1;
+    if (last_part) {
+      __threadfence();
+      dp = __ldcg(&out[LS_SITE_DP * LS_TILE + s]);
+      nc = __ldcg(&out[LS_SITE_NC * LS_TILE + s]);
+      if (a.min_ac > 0) ac = __ldcg(&a.acbuf[(size_t)slot * LS_TILE + s]);
+    }
+  }
+  if (last_part) {
+    bool pass = (tile_start + s < tile_end) && rb != 'N' && dp > 0 && (int)dp >= a.min_dp && (int)nc >= a.min_cc;
+    if (pass && a.min_ac > 0) pass = (int)ac >= a.min_ac;
+    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) {
+      a.mask[(size_t)slot * (LS_TILE / 32) + (s >> 5)] = bal;
+      if (bal) atomicAdd(&sm.npass, (uint32_t)__popc(bal));
+    }
+    if (pass && nparts == 1) {
+      out[LS_SITE_DP * LS_TILE + s] = dp;
+      out[LS_SITE_NC * LS_TILE + s] = nc;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        out[(LS_SITE_CC + k) * LS_TILE + s] = cc[k];
+        out[(LS_SITE_BCF + k) * LS_TILE + s] = f[k];
+        out[(LS_SITE_BCR + k) * LS_TILE + s] = r[k];
+        out[(LS_SITE_BQ + k) * LS_TILE + s] = bq[k];
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) nev += __shfl_xor_sync(0xffffffffu, nev, o);
+  if (lane == 0 && nev) atomicAdd(a.n_events, (unsigned long long)nev);
+  __syncthreads();
+  if (last_part && threadIdx.x == 0) a.npass[slot] = sm.npass;
+}
+
+// One CTA per slot: split the slot into parts, register them, and zero the HBM slot of
+// multi-part tiles (their parts merge with atomics).
+__global__ void __launch_bounds__(128) part_build_kernel(const uint32_t *__restrict__ slot_lo, int64_t n_slots,
+                                                         uint32_t *__restrict__ part_slot, uint32_t *__restrict__ part_k,
+                                                         uint32_t *__restrict__ slot_nparts, uint32_t *__restrict__ slot_done,
+                                                         uint32_t *__restrict__ n_parts, uint32_t *__restrict__ out,
+                                                         uint32_t *__restrict__ acbuf) {
+  const int64_t slot = blockIdx.x;
+  if (slot >= n_slots) return;
+  const uint32_t n = slot_lo[slot + 1] - slot_lo[slot];
+  const uint32_t np = n == 0 ? 1u : (n + K1_PART_SEGS - 1) / K1_PART_SEGS;
+  __shared__ uint32_t base;
+  if (threadIdx.x == 0) {
+    base = atomicAdd(n_parts, np);
+    slot_nparts[slot] = np;
+    slot_done[slot] = 0;
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k < np; k += blockDim.x) {
+    part_slot[base + k] = (uint32_t)slot;
+    part_k[base + k] = k;
+  }
+  if (np > 1) {
+    uint32_t *o = out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
+    for (int i = threadIdx.x; i < LS_SITE_WORDS * LS_TILE; i += blockDim.x) o[i] = 0u;
+    if (acbuf)
+      for (int i = threadIdx.x; i < LS_TILE; i += blockDim.x) acbuf[(size_t)slot * LS_TILE + i] = 0u;
+  }
+}
+
+// any same-(tile, cell) run longer than K1_MAX_RUN_PACKED segments? (then the 12-bit packed counters could overflow)
+__global__ void __launch_bounds__(256) long_run_kernel(const uint64_t *__restrict__ keys, int64_t n, uint64_t cmask,
+                                                       uint64_t unc, uint32_t *__restrict__ flag) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < K1_MAX_RUN_PACKED || i >= n) return;
+  const uint64_t k = keys[i];
+  if ((k & cmask) != unc && keys[i - K1_MAX_RUN_PACKED] == k) *flag = 1u;
+}

@@ -24,9 +24,6 @@
 #ifndef LS_TILE
 #define LS_TILE 512
 #endif
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
-constexpr int K1_CHUNK = 4;  // segments grabbed per warp per scheduling step
 
 struct SegArgs {
   int64_t n_reads;
@@ -208,273 +205,7 @@ __global__ void __launch_bounds__(256) slot_fill_kernel(const uint64_t *__restri
   }
 }
 
-// ------------------------------------------------------------------------------------------
-struct CountArgs {
-  const int32_t *pos;
-  const uint16_t *flag;
-  const uint32_t *cigar_off, *cigar;
-  const uint64_t *base_off;
-  const int32_t *lq;
-  const uint8_t *seq4, *qual;
-  const Segment *segs;
-  const uint64_t *keys;
-  const uint32_t *vals;
-  const int64_t *slot_tile;
-  const uint32_t *slot_lo;
-  int64_t n_windows;
-  const int32_t *wstart, *wend;
-  const int64_t *wtile_base;
-  const uint64_t *wref_off;
-  const uint8_t *ref;
-  uint32_t *out;    // [n_slots][LS_SITE_WORDS][LS_TILE]
-  uint32_t *mask;   // [n_slots][LS_TILE/32]
-  uint32_t *npass;  // [n_slots]
-  unsigned long long *n_events;
-  int cell_bits;
-  uint32_t uncounted_key;
-  int min_bq, min_dp, min_cc, min_ac;
-};
-
-struct TileSmem {
-  uint32_t cnt[16][LS_TILE];   // [class*2 + strand] reads
-  uint32_t bq[6][LS_TILE];     // base-quality sums of the printed classes A,C,T,G,I,D
-  uint32_t dupcc[6][LS_TILE];  // entries whose (cell, class) was already seen at the site
-  uint32_t dupnc[LS_TILE];     // entries whose cell was already seen at the site (any class)
-  uint32_t acx[LS_TILE];       // alt entries of visible-but-uncounted reads (only for --min_ac > 0)
-  uint8_t seen[K1_WARPS][LS_TILE];
-  uint8_t ref[LS_TILE];
-  uint32_t next;
-  uint32_t npass;
-};
-
-__device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t tile) {
-  int64_t lo = 0, hi = a.n_windows;  // last w with wtile_base[w] <= tile
-  while (hi - lo > 1) {
-    int64_t m = (lo + hi) >> 1;
-    if (a.wtile_base[m] <= tile)
-      lo = m;
-    else
-      hi = m;
-  }
-  return lo;
-}
-
-template <bool SEEN>
-__device__ __forceinline__ void add_entry(TileSmem &sm, uint8_t *seen, int s, int cls, uint32_t q, int strand) {
-  atomicAdd(&sm.cnt[cls * 2 + strand][s], 1u);
-  if (cls < 6) atomicAdd(&sm.bq[cls][s], q);
-  if (SEEN) {
-    uint32_t old = seen[s];
-    uint32_t bit = 1u << cls;
-    if ((old & bit) && cls < 6) atomicAdd(&sm.dupcc[cls][s], 1u);
-    if (old) atomicAdd(&sm.dupnc[s], 1u);
-    seen[s] = (uint8_t)(old | bit);
-  }
-}
-
-// One segment = the part of one read inside the tile.  Warp-cooperative: the CIGAR walk is
-// warp-uniform, lanes stride consecutive reference positions of the current op.
-template <bool SEEN>
-__device__ __forceinline__ uint32_t process_segment(const CountArgs &a, TileSmem &sm, uint8_t *seen,
-                                                    const Segment seg, int32_t tile_start, int32_t tile_end,
-                                                    bool counted, int lane) {
-  const uint32_t r = seg.read;
-  const uint32_t kend = a.cigar_off[r + 1];
-  const uint64_t boff = a.base_off[r];
-  const uint32_t lq = (uint32_t)a.lq[r];
-  const int strand = (a.flag[r] & LS_FLAG_REVERSE) ? 1 : 0;
-  const uint8_t *__restrict__ qual = a.qual + boff;
-  const uint8_t *__restrict__ seq4 = a.seq4 + (boff >> 1);
-  int32_t x = seg.x0;
-  uint32_t y = seg.y0;
-  uint32_t nev = 0;
-  for (uint32_t k = seg.cig; k < kend && x < tile_end; ++k) {
-    const uint32_t c = a.cigar[k];
-    const uint32_t op = c & 15u;
-    const int32_t len = (int32_t)(c >> 4);
-    const bool match = op_is_match(op);
-    if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
-      const int32_t last = x + len - 1;
-      int ind = 0;
-      if (last >= tile_start && last < tile_end) ind = indel_after(a.cigar, k, kend, op);
-      if (op == OP_N) {
-        if (ind != 0 && lane == 0) {
-          uint32_t q = y < lq ? qual[y] : 0u;
-          if ((int)q >= a.min_bq) {
-            int cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-            int s = last - tile_start;
-            if (counted) {
-              add_entry<SEEN>(sm, seen, s, cls, q, strand);
-              ++nev;
-            } else {
-              atomicAdd(&sm.acx[s], 1u);
-            }
-          }
-        }
-      } else {
-        const int32_t lo = x > tile_start ? x : tile_start;
-        const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
-        for (int32_t p = lo + lane; p < hi; p += 32) {
-          const uint32_t qpos = match ? y + (uint32_t)(p - x) : y;
-          const uint32_t q = qpos < lq ? qual[qpos] : 0u;
-          if ((int)q >= a.min_bq) {
-            int cls;
-            if (p == last && ind != 0) {
-              cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-            } else if (match) {
-              uint32_t code = 15u;
-              if (qpos < lq) {
-                uint32_t b = seq4[qpos >> 1];
-                code = (qpos & 1u) ? (b & 15u) : (b >> 4);
-              }
-              cls = class_of_code(code);
-            } else {
-              cls = LS_CLASS_O;
-            }
-            if (cls != LS_CLASS_NA) {
-              const int s = p - tile_start;
-              if (counted) {
-                add_entry<SEEN>(sm, seen, s, cls, q, strand);
-                ++nev;
-              } else {
-                // AC pre-gate of BaseCellCounter.py:165-174 for reads the counts ignore
-                bool alt = (cls == LS_CLASS_D || cls == LS_CLASS_I) ||
-                           (cls != LS_CLASS_O && class_letter(cls) != sm.ref[s]);
-                if (alt) atomicAdd(&sm.acx[s], 1u);
-              }
-            }
-          }
-        }
-      }
-      if (SEEN) __syncwarp();
-    }
-    if (match) {
-      x += len;
-      y += (uint32_t)len;
-    } else if (op == OP_D || op == OP_N) {
-      x += len;
-    } else if (op == OP_I || op == OP_S) {
-      y += (uint32_t)len;
-    }
-  }
-  return nev;
-}
-
-__global__ void __launch_bounds__(K1_THREADS) pileup_count_kernel(CountArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TileSmem &sm = *reinterpret_cast<TileSmem *>(smem_raw);
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t slot = blockIdx.x;
-  const int64_t tile = a.slot_tile[slot];
-  const uint32_t seg_lo = a.slot_lo[slot], seg_hi = a.slot_lo[slot + 1];
-  const int64_t w = window_of_tile(a, tile);
-  const int32_t tile_start = a.wstart[w] + (int32_t)(tile - a.wtile_base[w]) * LS_TILE;
-  const int32_t tile_end = (tile_start + LS_TILE) < a.wend[w] ? (tile_start + LS_TILE) : a.wend[w];
-  const uint64_t ref_base = a.wref_off[w] + (uint64_t)(tile_start - a.wstart[w]);
-
-  {  // zero the accumulators, stage the reference bases
-    uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
-    constexpr int NZ = (int)((sizeof(uint32_t) * (16 + 6 + 6 + 1 + 1) * LS_TILE) / 4);
-    for (int i = threadIdx.x; i < NZ; i += K1_THREADS) z[i] = 0u;
-    for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS)
-      sm.ref[i] = (tile_start + i < tile_end) ? upper_ascii(a.ref[ref_base + i]) : (uint8_t)'N';
-    if (threadIdx.x == 0) {
-      sm.next = 0;
-      sm.npass = 0;
-    }
-  }
-  __syncthreads();
-
-  const uint64_t cmask = (1ull << a.cell_bits) - 1ull;
-  uint8_t *seen = sm.seen[warp];
-  uint32_t nev = 0;
-  for (;;) {
-    uint32_t g = 0;
-    if (lane == 0) g = atomicAdd(&sm.next, (uint32_t)K1_CHUNK);
-    g = __shfl_sync(0xffffffffu, g, 0);
-    uint32_t aidx = seg_lo + g;
-    if (aidx >= seg_hi) break;
-    const uint32_t b = (aidx + K1_CHUNK) < seg_hi ? (aidx + K1_CHUNK) : seg_hi;
-    uint32_t i = aidx;
-    if (i > seg_lo) {  // leading segments that continue a run owned by the previous chunk
-      const uint64_t cprev = a.keys[i - 1] & cmask;
-      if (cprev != (uint64_t)a.uncounted_key)
-        while (i < seg_hi && (a.keys[i] & cmask) == cprev) ++i;
-    }
-    while (i < b) {
-      const uint64_t ck = a.keys[i] & cmask;
-      uint32_t e = i + 1;
-      const bool counted = ck != (uint64_t)a.uncounted_key;
-      if (counted) {
-        while (e < seg_hi && (a.keys[e] & cmask) == ck) ++e;
-      }
-      if (e - i == 1 || !counted) {
-        const Segment sg = a.segs[a.vals[i]];
-        nev += process_segment<false>(a, sm, seen, sg, tile_start, tile_end, counted, lane);
-      } else {
-        uint32_t *s4 = reinterpret_cast<uint32_t *>(seen);
-        for (int j = lane; j < LS_TILE / 4; j += 32) s4[j] = 0u;
-        __syncwarp();
-        for (uint32_t j = i; j < e; ++j) {
-          const Segment sg = a.segs[a.vals[j]];
-          nev += process_segment<true>(a, sm, seen, sg, tile_start, tile_end, true, lane);
-        }
-      }
-      i = e;
-    }
-  }
-  __syncthreads();
-
-  // ---- site epilogue: gates of BaseCellCounter.py:211,220-222,282,294 -------------------
-  uint32_t *out = a.out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
-  uint32_t my_pass = 0;
-  for (int s = threadIdx.x; s < LS_TILE; s += K1_THREADS) {
-    uint32_t f[8], r[8];
-    uint32_t dp = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      f[k] = sm.cnt[k * 2][s];
-      r[k] = sm.cnt[k * 2 + 1][s];
-      dp += f[k] + r[k];
-    }
-    const uint8_t rb = sm.ref[s];
-    const uint32_t nc = dp - sm.dupnc[s];
-    bool pass = (tile_start + s < tile_end) && rb != 'N' && dp > 0 && (int)dp >= a.min_dp && (int)nc >= a.min_cc;
-    if (pass && a.min_ac > 0) {
-      uint32_t ac = sm.acx[s] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
-      const int base_cls[5] = {LS_CLASS_A, LS_CLASS_C, LS_CLASS_T, LS_CLASS_G, LS_CLASS_N};
-#pragma unroll
-      for (int j = 0; j < 5; ++j)
-        if (class_letter(base_cls[j]) != rb) ac += f[base_cls[j]] + r[base_cls[j]];
-      pass = (int)ac >= a.min_ac;
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) a.mask[(size_t)slot * (LS_TILE / 32) + (s >> 5)] = bal;
-    if (pass) {
-      ++my_pass;
-      out[LS_SITE_DP * LS_TILE + s] = dp;
-      out[LS_SITE_NC * LS_TILE + s] = nc;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        out[(LS_SITE_CC + k) * LS_TILE + s] = f[k] + r[k] - sm.dupcc[k][s];
-        out[(LS_SITE_BCF + k) * LS_TILE + s] = f[k];
-        out[(LS_SITE_BCR + k) * LS_TILE + s] = r[k];
-        out[(LS_SITE_BQ + k) * LS_TILE + s] = sm.bq[k][s];
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    my_pass += __shfl_xor_sync(0xffffffffu, my_pass, o);
-    nev += __shfl_xor_sync(0xffffffffu, nev, o);
-  }
-  if (lane == 0) {
-    atomicAdd(&sm.npass, my_pass);
-    if (nev) atomicAdd(a.n_events, (unsigned long long)nev);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) a.npass[slot] = sm.npass;
-}
+#include "ls_count.cuh"
 
 // ---- compaction of passing sites (fetch path) -----------------------------------------------
 struct CompactArgs {
@@ -593,9 +324,11 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   unsigned long long *d_events = d_aligned + 1;
   uint64_t *d_nseg_total = reinterpret_cast<uint64_t *>(d_aligned + 2);
   uint64_t *d_nslot_total = reinterpret_cast<uint64_t *>(d_aligned + 3);
+  uint32_t *d_nparts = reinterpret_cast<uint32_t *>(d_aligned + 4);
+  uint32_t *d_longrun = reinterpret_cast<uint32_t *>(d_aligned + 5);
 
   LS_CK(cudaEventRecord(ctx->ev[0], st));
-  uint64_t h_tot[4] = {0, 0, 0, 0};
+  uint64_t h_tot[6] = {0, 0, 0, 0, 0, 0};
   if (n > 0 && ctx->n_windows > 0) {
     LS_CK(ctx->nseg.ensure((size_t)n * 4));
     LS_CK(ctx->seg_off.ensure((size_t)n * 4));
@@ -662,9 +395,16 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     LS_CK(ls_scan_exclusive_u32(ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), nseg, d_nslot_total,
                                 ctx->scan_tmp, st));
     launches += 3;
-    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
+    {
+      const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
+      long_run_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, cmask,
+                                                                      (uint64_t)(uint32_t)(ctx->max_cell + 1), d_longrun);
+      ++launches;
+    }
+    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 48, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
     n_slots = (int64_t)h_tot[3];
+    const bool packed = (h_tot[5] & 0xffffffffull) == 0;
     LS_CK(ctx->slot_tile.ensure((size_t)n_slots * 8));
     LS_CK(ctx->slot_lo.ensure((size_t)(n_slots + 1) * 4));
     slot_fill_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(
@@ -677,8 +417,24 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     LS_CK(ctx->slot_mask.ensure((size_t)n_slots * (LS_TILE / 32) * 4));
     LS_CK(ctx->slot_npass.ensure((size_t)n_slots * 4));
     LS_CK(ctx->slot_off.ensure((size_t)n_slots * 4));
+    const int64_t max_parts = n_slots + nseg / K1_PART_SEGS + 1;
+    LS_CK(ctx->part_slot.ensure((size_t)max_parts * 4));
+    LS_CK(ctx->part_k.ensure((size_t)max_parts * 4));
+    LS_CK(ctx->slot_nparts.ensure((size_t)n_slots * 4));
+    LS_CK(ctx->slot_done.ensure((size_t)n_slots * 4));
+    if (params->min_ac > 0) LS_CK(ctx->acbuf.ensure((size_t)n_slots * LS_TILE * 4));
+    part_build_kernel<<<(unsigned)n_slots, 128, 0, st>>>(
+        ctx->slot_lo.as<uint32_t>(), n_slots, ctx->part_slot.as<uint32_t>(), ctx->part_k.as<uint32_t>(),
+        ctx->slot_nparts.as<uint32_t>(), ctx->slot_done.as<uint32_t>(), d_nparts, ctx->slot_out.as<uint32_t>(),
+        params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr);
+    ++launches;
     CountArgs ca;
-    ca.pos = ctx->pos.as<int32_t>();
+    ca.part_slot = ctx->part_slot.as<uint32_t>();
+    ca.part_k = ctx->part_k.as<uint32_t>();
+    ca.slot_nparts = ctx->slot_nparts.as<uint32_t>();
+    ca.slot_done = ctx->slot_done.as<uint32_t>();
+    ca.n_parts = d_nparts;
+    ca.acbuf = params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr;
     ca.flag = ctx->flag.as<uint16_t>();
     ca.cigar_off = ctx->cigar_off.as<uint32_t>();
     ca.cigar = ctx->cigar.as<uint32_t>();
@@ -708,11 +464,17 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.min_cc = params->min_cc;
     ca.min_ac = params->min_ac;
     if (!ctx->k1_attr_set) {
-      LS_CK(cudaFuncSetAttribute(pileup_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(TileSmem)));
+      LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(TileSmemT<true>)));
+      LS_CK(cudaFuncSetAttribute(pileup_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(TileSmemT<false>)));
       ctx->k1_attr_set = true;
     }
-    pileup_count_kernel<<<(unsigned)n_slots, K1_THREADS, sizeof(TileSmem), st>>>(ca);
+    // 12-bit packed counters unless some cell has > K1_MAX_RUN_PACKED reads in one tile
+    if (packed)
+      pileup_count_kernel<true><<<(unsigned)max_parts, K1_THREADS, sizeof(TileSmemT<true>), st>>>(ca);
+    else
+      pileup_count_kernel<false><<<(unsigned)max_parts, K1_THREADS, sizeof(TileSmemT<false>), st>>>(ca);
     ++launches;
     LS_CK(cudaGetLastError());
     LS_CK(cudaEventRecord(ctx->ev[3], st));

@@ -181,8 +181,8 @@ static void read_body(const synth_plan *pl, const rhead *h, int mode, int32_t *n
 #define PUSH_OP(op, len) do { if ((len) > 0) { if (mode) cigar[nc] = ((uint32_t)(len) << 4) | (op); ++nc; } } while (0)
 #define PUT_BASE(code, q) do { if (mode) { if (y & 1) seq4[y >> 1] |= (uint8_t)(code); else seq4[y >> 1] = (uint8_t)((code) << 4); \
                                  qual[y] = (uint8_t)(q); } ++y; } while (0)
-#define DRAW_Q() (qd = rng_f(&r), qd < 0.90 ? 40 : (qd < 0.95 ? 93 : 2 + (int)rng_int(&r, 28)))
-  double qd;
+#define DRAW_Q() (qw = rng_u64(&r), (qw & 0xffffu) < 58982u ? 40 : ((qw & 0xffffu) < 62259u ? 93 : 2 + (int)((qw >> 16) % 28u)))
+  uint64_t qw; const uint32_t mm_thr = (uint32_t)(p->p_mismatch * 1048576.0);
   for (int i = 0; i < h->clip5; ++i) { int q = DRAW_Q(); int cd = code_of(BASES[rng_int(&r, 4)]); PUT_BASE(cd, q); }
   PUSH_OP(4, h->clip5);
   /* walk the transcript interval [tstart, tstart+tlen) exon by exon */
@@ -225,8 +225,8 @@ static void read_body(const synth_plan *pl, const rhead *h, int mode, int32_t *n
         }
         ++vi;
       }
-      if (rng_f(&r) < p->p_mismatch) b = BASES[rng_int(&r, 4)];
       int q = DRAW_Q();
+      if (((uint32_t)(qw >> 24) & 0xfffffu) < mm_thr) b = BASES[(qw >> 44) & 3u];
       int cd = code_of(b);
       PUT_BASE(cd, q);
       ++run_m; ++t; first_base = 0;
@@ -451,12 +451,11 @@ void synth_variants(const synth_plan *pl, int32_t *tid, int32_t *pos, uint8_t *a
 }
 
 /* pass 1: per-read sizes in sorted order.  cigar_off[n+1], base_off[n+1] (padded to 16). */
-void synth_sizes(const synth_plan *pl, uint32_t *cigar_off, uint64_t *base_off, int32_t *l_qseq) {
-  const int64_t n = pl->p.n_reads;
+void synth_sizes(const synth_plan *pl, const int64_t *sel, int64_t n, uint32_t *cigar_off, uint64_t *base_off, int32_t *l_qseq) {
   int32_t *nc = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n ? n : 1));
 #pragma omp parallel for schedule(dynamic, 1024)
   for (int64_t i = 0; i < n; ++i) {
-    rhead h; read_header(pl, pl->order[i], &h);
+    rhead h; read_header(pl, pl->order[sel ? sel[i] : i], &h);
     int32_t c, l; read_body(pl, &h, 0, &c, &l, NULL, NULL, NULL);
     nc[i] = c; l_qseq[i] = l;
   }
@@ -467,20 +466,33 @@ void synth_sizes(const synth_plan *pl, uint32_t *cigar_off, uint64_t *base_off, 
 }
 
 /* pass 2: fill every array (seq4 must be zero-initialised or is overwritten nibble-wise here) */
-void synth_fill(const synth_plan *pl, const uint32_t *cigar_off, const uint64_t *base_off, int32_t *tid, int32_t *pos,
+void synth_fill(const synth_plan *pl, const int64_t *sel, int64_t n, const uint32_t *cigar_off, const uint64_t *base_off, int32_t *tid, int32_t *pos,
                 uint16_t *flag, uint8_t *mapq, int32_t *cell, uint32_t *cigar, uint8_t *seq4, uint8_t *qual,
                 int64_t *uid_out) {
-  const int64_t n = pl->p.n_reads;
 #pragma omp parallel for schedule(dynamic, 1024)
   for (int64_t i = 0; i < n; ++i) {
-    rhead h; read_header(pl, pl->order[i], &h);
+    rhead h; read_header(pl, pl->order[sel ? sel[i] : i], &h);
     tid[i] = h.tid; pos[i] = h.pos; flag[i] = h.flag; mapq[i] = h.mapq; cell[i] = h.cell;
-    if (uid_out) uid_out[i] = pl->order[i];
+    if (uid_out) uid_out[i] = pl->order[sel ? sel[i] : i];
     int32_t c, l;
     uint64_t bo = base_off[i];
     uint64_t padded = base_off[i + 1] - bo;
     memset(seq4 + (bo >> 1), 0, (size_t)(padded >> 1));
     memset(qual + bo, 0, (size_t)padded);
     read_body(pl, &h, 1, &c, &l, cigar + cigar_off[i], seq4 + (bo >> 1), qual + bo);
+  }
+}
+
+/* header-only view of every read in sorted order: position, end of its gene (an upper bound of
+ * the alignment end) and transcript bases (~ aligned bases); used to shard without materialising */
+void synth_headers(const synth_plan *pl, int32_t *tid, int32_t *pos, int32_t *gene_end, int32_t *tlen) {
+  const int64_t n = pl->p.n_reads;
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    rhead h; read_header(pl, pl->order[i], &h);
+    const gene_t *G = &pl->genes[h.gene];
+    int last = G->ex_first + G->n_exons - 1;
+    tid[i] = h.tid; pos[i] = h.pos; tlen[i] = h.tlen;
+    gene_end[i] = pl->ex_start[last] + pl->ex_len[last];
   }
 }

@@ -49,8 +49,9 @@ def _load():
         lib.synth_n_exons.argtypes = [C.c_void_p]
         lib.synth_exons.argtypes = [C.c_void_p] * 4
         lib.synth_variants.argtypes = [C.c_void_p] * 7
-        lib.synth_sizes.argtypes = [C.c_void_p] * 4
-        lib.synth_fill.argtypes = [C.c_void_p] * 12
+        lib.synth_sizes.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.synth_fill.argtypes = [C.c_void_p, C.c_void_p, C.c_int64] + [C.c_void_p] * 11
+        lib.synth_headers.argtypes = [C.c_void_p] * 5
         _lib = lib
     return _lib
 
@@ -103,73 +104,119 @@ class SynthData:
         return "Cancer" if cell_id < self.n_cancer() else "Non-Cancer"
 
 
-def generate(seed=1, contig_lens=(200000,), contig_names=None, n_genes=20, n_reads=2000, n_cells=100,
-             n_extra_cells=None, frac_cancer=0.4, n_hot_genes=0, hot_fraction=0.0, chrm=False, chrm_fraction=0.02,
-             mean_len=1500.0, sigma_len=0.35, p_mismatch=3e-3, p_ins=1e-3, p_del=1e-3, p_softclip=0.3,
-             p_no_cb=0.005, p_extra_cb=0.01, p_reverse=0.5, p_suppl=0.01, p_secondary=0.005, p_dup=0.005,
-             p_qcfail=0.002, p_lowmapq=0.07, variants_per_gene=3):
-    lib = _load()
-    contig_lens = [int(x) for x in contig_lens]
-    nct = len(contig_lens)
-    if contig_names is None:
-        contig_names = ["chr%d" % (i + 1) for i in range(nct)]
-        if chrm:
-            contig_names[-1] = "chrM"
-    if n_extra_cells is None:
-        n_extra_cells = max(1, n_cells // 50)
-    p = _Params()
-    p.seed, p.n_contigs, p.n_genes, p.n_reads = seed, nct, n_genes, n_reads
-    p.n_cells, p.n_extra_cells, p.frac_cancer = n_cells, n_extra_cells, frac_cancer
-    p.n_hot_genes, p.hot_fraction = n_hot_genes, hot_fraction
-    p.chrm_tid, p.chrm_fraction = (nct - 1 if chrm else -1), chrm_fraction
-    p.mean_len, p.sigma_len = mean_len, sigma_len
-    p.p_mismatch, p.p_ins, p.p_del, p.p_softclip = p_mismatch, p_ins, p_del, p_softclip
-    p.p_no_cb, p.p_extra_cb, p.p_reverse, p.p_suppl = p_no_cb, p_extra_cb, p_reverse, p_suppl
-    p.p_secondary, p.p_dup, p.p_qcfail, p.p_lowmapq = p_secondary, p_dup, p_qcfail, p_lowmapq
-    p.variants_per_gene = variants_per_gene
-    cl = np.array(contig_lens, np.int32)
-    plan = lib.synth_plan_create(C.byref(p), cl.ctypes.data_as(C.c_void_p))
-    if not plan:
-        raise RuntimeError("synth_plan_create failed (too few genes?)")
-    try:
+class Plan:
+    """Genome + gene models + sorted read order; reads are materialised on demand (all or a subset)."""
+
+    def __init__(self, seed=1, contig_lens=(200000,), contig_names=None, n_genes=20, n_reads=2000, n_cells=100,
+                 n_extra_cells=None, frac_cancer=0.4, n_hot_genes=0, hot_fraction=0.0, chrm=False,
+                 chrm_fraction=0.02, mean_len=1500.0, sigma_len=0.35, p_mismatch=3e-3, p_ins=1e-3, p_del=1e-3,
+                 p_softclip=0.3, p_no_cb=0.005, p_extra_cb=0.01, p_reverse=0.5, p_suppl=0.01, p_secondary=0.005,
+                 p_dup=0.005, p_qcfail=0.002, p_lowmapq=0.07, variants_per_gene=3):
+        lib = _load()
+        self.contig_lens = [int(x) for x in contig_lens]
+        nct = len(self.contig_lens)
+        if contig_names is None:
+            contig_names = ["chr%d" % (i + 1) for i in range(nct)]
+            if chrm:
+                contig_names[-1] = "chrM"
+        self.contig_names = list(contig_names)
+        if n_extra_cells is None:
+            n_extra_cells = max(1, n_cells // 50)
+        p = _Params()
+        p.seed, p.n_contigs, p.n_genes, p.n_reads = seed, nct, n_genes, n_reads
+        p.n_cells, p.n_extra_cells, p.frac_cancer = n_cells, n_extra_cells, frac_cancer
+        p.n_hot_genes, p.hot_fraction = n_hot_genes, hot_fraction
+        p.chrm_tid, p.chrm_fraction = (nct - 1 if chrm else -1), chrm_fraction
+        p.mean_len, p.sigma_len = mean_len, sigma_len
+        p.p_mismatch, p.p_ins, p.p_del, p.p_softclip = p_mismatch, p_ins, p_del, p_softclip
+        p.p_no_cb, p.p_extra_cb, p.p_reverse, p.p_suppl = p_no_cb, p_extra_cb, p_reverse, p_suppl
+        p.p_secondary, p.p_dup, p.p_qcfail, p.p_lowmapq = p_secondary, p_dup, p_qcfail, p_lowmapq
+        p.variants_per_gene = variants_per_gene
+        self.p = p
+        self.n_reads, self.n_cells, self.n_extra_cells, self.frac_cancer = n_reads, n_cells, n_extra_cells, frac_cancer
+        cl = np.array(self.contig_lens, np.int32)
+        self._plan = lib.synth_plan_create(C.byref(p), cl.ctypes.data_as(C.c_void_p))
+        if not self._plan:
+            raise RuntimeError("synth_plan_create failed (too few genes?)")
+        self.contig_off = np.zeros(nct + 1, np.int64)
+        np.cumsum(cl.astype(np.int64), out=self.contig_off[1:])
+        ref_len = lib.synth_ref_len(self._plan)
+        self.ref = np.ctypeslib.as_array(C.cast(lib.synth_ref(self._plan), C.POINTER(C.c_uint8)),
+                                         shape=(ref_len,)).copy()
+
+    def close(self):
+        if getattr(self, "_plan", None):
+            _load().synth_free(self._plan)
+            self._plan = None
+
+    def __del__(self):
+        self.close()
+
+    def headers(self):
+        """(tid, pos, gene_end, tlen) of every read in coordinate order, without materialising bases."""
+        n = self.n_reads
+        tid, pos, gend, tlen = (np.zeros(n, np.int32) for _ in range(4))
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        ref_len = lib.synth_ref_len(plan)
-        ref = np.ctypeslib.as_array(C.cast(lib.synth_ref(plan), C.POINTER(C.c_uint8)), shape=(ref_len,)).copy()
-        contig_off = np.zeros(nct + 1, np.int64)
-        np.cumsum(cl.astype(np.int64), out=contig_off[1:])
-        n = n_reads
+        _load().synth_headers(self._plan, vp(tid), vp(pos), vp(gend), vp(tlen))
+        return tid, pos, gend, tlen
+
+    def materialize(self, sel=None):
+        """ReadBatch of all reads (sel=None) or of the sorted-order indices in `sel` (ascending)."""
+        lib = _load()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        if sel is not None:
+            sel = np.ascontiguousarray(sel, np.int64)
+            n = int(sel.shape[0])
+            selp = vp(sel) if n else None
+        else:
+            n, selp = self.n_reads, None
         cigar_off = np.zeros(n + 1, np.uint32)
         base_off = np.zeros(n + 1, np.uint64)
-        l_qseq = np.zeros(n, np.int32)
-        lib.synth_sizes(plan, vp(cigar_off), vp(base_off), vp(l_qseq))
+        l_qseq = np.zeros(max(n, 1), np.int32)[:n]
+        lib.synth_sizes(self._plan, selp, n, vp(cigar_off), vp(base_off), vp(l_qseq))
         n_cigar, n_bases = int(cigar_off[-1]), int(base_off[-1])
-        tid = np.zeros(n, np.int32)
-        pos = np.zeros(n, np.int32)
-        flag = np.zeros(n, np.uint16)
-        mapq = np.zeros(n, np.uint8)
-        cell = np.zeros(n, np.int32)
+        tid, pos, cell = (np.zeros(max(n, 1), np.int32)[:n] for _ in range(3))
+        flag = np.zeros(max(n, 1), np.uint16)[:n]
+        mapq = np.zeros(max(n, 1), np.uint8)[:n]
         cigar = np.zeros(max(n_cigar, 1), np.uint32)[:n_cigar]
         seq4 = np.zeros(max(n_bases // 2, 1), np.uint8)[:n_bases // 2]
         qual = np.zeros(max(n_bases, 1), np.uint8)[:n_bases]
-        uid = np.zeros(n, np.int64)
-        lib.synth_fill(plan, vp(cigar_off), vp(base_off), vp(tid), vp(pos), vp(flag), vp(mapq), vp(cell), vp(cigar),
-                       vp(seq4), vp(qual), vp(uid))
-        ne = lib.synth_n_exons(plan)
+        uid = np.zeros(max(n, 1), np.int64)[:n]
+        lib.synth_fill(self._plan, selp, n, vp(cigar_off), vp(base_off), vp(tid), vp(pos), vp(flag), vp(mapq), vp(cell),
+                       vp(cigar), vp(seq4), vp(qual), vp(uid))
+        batch = ReadBatch(tid, pos, flag, mapq, cell, cigar_off, cigar, base_off, l_qseq, seq4, qual)
+        batch.uid = uid
+        return batch
+
+    def truth(self):
+        lib = _load()
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        ne = lib.synth_n_exons(self._plan)
         e_tid, e_start, e_len = np.zeros(ne, np.int32), np.zeros(ne, np.int32), np.zeros(ne, np.int32)
-        lib.synth_exons(plan, vp(e_tid), vp(e_start), vp(e_len))
-        nv = lib.synth_n_vars(plan)
+        lib.synth_exons(self._plan, vp(e_tid), vp(e_start), vp(e_len))
+        nv = lib.synth_n_vars(self._plan)
         v = dict(tid=np.zeros(nv, np.int32), pos=np.zeros(nv, np.int32), alt=np.zeros(nv, np.uint8),
                  scope=np.zeros(nv, np.uint8), read_prob=np.zeros(nv, np.float32),
                  cell_frac=np.zeros(nv, np.float32))
         if nv:
-            lib.synth_variants(plan, vp(v["tid"]), vp(v["pos"]), vp(v["alt"]), vp(v["scope"]), vp(v["read_prob"]),
+            lib.synth_variants(self._plan, vp(v["tid"]), vp(v["pos"]), vp(v["alt"]), vp(v["scope"]), vp(v["read_prob"]),
                                vp(v["cell_frac"]))
+        return (e_tid, e_start, e_len), v
+
+    def data(self, sel=None):
+        exons, variants = self.truth()
+        return SynthData(self.contig_names, self.contig_lens, self.ref, self.contig_off, self.materialize(sel),
+                         self.n_cells, self.n_extra_cells, self.frac_cancer, exons, variants,
+                         dict(seed=int(self.p.seed), n_reads=self.n_reads))
+
+
+def generate(**kw):
+    """All reads of a plan as a SynthData."""
+    plan = Plan(**kw)
+    try:
+        return plan.data()
     finally:
-        lib.synth_free(plan)
-    batch = ReadBatch(tid, pos, flag, mapq, cell, cigar_off, cigar, base_off, l_qseq, seq4, qual)
-    batch.uid = uid
-    return SynthData(contig_names, contig_lens, ref, contig_off, batch, n_cells, n_extra_cells, frac_cancer,
-                     (e_tid, e_start, e_len), v, dict(seed=seed, n_reads=n_reads, n_genes=n_genes))
+        plan.close()
 
 
 # ---- BASELINE.json configs ---------------------------------------------------------------------

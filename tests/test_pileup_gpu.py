@@ -93,3 +93,33 @@ def test_rejects_bad_input(engine):
                     b.seq4, b.qual)
     with pytest.raises(LongSomError):
         engine.pileup_count(bad, w, CountParams())
+
+
+def test_few_cells_long_runs(engine):
+    """3 cells x 20k reads on one locus: same-cell runs of thousands of segments per tile
+    (the kernel must leave its 12-bit packed-counter variant) and multi-part tiles."""
+    import oracle
+    d = synth.generate(seed=8, contig_lens=[100000], n_genes=3, n_reads=20000, n_cells=3, n_extra_cells=1,
+                       n_hot_genes=1, hot_fraction=0.9)
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    p = CountParams(min_bq=20, min_mq=60, min_dp=5, min_cc=2)
+    _compare(engine.pileup_count(d.batch, w, p), oracle.pileup_count(d.batch, w, p, threads=4)[0])
+
+
+def test_results_independent_of_batch_composition(engine):
+    """Size-independent property: counting a window from the full batch or from only the reads
+    that overlap it gives identical sites (what multi-GPU sharding relies on)."""
+    d = synth.generate(seed=12, contig_lens=[260000], n_genes=16, n_reads=15000, n_cells=120)
+    iv = make_windows(d.contig_lens, 50000)
+    p = CountParams(min_bq=20, min_mq=60)
+    full = engine.pileup_count(d.batch, Windows.from_intervals(iv, d.contig_seqs()), p)
+    parts = []
+    for t, s, e in iv:
+        op = d.batch.cigar & 15
+        ln = np.where(np.isin(op, [0, 2, 3, 7, 8]), d.batch.cigar >> 4, 0).astype(np.int64)
+        span = np.add.reduceat(ln, d.batch.cigar_off[:-1].astype(np.int64))
+        sel = np.nonzero((d.batch.pos < e) & (d.batch.pos + span > s))[0]
+        parts.append(engine.pileup_count(d.batch.select(sel), Windows.from_intervals([(t, s, e)], d.contig_seqs()), p))
+    assert sum(x.n_sites for x in parts) == full.n_sites
+    assert np.array_equal(np.concatenate([x.pos for x in parts]), full.pos)
+    assert np.array_equal(np.concatenate([x.counts for x in parts]), full.counts)
