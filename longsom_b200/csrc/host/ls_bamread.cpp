@@ -1,0 +1,317 @@
+// Host-side BAM decoder: BGZF inflate (zlib, multi-threaded) + record parse into the
+// structure-of-arrays batch of include/longsom_b200.h.
+//
+// Takes the place of pysam/htslib record decoding on the hot path (reference call sites:
+// pysam.AlignmentFile(BAM) at BaseCellCounter.py:190, SingleCellGenotype.py:123).  The
+// reference re-opens and re-decodes the BAM once per 50 kb window and touches every read
+// through Python objects; here the file is inflated once, block-parallel, and every record
+// becomes one row of the SoA arrays that are handed to the GPU.
+//
+// Format facts used (SAM/BAM spec v1, sections 4.1-4.2): BGZF = concatenated gzip members with
+// a BC extra sub-field holding BSIZE; BAM record = block_size, refID, pos, l_read_name, mapq,
+// bin, n_cigar_op, flag, l_seq, next_refID, next_pos, tlen, read_name, cigar, seq (4-bit),
+// qual, aux.  The CB:Z aux tag is interned (raw text) into dense ids.
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+struct Block {
+  uint64_t coff;   // offset of the gzip member in the file
+  uint32_t csize;  // compressed member size
+  uint32_t usize;  // ISIZE
+  uint64_t uoff;   // offset in the inflated stream
+};
+
+struct Bam {
+  std::string err;
+  std::vector<std::string> contig_names;
+  std::vector<int32_t> contig_lens;
+  std::string header_text;
+  // SoA
+  std::vector<int32_t> tid, pos, cb, lq;
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq;
+  std::vector<uint32_t> cigar_off, cigar;
+  std::vector<uint64_t> base_off;
+  std::vector<uint8_t> seq4, qual;
+  std::vector<std::string> barcodes;
+  int64_t n_reads = 0;
+};
+
+static inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+
+static bool inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
+  // gzip member: 10-byte header + XLEN extra, deflate stream, CRC32, ISIZE
+  if (csize < 18) return false;
+  uint32_t xlen = rd16(src + 10);
+  const uint8_t *def = src + 12 + xlen;
+  uint32_t dlen = csize - 12 - xlen - 8;
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  zs.next_in = const_cast<Bytef *>(def);
+  zs.avail_in = dlen;
+  zs.next_out = dst;
+  zs.avail_out = usize;
+  int rc = inflate(&zs, Z_FINISH);
+  inflateEnd(&zs);
+  return rc == Z_STREAM_END && zs.total_out == usize;
+}
+
+// find "CB" aux tag of type Z; returns pointer to the NUL-terminated text or nullptr
+static const char *find_cb(const uint8_t *p, const uint8_t *end) {
+  while (p + 3 <= end) {
+    const uint8_t t0 = p[0], t1 = p[1], ty = p[2];
+    p += 3;
+    const bool is_cb = (t0 == 'C' && t1 == 'B');
+    switch (ty) {
+      case 'A': case 'c': case 'C': p += 1; break;
+      case 's': case 'S': p += 2; break;
+      case 'i': case 'I': case 'f': p += 4; break;
+      case 'Z': case 'H': {
+        const uint8_t *s = p;
+        while (p < end && *p) ++p;
+        if (p >= end) return nullptr;
+        ++p;
+        if (is_cb && ty == 'Z') return reinterpret_cast<const char *>(s);
+        break;
+      }
+      case 'B': {
+        if (p + 5 > end) return nullptr;
+        const uint8_t sub = p[0];
+        const uint32_t cnt = rd32(p + 1);
+        p += 5;
+        size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+        p += es * (size_t)cnt;
+        break;
+      }
+      default: return nullptr;  // unknown type: stop scanning
+    }
+  }
+  return nullptr;
+}
+
+}  // namespace
+
+extern "C" {
+
+void *ls_bam_read(const char *path, int threads) {
+  Bam *b = new Bam();
+  FILE *f = fopen(path, "rb");
+  if (!f) {
+    b->err = std::string("cannot open ") + path;
+    return b;
+  }
+  fseek(f, 0, SEEK_END);
+  const uint64_t fsize = (uint64_t)ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::vector<uint8_t> comp(fsize);
+  if (fsize && fread(comp.data(), 1, fsize, f) != fsize) {
+    fclose(f);
+    b->err = "short read";
+    return b;
+  }
+  fclose(f);
+  // pass 1: BGZF block table
+  std::vector<Block> blocks;
+  uint64_t off = 0, uoff = 0;
+  while (off + 18 <= fsize) {
+    const uint8_t *p = comp.data() + off;
+    if (p[0] != 0x1f || p[1] != 0x8b || !(p[3] & 4)) {
+      b->err = "not a BGZF file (bad gzip member header)";
+      return b;
+    }
+    uint32_t xlen = rd16(p + 10);
+    uint32_t bsize = 0;
+    const uint8_t *x = p + 12, *xe = p + 12 + xlen;
+    while (x + 4 <= xe) {
+      uint32_t slen = rd16(x + 2);
+      if (x[0] == 'B' && x[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(x + 4) + 1;
+      x += 4 + slen;
+    }
+    if (bsize == 0 || off + bsize > fsize) {
+      b->err = "corrupt BGZF block";
+      return b;
+    }
+    Block bl;
+    bl.coff = off;
+    bl.csize = bsize;
+    bl.usize = rd32(p + bsize - 4);
+    bl.uoff = uoff;
+    blocks.push_back(bl);
+    uoff += bl.usize;
+    off += bsize;
+  }
+  // pass 2: inflate in parallel
+  std::vector<uint8_t> raw(uoff);
+  if (threads < 1) threads = 1;
+  std::atomic<size_t> next(0);
+  std::atomic<int> bad(0);
+  auto worker = [&]() {
+    for (;;) {
+      size_t i = next.fetch_add(16);
+      if (i >= blocks.size()) break;
+      for (size_t j = i; j < i + 16 && j < blocks.size(); ++j) {
+        const Block &bl = blocks[j];
+        if (bl.usize && !inflate_block(comp.data() + bl.coff, bl.csize, raw.data() + bl.uoff, bl.usize)) bad = 1;
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(worker);
+    for (auto &t : th) t.join();
+  }
+  comp.clear();
+  comp.shrink_to_fit();
+  if (bad) {
+    b->err = "inflate failed";
+    return b;
+  }
+  // header
+  const uint8_t *p = raw.data(), *end = raw.data() + raw.size();
+  if (raw.size() < 12 || memcmp(p, "BAM\1", 4) != 0) {
+    b->err = "bad BAM magic";
+    return b;
+  }
+  uint32_t l_text = rd32(p + 4);
+  b->header_text.assign(reinterpret_cast<const char *>(p + 8), l_text);
+  p += 8 + l_text;
+  uint32_t n_ref = rd32(p);
+  p += 4;
+  for (uint32_t i = 0; i < n_ref; ++i) {
+    uint32_t l_name = rd32(p);
+    b->contig_names.emplace_back(reinterpret_cast<const char *>(p + 4), l_name ? l_name - 1 : 0);
+    b->contig_lens.push_back((int32_t)rd32(p + 4 + l_name));
+    p += 8 + l_name;
+  }
+  // pass 3: record offsets (sequential walk over block_size fields)
+  std::vector<const uint8_t *> recs;
+  while (p + 4 <= end) {
+    uint32_t bs = rd32(p);
+    if (p + 4 + bs > end) {
+      b->err = "truncated BAM record";
+      return b;
+    }
+    recs.push_back(p + 4);
+    p += 4 + bs;
+  }
+  const int64_t n = (int64_t)recs.size();
+  b->n_reads = n;
+  b->tid.resize(n);
+  b->pos.resize(n);
+  b->cb.resize(n);
+  b->lq.resize(n);
+  b->flag.resize(n);
+  b->mapq.resize(n);
+  b->cigar_off.resize(n + 1);
+  b->base_off.resize(n + 1);
+  // pass 4: sizes + barcode interning (sequential: the map is shared)
+  std::unordered_map<std::string, int32_t> bmap;
+  uint32_t co = 0;
+  uint64_t bo = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const uint8_t *r = recs[i];
+    const uint32_t l_name = r[8];
+    const uint32_t n_cig = rd16(r + 12);
+    const uint32_t l_seq = rd32(r + 16);
+    b->tid[i] = (int32_t)rd32(r);
+    b->pos[i] = (int32_t)rd32(r + 4);
+    b->mapq[i] = r[9];
+    b->flag[i] = rd16(r + 14);
+    b->lq[i] = (int32_t)l_seq;
+    b->cigar_off[i] = co;
+    b->base_off[i] = bo;
+    co += n_cig;
+    bo += ((uint64_t)l_seq + 15u) & ~(uint64_t)15u;
+    const uint8_t *aux = r + 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq;
+    const uint8_t *rend = r + rd32(r - 4);
+    const char *cbs = aux <= rend ? find_cb(aux, rend) : nullptr;
+    if (!cbs) {
+      b->cb[i] = -1;
+    } else {
+      auto it = bmap.find(cbs);
+      if (it == bmap.end()) {
+        int32_t id = (int32_t)b->barcodes.size();
+        b->barcodes.emplace_back(cbs);
+        bmap.emplace(b->barcodes.back(), id);
+        b->cb[i] = id;
+      } else {
+        b->cb[i] = it->second;
+      }
+    }
+  }
+  b->cigar_off[n] = co;
+  b->base_off[n] = bo;
+  b->cigar.resize(co);
+  b->seq4.assign(bo / 2, 0);
+  b->qual.assign(bo, 0);
+  // pass 5: fill cigar / seq / qual in parallel
+  std::atomic<int64_t> nx(0);
+  auto filler = [&]() {
+    for (;;) {
+      int64_t i0 = nx.fetch_add(4096);
+      if (i0 >= n) break;
+      for (int64_t i = i0; i < i0 + 4096 && i < n; ++i) {
+        const uint8_t *r = recs[i];
+        const uint32_t l_name = r[8];
+        const uint32_t n_cig = rd16(r + 12);
+        const uint32_t l_seq = rd32(r + 16);
+        const uint8_t *cg = r + 32 + l_name;
+        memcpy(b->cigar.data() + b->cigar_off[i], cg, 4 * (size_t)n_cig);
+        const uint8_t *sq = cg + 4 * n_cig;
+        memcpy(b->seq4.data() + b->base_off[i] / 2, sq, (l_seq + 1) / 2);
+        memcpy(b->qual.data() + b->base_off[i], sq + (l_seq + 1) / 2, l_seq);
+      }
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; ++t) th.emplace_back(filler);
+    for (auto &t : th) t.join();
+  }
+  return b;
+}
+
+const char *ls_bam_error(void *h) { Bam *b = (Bam *)h; return b->err.empty() ? nullptr : b->err.c_str(); }
+void ls_bam_free(void *h) { delete (Bam *)h; }
+int64_t ls_bam_n_reads(void *h) { return ((Bam *)h)->n_reads; }
+int64_t ls_bam_n_cigar(void *h) { return (int64_t)((Bam *)h)->cigar.size(); }
+int64_t ls_bam_n_bases(void *h) { return (int64_t)((Bam *)h)->qual.size(); }
+int32_t ls_bam_n_contigs(void *h) { return (int32_t)((Bam *)h)->contig_names.size(); }
+const char *ls_bam_contig_name(void *h, int i) { return ((Bam *)h)->contig_names[i].c_str(); }
+int32_t ls_bam_contig_len(void *h, int i) { return ((Bam *)h)->contig_lens[i]; }
+int32_t ls_bam_n_barcodes(void *h) { return (int32_t)((Bam *)h)->barcodes.size(); }
+const char *ls_bam_barcode(void *h, int i) { return ((Bam *)h)->barcodes[i].c_str(); }
+const char *ls_bam_header_text(void *h) { return ((Bam *)h)->header_text.c_str(); }
+// array getters: 0 tid 1 pos 2 flag 3 mapq 4 cb 5 cigar_off 6 cigar 7 base_off 8 l_qseq 9 seq4 10 qual
+const void *ls_bam_array(void *h, int which) {
+  Bam *b = (Bam *)h;
+  switch (which) {
+    case 0: return b->tid.data();
+    case 1: return b->pos.data();
+    case 2: return b->flag.data();
+    case 3: return b->mapq.data();
+    case 4: return b->cb.data();
+    case 5: return b->cigar_off.data();
+    case 6: return b->cigar.data();
+    case 7: return b->base_off.data();
+    case 8: return b->lq.data();
+    case 9: return b->seq4.data();
+    case 10: return b->qual.data();
+  }
+  return nullptr;
+}
+
+}  // extern "C"

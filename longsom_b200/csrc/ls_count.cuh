@@ -1,32 +1,40 @@
-// K1 pileup-count kernel (second generation) + host orchestration.  Included by ls_pileup.cu.
+// K1 pileup-count kernel (third generation) + part bookkeeping.  Included by ls_pileup.cu.
 //
 // Unit of work: a PART = up to K1_PART_SEGS consecutive (tile, cell)-sorted segments of one
 // tile.  Most tiles are one part; deep tiles (chrM, hotspot genes: >1e5 reads per locus) are
-// split so that no CTA owns more than ~4e5 pileup entries -- the skew that made the first
-// version's tail 70 ms long.  Same-cell runs never straddle parts (a run belongs to the part /
-// chunk that holds its first segment), so NC / CC stay exact and every output word is additive
-// across parts; multi-part tiles add into their HBM slot and the last part to finish applies
-// the reference's gates.
+// split so that no CTA owns more than ~4e5 pileup entries.  Same-cell runs never straddle
+// parts (a run belongs to the part / chunk that holds its first segment), so NC / CC stay
+// exact and every output word is additive across parts; multi-part tiles add into their HBM
+// slot and the last part to finish applies the reference's gates.
 //
-// Inside a part (CTA of 16 warps, tile accumulators in shared memory):
-//   * a warp grabs a chunk of <= 32 segments; lane j loads segment j's record and read
-//     metadata (one global-latency for the whole chunk instead of one per segment);
-//   * per segment the lanes fetch the next 32 CIGAR ops at once, then walk them warp-uniformly;
-//   * a match op is consumed 128 query bases per step: lane L loads one aligned 32-bit word of
-//     qualities and one 16-bit word of 4-bit bases (vectorised, coalesced), classifies its 4
-//     bases and issues ONE packed shared atomic per visible base (count<<20 | quality);
-//   * the site index is swizzled so that the 4-bases-per-lane pattern is bank-conflict free.
+// Inside a part (CTA of 8 warps, tile accumulators in shared memory) a warp grabs a chunk of
+// <= 32 segments and processes it in two phases so that global-memory latency is paid once
+// per chunk, not once per segment:
+//   phase 1 (lane = segment): every lane loads its segment record + read metadata and walks its
+//     own CIGAR; each op piece inside the tile becomes a 16-byte UNIT in a per-warp shared queue
+//     (first base address, length, first site, strand, indel class of the last base);
+//   phase 2 (lane = 4 query bases): the units' 32-bit quality words are flattened into one
+//     index space; lane L takes words L, L+32, ... (binary search in the unit prefix table),
+//     two words in flight per lane; per word one aligned 32-bit load of qualities and one
+//     16-bit load of 4-bit bases, 4 classifications, ONE packed shared atomic per visible base
+//     (count<<20 | quality).  Lanes are fully used however short the op pieces are.
+// Distinct-cell counts: NC/CC = reads minus same-cell duplicates.  Runs of >1 same-cell
+// segments mark (site, class) bits with atomicOr in a per-warp seen[] array, so the order in
+// which a run's bases are visited does not matter; single-segment runs skip this entirely.
+// The accumulator column of site s is [s mod 4][s / 4]: the 4-bases-per-lane pattern then
+// hits 32 distinct banks on each of its 4 atomics.
 #pragma once
 
-constexpr int K1_THREADS = 512;
+constexpr int K1_THREADS = 256;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_PART_SEGS = 2048;       // nominal segments per part
 constexpr int K1_MAX_RUN_PACKED = 2039;  // packed counters (12-bit) need: part segs + run extension <= 4095
 constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
+constexpr int K1_UNIT_CAP = 128;         // op pieces queued per warp per phase-1 round
 
-static_assert(LS_TILE % 128 == 0 && LS_TILE == K1_THREADS, "epilogue maps one thread to one site");
+static_assert(LS_TILE % 128 == 0 && LS_TILE % K1_THREADS == 0 && LS_TILE <= 65536, "tile / block shape");
 
-__host__ __device__ __forceinline__ int swz(int s) { return (s & ~127) | ((s & 3) << 5) | ((s >> 2) & 31); }
+__host__ __device__ __forceinline__ int swz(int s) { return ((s & 3) * (LS_TILE / 4)) | (s >> 2); }
 
 struct CountArgs {
   const uint16_t *flag;
@@ -57,13 +65,29 @@ struct CountArgs {
   int min_bq, min_dp, min_cc, min_ac;
 };
 
+// one op piece inside the tile
+struct __align__(16) Unit {
+  uint64_t qaddr;  // match: index of the first base in qual[] (read base offset + query index)
+  uint16_t n;      // bases (match) / columns (deletion)
+  uint16_t sbase;  // site (tile-relative) of the first base / column
+  uint8_t flags;   // bit0 strand, bit1 counted, bit2 deletion-kind, bits 3-4 class of the LAST base: 1 = D, 2 = I
+  uint8_t q;       // deletion-kind: the quality shared by all its columns
+  uint16_t pad;
+};
+#define UF_STRAND 1u
+#define UF_COUNTED 2u
+#define UF_DEL 4u
+
 template <bool PACKED>
 struct TileSmemT {
   uint32_t hist[PACKED ? 16 : 32][LS_TILE];  // PACKED: [cls*2+strand] = cnt<<20|bq ; else [0..15] cnt, [16..31] bq
   uint32_t dupcc[6][LS_TILE];                // entries whose (cell, class) was already seen at the site
   uint32_t dupnc[LS_TILE];                   // entries whose cell was already seen at the site (any class)
   uint32_t acx[LS_TILE];                     // alt entries of visible-but-uncounted reads (--min_ac > 0)
-  uint8_t seen[K1_WARPS][LS_TILE];
+  uint32_t seen[K1_WARPS][LS_TILE / 4];      // per warp: class bits (1 byte per site) of the current same-cell run
+  Unit units[K1_WARPS][K1_UNIT_CAP];
+  uint32_t upre[K1_WARPS][K1_UNIT_CAP + 1];  // exclusive prefix of 32-bit words per unit
+  uint32_t ucount[K1_WARPS];
   uint8_t ref[LS_TILE];
   uint32_t next, npass, ticket;
 };
@@ -81,8 +105,9 @@ __device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t ti
 }
 
 template <bool PACKED, bool SEEN>
-__device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint8_t *seen, int sidx, int cls, uint32_t q,
+__device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint32_t *seen, int s, int cls, uint32_t q,
                                           int strand) {
+  const int sidx = swz(s);
   if (PACKED) {
     atomicAdd(&sm.hist[cls * 2 + strand][sidx], (1u << K1_CNT_SHIFT) | q);
   } else {
@@ -90,11 +115,12 @@ __device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint8_t *seen, 
     atomicAdd(&sm.hist[16 + cls * 2 + strand][sidx], q);
   }
   if (SEEN) {
-    const uint32_t old = seen[sidx];
-    const uint32_t bit = 1u << cls;
-    if ((old & bit) && cls < 6) atomicAdd(&sm.dupcc[cls][sidx], 1u);
+    const int sh = 8 * (s & 3);
+    const uint32_t old = (atomicOr(&seen[s >> 2], (1u << cls) << sh) >> sh) & 255u;
+    if ((old >> cls) & 1u) {
+      if (cls < 6) atomicAdd(&sm.dupcc[cls][sidx], 1u);
+    }
     if (old) atomicAdd(&sm.dupnc[sidx], 1u);
-    seen[sidx] = (uint8_t)(old | bit);
   }
 }
 
@@ -115,131 +141,76 @@ struct SegMeta {
   int strand;
 };
 
-// One segment = the part of one read inside the tile; warp-cooperative.
-template <bool PACKED, bool SEEN>
-__device__ __forceinline__ uint32_t process_segment(const CountArgs &a, TileSmemT<PACKED> &sm, uint8_t *seen,
-                                                    const SegMeta m, int32_t tile_start, int32_t tile_end,
-                                                    bool counted, int lane) {
+// ---- slow path: one segment, warp-cooperative CIGAR walk (used for queue overflow and malformed
+// records whose CIGAR outruns the stored sequence) -----------------------------------------------
+template <bool PACKED, bool SEEN, bool COUNTED>
+__device__ __noinline__ void process_segment(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen,
+                                             const SegMeta m, int32_t tile_start, int32_t tile_end, int lane) {
   const uint8_t *__restrict__ qual = a.qual + m.boff;
   const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
   const int strand = m.strand;
   const uint32_t lq = m.lq;
   int32_t x = m.x0;
   uint32_t y = m.y0;
-  uint32_t nev = 0;
-  uint32_t k = m.cig;
-  while (k < m.kend && x < tile_end) {
-    // the next (up to) 32 ops in one coalesced load; op k+1 alongside for the indel peek
-    const uint32_t kk = k + (uint32_t)lane;
-    const uint32_t c_l = kk < m.kend ? a.cigar[kk] : 0xfu;
-    const uint32_t c_n = kk + 1 < m.kend ? a.cigar[kk + 1] : 0xfu;
-    const int nwin = (int)((m.kend - k) < 32u ? (m.kend - k) : 32u);
-    for (int t = 0; t < nwin && x < tile_end; ++t) {
-      const uint32_t c = __shfl_sync(0xffffffffu, c_l, t);
-      const uint32_t cn = __shfl_sync(0xffffffffu, c_n, t);
-      const uint32_t op = c & 15u;
-      const int32_t len = (int32_t)(c >> 4);
-      const bool match = op_is_match(op);
-      if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
-        const int32_t last = x + len - 1;
-        int ind = 0;
-        if (last >= tile_start && last < tile_end) {
-          const uint32_t op2 = cn & 15u;
-          if (op2 == OP_D && op != OP_D)
-            ind = -1;
-          else if (op2 == OP_I)
-            ind = 1;
-          else if (op2 == OP_P)
-            ind = indel_after(a.cigar, k + (uint32_t)t, m.kend, op);
-        }
-        if (op == OP_N) {
-          if (ind != 0 && lane == 0) {
-            const uint32_t q = y < lq ? qual[y] : 0u;
-            if ((int)q >= a.min_bq) {
-              const int cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-              const int s = last - tile_start;
-              if (counted) {
-                add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, q, strand);
-                ++nev;
-              } else {
-                add_uncounted<PACKED>(sm, s, cls);
-              }
-            }
-          }
-        } else if (!match) {  // deletion: every column carries the quality of the next query base
-          const int32_t lo = x > tile_start ? x : tile_start;
-          const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
+  for (uint32_t k = m.cig; k < m.kend && x < tile_end; ++k) {
+    const uint32_t c = a.cigar[k];
+    const uint32_t op = c & 15u;
+    const int32_t len = (int32_t)(c >> 4);
+    const bool match = op_is_match(op);
+    if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
+      const int32_t last = x + len - 1;
+      int ind = 0;
+      if (last >= tile_start && last < tile_end) ind = indel_after(a.cigar, k, m.kend, op);
+      const int32_t lo = x > tile_start ? x : tile_start;
+      const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
+      if (op == OP_N) {
+        if (ind != 0 && lane == 0) {
           const uint32_t q = y < lq ? qual[y] : 0u;
           if ((int)q >= a.min_bq) {
-            for (int32_t p = lo + lane; p < hi; p += 32) {
-              const int cls = (p == last && ind != 0) ? (ind < 0 ? LS_CLASS_D : LS_CLASS_I) : LS_CLASS_O;
-              const int s = p - tile_start;
-              if (counted) {
-                add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, q, strand);
-                ++nev;
-              } else {
-                add_uncounted<PACKED>(sm, s, cls);
-              }
-            }
+            const int cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
+            if (COUNTED)
+              add_entry<PACKED, SEEN>(sm, seen, last - tile_start, cls, q, strand);
+            else
+              add_uncounted<PACKED>(sm, last - tile_start, cls);
           }
-        } else {
-          const int32_t lo = x > tile_start ? x : tile_start;
-          const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
-          const uint32_t ya = y + (uint32_t)(lo - x), yb = y + (uint32_t)(hi - x);  // query range inside the tile
-          const uint32_t ybl = yb < lq ? yb : lq;                                    // bases that exist
-          const int sbase = lo - tile_start;
-          const uint32_t ylast = (ind != 0) ? (y + (uint32_t)len - 1u) : 0xffffffffu;
-          for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < ybl; g += 128u) {
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
-            const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t qp = g + (uint32_t)j;
-              const uint32_t q = (w >> (8 * j)) & 255u;
-              if (qp >= ya && qp < ybl && (int)q >= a.min_bq) {
-                const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
-                int cls = (int)((K1_CLASS_LUT >> (4 * code)) & 15ull);
-                if (qp == ylast) cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-                if (cls != LS_CLASS_NA) {
-                  const int s = sbase + (int)(qp - ya);
-                  if (counted) {
-                    add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, q, strand);
-                    ++nev;
-                  } else {
-                    add_uncounted<PACKED>(sm, s, cls);
-                  }
-                }
+        }
+      } else {
+        for (int32_t p = lo + lane; p < hi; p += 32) {
+          const uint32_t qpos = match ? y + (uint32_t)(p - x) : y;
+          const uint32_t q = qpos < lq ? qual[qpos] : 0u;
+          if ((int)q >= a.min_bq) {
+            int cls;
+            if (p == last && ind != 0) {
+              cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
+            } else if (match) {
+              uint32_t code = 15u;
+              if (qpos < lq) {
+                const uint32_t b = seq4[qpos >> 1];
+                code = (qpos & 1u) ? (b & 15u) : (b >> 4);
               }
+              cls = class_of_code(code);
+            } else {
+              cls = LS_CLASS_O;
             }
-          }
-          // query positions past the stored sequence (malformed record): base 'N', quality 0
-          if (yb > lq && a.min_bq <= 0) {
-            for (uint32_t qp = (ya > lq ? ya : lq) + (uint32_t)lane; qp < yb; qp += 32u) {
-              const int cls = (qp == ylast) ? (ind < 0 ? LS_CLASS_D : LS_CLASS_I) : LS_CLASS_N;
-              const int s = sbase + (int)(qp - ya);
-              if (counted) {
-                add_entry<PACKED, SEEN>(sm, seen, swz(s), cls, 0u, strand);
-                ++nev;
-              } else {
-                add_uncounted<PACKED>(sm, s, cls);
-              }
+            if (cls != LS_CLASS_NA) {
+              if (COUNTED)
+                add_entry<PACKED, SEEN>(sm, seen, p - tile_start, cls, q, strand);
+              else
+                add_uncounted<PACKED>(sm, p - tile_start, cls);
             }
           }
         }
-        if (SEEN) __syncwarp();
-      }
-      if (match) {
-        x += len;
-        y += (uint32_t)len;
-      } else if (op == OP_D || op == OP_N) {
-        x += len;
-      } else if (op == OP_I || op == OP_S) {
-        y += (uint32_t)len;
       }
     }
-    k += (uint32_t)nwin;
+    if (match) {
+      x += len;
+      y += (uint32_t)len;
+    } else if (op == OP_D || op == OP_N) {
+      x += len;
+    } else if (op == OP_I || op == OP_S) {
+      y += (uint32_t)len;
+    }
   }
-  return nev;
 }
 
 __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
@@ -267,8 +238,229 @@ __device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
   return r;
 }
 
+// ---- phase 2: one 32-bit word (4 query bases, or 4 deletion columns) of one unit ---------------
+template <bool PACKED, bool SEEN>
+__device__ __forceinline__ void process_word(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen, const Unit u,
+                                             uint32_t wl, uint32_t w, uint32_t h) {
+  const int strand = (int)(u.flags & UF_STRAND);
+  const bool counted = (u.flags & UF_COUNTED) != 0;
+  const int lastcls = (u.flags >> 3) & 3;  // 0 none, 1 D, 2 I
+  const int indcls = lastcls == 1 ? LS_CLASS_D : LS_CLASS_I;
+  if (!(u.flags & UF_DEL)) {
+    const uint32_t a0 = (uint32_t)(u.qaddr & 3ull);  // first base's offset inside its word
+    const int rel0 = (int)(4u * wl) - (int)a0;       // unit-relative index of this word's first base
+    const int n = (int)u.n;
+    const bool full = rel0 >= 0 && rel0 + 4 <= n;
+    const int dl = lastcls ? (n - 1 - rel0) : -1;    // == j for the base that carries the indel
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t q = (w >> (8 * j)) & 255u;
+      bool ok = (int)q >= a.min_bq;
+      if (!full) ok = ok && (rel0 + j >= 0) && (rel0 + j < n);
+      const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
+      int cls = (int)((K1_CLASS_LUT >> (4 * code)) & 15ull);
+      if (dl == j) cls = indcls;
+      if (ok && cls != LS_CLASS_NA) {
+        const int s = (int)u.sbase + rel0 + j;
+        if (counted)
+          add_entry<PACKED, SEEN>(sm, seen, s, cls, q, strand);
+        else
+          add_uncounted<PACKED>(sm, s, cls);
+      }
+    }
+  } else {
+    const int n = (int)u.n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = (int)(4u * wl) + j;
+      if (col < n) {
+        const int cls = (lastcls && col == n - 1) ? indcls : LS_CLASS_O;
+        const int s = (int)u.sbase + col;
+        if (counted)
+          add_entry<PACKED, SEEN>(sm, seen, s, cls, (uint32_t)u.q, strand);
+        else
+          add_uncounted<PACKED>(sm, s, cls);
+      }
+    }
+  }
+}
+
+// find the unit that owns flattened word index wi: largest u with pre[u] <= wi
+__device__ __forceinline__ int find_unit(const uint32_t *pre, int U, uint32_t wi) {
+  int lo = 0, hi = U;
+  while (hi - lo > 1) {
+    const int m = (lo + hi) >> 1;
+    if (pre[m] <= wi)
+      lo = m;
+    else
+      hi = m;
+  }
+  return lo;
+}
+
+// Process the segments held by the lanes with `active` set (lane j: metadata mm).  Warp-cooperative.
+template <bool PACKED, bool SEEN>
+__device__ __forceinline__ void process_lanes(const CountArgs &a, TileSmemT<PACKED> &sm, int warp, int lane,
+                                              bool active, bool counted, SegMeta mm, int32_t tile_start,
+                                              int32_t tile_end) {
+  Unit *units = sm.units[warp];
+  uint32_t *pre = sm.upre[warp];
+  uint32_t *seen = sm.seen[warp];
+  uint32_t *ucount = &sm.ucount[warp];
+  bool pending = active;
+  while (__any_sync(0xffffffffu, pending)) {
+    if (lane == 0) *ucount = 0;
+    __syncwarp();
+    // ---- phase 1: lane = segment; walk the CIGAR, queue op pieces --------------------------
+    bool slow = false;
+    if (pending) {
+      pending = false;
+      int32_t x = mm.x0;
+      uint32_t y = mm.y0;
+      uint32_t k = mm.cig;
+      const uint32_t fl = (uint32_t)mm.strand | (counted ? UF_COUNTED : 0u);
+      while (k < mm.kend && x < tile_end) {
+        const uint32_t c = a.cigar[k];
+        const uint32_t op = c & 15u;
+        const int32_t len = (int32_t)(c >> 4);
+        const bool match = op_is_match(op);
+        if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
+          const int32_t last = x + len - 1;
+          int ind = 0;
+          if (last >= tile_start && last < tile_end) ind = indel_after(a.cigar, k, mm.kend, op);
+          const int32_t lo = x > tile_start ? x : tile_start;
+          const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
+          const uint32_t lastbits = ind < 0 ? (1u << 3) : (ind > 0 ? (2u << 3) : 0u);
+          Unit u;
+          bool emit = false;
+          if (match) {
+            if (y + (uint32_t)len > mm.lq) {  // CIGAR outruns the stored sequence: exact slow path
+              slow = true;
+              break;
+            }
+            u.qaddr = mm.boff + (uint64_t)(y + (uint32_t)(lo - x));
+            u.n = (uint16_t)(hi - lo);
+            u.sbase = (uint16_t)(lo - tile_start);
+            u.flags = (uint8_t)(fl | lastbits);
+            u.q = 0;
+            emit = true;
+          } else {
+            const uint32_t q = y < mm.lq ? a.qual[mm.boff + y] : 0u;
+            if ((int)q >= a.min_bq) {
+              if (op == OP_D) {
+                u.n = (uint16_t)(hi - lo);
+                u.sbase = (uint16_t)(lo - tile_start);
+                emit = true;
+              } else if (ind != 0) {  // ref-skip whose last column carries a following indel
+                u.n = 1;
+                u.sbase = (uint16_t)(last - tile_start);
+                emit = true;
+              }
+              u.qaddr = 0;
+              u.flags = (uint8_t)(fl | UF_DEL | lastbits);
+              u.q = (uint8_t)q;
+            }
+          }
+          if (emit) {
+            u.pad = 0;
+            const uint32_t slot = atomicAdd(ucount, 1u);
+            if (slot >= (uint32_t)K1_UNIT_CAP) {  // queue full: resume from this op in the next round
+              mm.cig = k;
+              mm.x0 = x;
+              mm.y0 = y;
+              pending = true;
+              break;
+            }
+            units[slot] = u;
+          }
+        }
+        if (match) {
+          x += len;
+          y += (uint32_t)len;
+        } else if (op == OP_D || op == OP_N) {
+          x += len;
+        } else if (op == OP_I || op == OP_S) {
+          y += (uint32_t)len;
+        }
+        ++k;
+      }
+      if (slow) {
+        mm.cig = k;
+        mm.x0 = x;
+        mm.y0 = y;
+      }
+    }
+    __syncwarp();
+    const int U = (int)min(*ucount, (uint32_t)K1_UNIT_CAP);
+    // ---- prefix of 32-bit words per unit ------------------------------------------------------
+    uint32_t carry = 0;
+    for (int base = 0; base < U; base += 32) {
+      const int ui = base + lane;
+      uint32_t nw = 0;
+      if (ui < U) {
+        const Unit u = units[ui];
+        nw = (u.flags & UF_DEL) ? (((uint32_t)u.n + 3u) >> 2)
+                                : ((((uint32_t)(u.qaddr & 3ull) + (uint32_t)u.n + 3u) >> 2));
+      }
+      uint32_t inc = nw;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      if (ui < U) pre[ui] = carry + inc - nw;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) pre[U] = carry;
+    __syncwarp();
+    const uint32_t W = carry;
+    // ---- phase 2: lane = word; two words in flight per lane -----------------------------------
+    for (uint32_t wbase = 0; wbase < W; wbase += 64u) {
+      const uint32_t wi0 = wbase + (uint32_t)lane, wi1 = wi0 + 32u;
+      Unit u0, u1;
+      uint32_t wl0 = 0, wl1 = 0, w0 = 0, h0 = 0, w1 = 0, h1 = 0;
+      const bool v0 = wi0 < W, v1 = wi1 < W;
+      if (v0) {
+        const int ui = find_unit(pre, U, wi0);
+        u0 = units[ui];
+        wl0 = wi0 - pre[ui];
+        if (!(u0.flags & UF_DEL)) {
+          const uint64_t g = (u0.qaddr & ~3ull) + 4ull * wl0;
+          w0 = *reinterpret_cast<const uint32_t *>(a.qual + g);
+          h0 = *reinterpret_cast<const uint16_t *>(a.seq4 + (g >> 1));
+        }
+      }
+      if (v1) {
+        const int ui = find_unit(pre, U, wi1);
+        u1 = units[ui];
+        wl1 = wi1 - pre[ui];
+        if (!(u1.flags & UF_DEL)) {
+          const uint64_t g = (u1.qaddr & ~3ull) + 4ull * wl1;
+          w1 = *reinterpret_cast<const uint32_t *>(a.qual + g);
+          h1 = *reinterpret_cast<const uint16_t *>(a.seq4 + (g >> 1));
+        }
+      }
+      if (v0) process_word<PACKED, SEEN>(a, sm, seen, u0, wl0, w0, h0);
+      if (v1) process_word<PACKED, SEEN>(a, sm, seen, u1, wl1, w1, h1);
+    }
+    __syncwarp();
+    // ---- exact slow path for the rare malformed record ---------------------------------------
+    uint32_t slowmask = __ballot_sync(0xffffffffu, slow);
+    while (slowmask) {
+      const int j = __ffs(slowmask) - 1;
+      slowmask &= slowmask - 1;
+      const SegMeta sm_j = shfl_meta(mm, j);
+      if (counted)
+        process_segment<PACKED, SEEN, true>(a, sm, seen, sm_j, tile_start, tile_end, lane);
+      else
+        process_segment<PACKED, SEEN, false>(a, sm, seen, sm_j, tile_start, tile_end, lane);
+    }
+    __syncwarp();
+  }
+}
+
 template <bool PACKED>
-__global__ void __launch_bounds__(K1_THREADS, 2) pileup_count_kernel(CountArgs a) {
+__global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
   const uint32_t part = blockIdx.x;
@@ -302,11 +494,10 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_count_kernel(CountArgs a
 
   const uint64_t cmask = (1ull << a.cell_bits) - 1ull;
   const uint64_t unc = (uint64_t)a.uncounted_key;
-  uint8_t *seen = sm.seen[warp];
-  uint32_t nev = 0;
+  uint32_t *seen = sm.seen[warp];
   const uint32_t nmine = my_hi - my_lo;
   uint32_t chunk = (nmine + K1_WARPS - 1) / K1_WARPS;
-  chunk = chunk < 4u ? 4u : (chunk > 32u ? 32u : chunk);
+  chunk = chunk < 8u ? 8u : (chunk > 32u ? 32u : chunk);
   for (;;) {
     uint32_t g = 0;
     if (lane == 0) g = atomicAdd(&sm.next, chunk);
@@ -326,29 +517,41 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_count_kernel(CountArgs a
       mm = load_meta(a, i);
     }
     const uint32_t startmask = __ballot_sync(0xffffffffu, start);
-    uint32_t rem = startmask;
+    const uint32_t validmask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
+    // a run that reaches the end of the chunk may continue into the following segments of the tile
+    const uint64_t lastkey = __shfl_sync(0xffffffffu, ck, n - 1);
+    uint32_t ext = 0;
+    if (lastkey != unc) {
+      while (cb + ext < slot_hi && (a.keys[cb + ext] & cmask) == lastkey) ++ext;
+    }
+    // lane j is a SINGLE run iff it starts a run and the next segment starts another one
+    const uint32_t next_start = (startmask >> 1) | ((n >= 32 || true) ? (ext == 0 ? (1u << (n - 1)) : 0u) : 0u);
+    const uint32_t singles = startmask & next_start & validmask;
+    const uint32_t unc_mask = __ballot_sync(0xffffffffu, lane < n && ck == unc);
+    // singles: counted first, then the (rare) visible-but-uncounted reads
+    if (singles & ~unc_mask)
+      process_lanes<PACKED, false>(a, sm, warp, lane, ((singles & ~unc_mask) >> lane) & 1u, true, mm, tile_start,
+                                   tile_end);
+    if (singles & unc_mask)
+      process_lanes<PACKED, false>(a, sm, warp, lane, ((singles & unc_mask) >> lane) & 1u, false, mm, tile_start,
+                                   tile_end);
+    // multi-segment runs that START in this chunk (leading lanes that continue an earlier run are skipped)
+    uint32_t rem = startmask & ~singles & validmask;
     while (rem) {
       const int j0 = __ffs(rem) - 1;
       rem &= rem - 1;
-      const int j1 = rem ? (__ffs(rem) - 1) : n;
-      const uint64_t rk = __shfl_sync(0xffffffffu, ck, j0);
-      const bool counted = rk != unc;
-      // a run that reaches the end of the chunk continues into the following segments of the tile
-      uint32_t ext = 0;
-      if (j1 == n && counted) {
-        while (cb + ext < slot_hi && (a.keys[cb + ext] & cmask) == rk) ++ext;
-      }
-      const uint32_t runlen = (uint32_t)(j1 - j0) + ext;
-      if (runlen == 1) {
-        nev += process_segment<PACKED, false>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, counted, lane);
-      } else {
-        uint32_t *s4 = reinterpret_cast<uint32_t *>(seen);
-        for (int q = lane; q < LS_TILE / 4; q += 32) s4[q] = 0u;
-        __syncwarp();
-        for (int j = j0; j < j1; ++j)
-          nev += process_segment<PACKED, true>(a, sm, seen, shfl_meta(mm, j), tile_start, tile_end, true, lane);
-        for (uint32_t e = 0; e < ext; ++e)
-          nev += process_segment<PACKED, true>(a, sm, seen, load_meta(a, cb + e), tile_start, tile_end, true, lane);
+      const uint32_t later = startmask & ~((2u << j0) - 1u) & validmask;
+      const int j1 = later ? (__ffs(later) - 1) : n;
+      for (int q = lane; q < LS_TILE / 4; q += 32) seen[q] = 0u;
+      __syncwarp();
+      process_lanes<PACKED, true>(a, sm, warp, lane, lane >= j0 && lane < j1, true, mm, tile_start, tile_end);
+      if (j1 == n) {
+        for (uint32_t e0 = 0; e0 < ext; e0 += 32u) {
+          const bool act = e0 + (uint32_t)lane < ext;
+          SegMeta me = {};
+          if (act) me = load_meta(a, cb + e0 + (uint32_t)lane);
+          process_lanes<PACKED, true>(a, sm, warp, lane, act, true, me, tile_start, tile_end);
+        }
       }
     }
   }
@@ -356,79 +559,87 @@ __global__ void __launch_bounds__(K1_THREADS, 2) pileup_count_kernel(CountArgs a
 
   // ---- site epilogue: gates of BaseCellCounter.py:211,220-222,282,294 -------------------
   uint32_t *out = a.out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
-  const int s = threadIdx.x;  // one site per thread
-  const int sidx = swz(s);
-  uint32_t f[8], r[8], bq[6];
-  uint32_t dp = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (PACKED) {
-      const uint32_t hf = sm.hist[k * 2][sidx], hr = sm.hist[k * 2 + 1][sidx];
-      f[k] = hf >> K1_CNT_SHIFT;
-      r[k] = hr >> K1_CNT_SHIFT;
-      if (k < 6) bq[k] = (hf & ((1u << K1_CNT_SHIFT) - 1u)) + (hr & ((1u << K1_CNT_SHIFT) - 1u));
-    } else {
-      f[k] = sm.hist[k * 2][sidx];
-      r[k] = sm.hist[k * 2 + 1][sidx];
-      if (k < 6) bq[k] = sm.hist[16 + k * 2][sidx] + sm.hist[16 + k * 2 + 1][sidx];
-    }
-    dp += f[k] + r[k];
-  }
-  const uint8_t rb = sm.ref[s];
-  uint32_t nc = dp - sm.dupnc[sidx];
-  uint32_t cc[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) cc[k] = f[k] + r[k] - sm.dupcc[k][sidx];
-  uint32_t ac = 0;
-  if (a.min_ac > 0) {
-    ac = sm.acx[sidx] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
-    const int base_cls[5] = {LS_CLASS_A, LS_CLASS_C, LS_CLASS_T, LS_CLASS_G, LS_CLASS_N};
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-      if (class_letter(base_cls[j]) != rb) ac += f[base_cls[j]] + r[base_cls[j]];
-  }
   bool last_part = true;
-  if (nparts > 1) {
-    // additive merge of this part's words into the tile's HBM slot; the last part applies the gates
-    if (dp) atomicAdd(&out[LS_SITE_DP * LS_TILE + s], dp);
-    if (nc) atomicAdd(&out[LS_SITE_NC * LS_TILE + s], nc);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      if (cc[k]) atomicAdd(&out[(LS_SITE_CC + k) * LS_TILE + s], cc[k]);
-      if (f[k]) atomicAdd(&out[(LS_SITE_BCF + k) * LS_TILE + s], f[k]);
-      if (r[k]) atomicAdd(&out[(LS_SITE_BCR + k) * LS_TILE + s], r[k]);
-      if (bq[k]) atomicAdd(&out[(LS_SITE_BQ + k) * LS_TILE + s], bq[k]);
-    }
-    if (a.min_ac > 0 && ac) atomicAdd(&a.acbuf[(size_t)slot * LS_TILE + s], ac);
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) sm.ticket = atomicAdd(&a.slot_done[slot], 1u);
-    __syncthreads();
-    last_part = sm.ticket == nparts - 1;
-    if (last_part) {
+  uint32_t nev = 0;
+  for (int pass_no = 0; pass_no < 2; ++pass_no) {
+    // pass 0: per-part words (direct store for single-part tiles, atomic merge otherwise)
+    // pass 1: only for the last part of a multi-part tile: gates on the merged totals
+    if (pass_no == 1) {
+      if (nparts == 1) break;
       __threadfence();
-      dp = __ldcg(&out[LS_SITE_DP * LS_TILE + s]);
-      nc = __ldcg(&out[LS_SITE_NC * LS_TILE + s]);
-      if (a.min_ac > 0) ac = __ldcg(&a.acbuf[(size_t)slot * LS_TILE + s]);
+      __syncthreads();
+      if (threadIdx.x == 0) sm.ticket = atomicAdd(&a.slot_done[slot], 1u);
+      __syncthreads();
+      last_part = sm.ticket == nparts - 1;
+      if (!last_part) break;
+      __threadfence();
     }
-  }
-  if (last_part) {
-    bool pass = (tile_start + s < tile_end) && rb != 'N' && dp > 0 && (int)dp >= a.min_dp && (int)nc >= a.min_cc;
-    if (pass && a.min_ac > 0) pass = (int)ac >= a.min_ac;
-    const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) {
-      a.mask[(size_t)slot * (LS_TILE / 32) + (s >> 5)] = bal;
-      if (bal) atomicAdd(&sm.npass, (uint32_t)__popc(bal));
-    }
-    if (pass && nparts == 1) {
-      out[LS_SITE_DP * LS_TILE + s] = dp;
-      out[LS_SITE_NC * LS_TILE + s] = nc;
+    for (int s = threadIdx.x; s < LS_TILE; s += K1_THREADS) {
+      const int sidx = swz(s);
+      const uint8_t rb = sm.ref[s];
+      uint32_t dp = 0, nc = 0, ac = 0;
+      uint32_t f[8], r[8], bq[6], cc[6];
+      if (pass_no == 0) {
 #pragma unroll
-      for (int k = 0; k < 6; ++k) {
-        out[(LS_SITE_CC + k) * LS_TILE + s] = cc[k];
-        out[(LS_SITE_BCF + k) * LS_TILE + s] = f[k];
-        out[(LS_SITE_BCR + k) * LS_TILE + s] = r[k];
-        out[(LS_SITE_BQ + k) * LS_TILE + s] = bq[k];
+        for (int k = 0; k < 8; ++k) {
+          if (PACKED) {
+            const uint32_t hf = sm.hist[k * 2][sidx], hr = sm.hist[k * 2 + 1][sidx];
+            f[k] = hf >> K1_CNT_SHIFT;
+            r[k] = hr >> K1_CNT_SHIFT;
+            if (k < 6) bq[k] = (hf & ((1u << K1_CNT_SHIFT) - 1u)) + (hr & ((1u << K1_CNT_SHIFT) - 1u));
+          } else {
+            f[k] = sm.hist[k * 2][sidx];
+            r[k] = sm.hist[k * 2 + 1][sidx];
+            if (k < 6) bq[k] = sm.hist[16 + k * 2][sidx] + sm.hist[16 + k * 2 + 1][sidx];
+          }
+          dp += f[k] + r[k];
+        }
+        nev += dp;
+        nc = dp - sm.dupnc[sidx];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cc[k] = f[k] + r[k] - sm.dupcc[k][sidx];
+        if (a.min_ac > 0) {
+          ac = sm.acx[sidx] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
+          const int base_cls[5] = {LS_CLASS_A, LS_CLASS_C, LS_CLASS_T, LS_CLASS_G, LS_CLASS_N};
+#pragma unroll
+          for (int j = 0; j < 5; ++j)
+            if (class_letter(base_cls[j]) != rb) ac += f[base_cls[j]] + r[base_cls[j]];
+        }
+        if (nparts > 1) {
+          if (dp) atomicAdd(&out[LS_SITE_DP * LS_TILE + s], dp);
+          if (nc) atomicAdd(&out[LS_SITE_NC * LS_TILE + s], nc);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            if (cc[k]) atomicAdd(&out[(LS_SITE_CC + k) * LS_TILE + s], cc[k]);
+            if (f[k]) atomicAdd(&out[(LS_SITE_BCF + k) * LS_TILE + s], f[k]);
+            if (r[k]) atomicAdd(&out[(LS_SITE_BCR + k) * LS_TILE + s], r[k]);
+            if (bq[k]) atomicAdd(&out[(LS_SITE_BQ + k) * LS_TILE + s], bq[k]);
+          }
+          if (a.min_ac > 0 && ac) atomicAdd(&a.acbuf[(size_t)slot * LS_TILE + s], ac);
+          continue;  // gates are applied in pass 1 by the last part
+        }
+      } else {
+        dp = __ldcg(&out[LS_SITE_DP * LS_TILE + s]);
+        nc = __ldcg(&out[LS_SITE_NC * LS_TILE + s]);
+        if (a.min_ac > 0) ac = __ldcg(&a.acbuf[(size_t)slot * LS_TILE + s]);
+      }
+      bool pass = (tile_start + s < tile_end) && rb != 'N' && dp > 0 && (int)dp >= a.min_dp && (int)nc >= a.min_cc;
+      if (pass && a.min_ac > 0) pass = (int)ac >= a.min_ac;
+      const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+      if (lane == 0) {
+        a.mask[(size_t)slot * (LS_TILE / 32) + (s >> 5)] = bal;
+        if (bal) atomicAdd(&sm.npass, (uint32_t)__popc(bal));
+      }
+      if (pass && pass_no == 0) {
+        out[LS_SITE_DP * LS_TILE + s] = dp;
+        out[LS_SITE_NC * LS_TILE + s] = nc;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          out[(LS_SITE_CC + k) * LS_TILE + s] = cc[k];
+          out[(LS_SITE_BCF + k) * LS_TILE + s] = f[k];
+          out[(LS_SITE_BCR + k) * LS_TILE + s] = r[k];
+          out[(LS_SITE_BQ + k) * LS_TILE + s] = bq[k];
+        }
       }
     }
   }
