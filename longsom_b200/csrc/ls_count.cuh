@@ -7,17 +7,15 @@
 // exact and every output word is additive across parts; multi-part tiles add into their HBM
 // slot and the last part to finish applies the reference's gates.
 //
-// Inside a part (CTA of 8 warps, tile accumulators in shared memory) a warp grabs a chunk of
-// <= 32 segments and processes it in two phases so that global-memory latency is paid once
-// per chunk, not once per segment:
-//   phase 1 (lane = segment): every lane loads its segment record + read metadata and walks its
-//     own CIGAR; each op piece inside the tile becomes a 16-byte UNIT in a per-warp shared queue
-//     (first base address, length, first site, strand, indel class of the last base);
-//   phase 2 (lane = 4 query bases): the units' 32-bit quality words are flattened into one
-//     index space; lane L takes words L, L+32, ... (binary search in the unit prefix table),
-//     two words in flight per lane; per word one aligned 32-bit load of qualities and one
-//     16-bit load of 4-bit bases, 4 classifications, ONE packed shared atomic per visible base
-//     (count<<20 | quality).  Lanes are fully used however short the op pieces are.
+// Inside a part (CTA of 8 warps, tile accumulators in shared memory):
+//   * a warp grabs a chunk of <= 32 segments; lane j loads segment j's record and read
+//     metadata (one global-latency for the whole chunk instead of one per segment);
+//   * per segment the lanes fetch the next 32 CIGAR ops at once, then walk them warp-uniformly;
+//   * a match op is consumed 128 query bases per step: lane L loads one aligned 32-bit word of
+//     qualities and one 16-bit word of 4-bit bases (vectorised, coalesced), classifies its 4
+//     bases and issues ONE packed shared atomic per visible base (count<<20 | quality).
+// (A two-phase variant that flattens op pieces into a per-warp unit queue was measured 1.8x
+//  slower on C2 -- register spills and the per-word unit search cost more than the idle lanes.)
 // Distinct-cell counts: NC/CC = reads minus same-cell duplicates.  Runs of >1 same-cell
 // segments mark (site, class) bits with atomicOr in a per-warp seen[] array, so the order in
 // which a run's bases are visited does not matter; single-segment runs skip this entirely.
@@ -30,7 +28,6 @@ constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_PART_SEGS = 2048;       // nominal segments per part
 constexpr int K1_MAX_RUN_PACKED = 2039;  // packed counters (12-bit) need: part segs + run extension <= 4095
 constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
-constexpr int K1_UNIT_CAP = 128;         // op pieces queued per warp per phase-1 round
 
 static_assert(LS_TILE % 128 == 0 && LS_TILE % K1_THREADS == 0 && LS_TILE <= 65536, "tile / block shape");
 
@@ -65,19 +62,6 @@ struct CountArgs {
   int min_bq, min_dp, min_cc, min_ac;
 };
 
-// one op piece inside the tile
-struct __align__(16) Unit {
-  uint64_t qaddr;  // match: index of the first base in qual[] (read base offset + query index)
-  uint16_t n;      // bases (match) / columns (deletion)
-  uint16_t sbase;  // site (tile-relative) of the first base / column
-  uint8_t flags;   // bit0 strand, bit1 counted, bit2 deletion-kind, bits 3-4 class of the LAST base: 1 = D, 2 = I
-  uint8_t q;       // deletion-kind: the quality shared by all its columns
-  uint16_t pad;
-};
-#define UF_STRAND 1u
-#define UF_COUNTED 2u
-#define UF_DEL 4u
-
 template <bool PACKED>
 struct TileSmemT {
   uint32_t hist[PACKED ? 16 : 32][LS_TILE];  // PACKED: [cls*2+strand] = cnt<<20|bq ; else [0..15] cnt, [16..31] bq
@@ -85,9 +69,6 @@ struct TileSmemT {
   uint32_t dupnc[LS_TILE];                   // entries whose cell was already seen at the site (any class)
   uint32_t acx[LS_TILE];                     // alt entries of visible-but-uncounted reads (--min_ac > 0)
   uint32_t seen[K1_WARPS][LS_TILE / 4];      // per warp: class bits (1 byte per site) of the current same-cell run
-  Unit units[K1_WARPS][K1_UNIT_CAP];
-  uint32_t upre[K1_WARPS][K1_UNIT_CAP + 1];  // exclusive prefix of 32-bit words per unit
-  uint32_t ucount[K1_WARPS];
   uint8_t ref[LS_TILE];
   uint32_t next, npass, ticket;
 };
@@ -141,78 +122,6 @@ struct SegMeta {
   int strand;
 };
 
-// ---- slow path: one segment, warp-cooperative CIGAR walk (used for queue overflow and malformed
-// records whose CIGAR outruns the stored sequence) -----------------------------------------------
-template <bool PACKED, bool SEEN, bool COUNTED>
-__device__ __noinline__ void process_segment(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen,
-                                             const SegMeta m, int32_t tile_start, int32_t tile_end, int lane) {
-  const uint8_t *__restrict__ qual = a.qual + m.boff;
-  const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
-  const int strand = m.strand;
-  const uint32_t lq = m.lq;
-  int32_t x = m.x0;
-  uint32_t y = m.y0;
-  for (uint32_t k = m.cig; k < m.kend && x < tile_end; ++k) {
-    const uint32_t c = a.cigar[k];
-    const uint32_t op = c & 15u;
-    const int32_t len = (int32_t)(c >> 4);
-    const bool match = op_is_match(op);
-    if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
-      const int32_t last = x + len - 1;
-      int ind = 0;
-      if (last >= tile_start && last < tile_end) ind = indel_after(a.cigar, k, m.kend, op);
-      const int32_t lo = x > tile_start ? x : tile_start;
-      const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
-      if (op == OP_N) {
-        if (ind != 0 && lane == 0) {
-          const uint32_t q = y < lq ? qual[y] : 0u;
-          if ((int)q >= a.min_bq) {
-            const int cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-            if (COUNTED)
-              add_entry<PACKED, SEEN>(sm, seen, last - tile_start, cls, q, strand);
-            else
-              add_uncounted<PACKED>(sm, last - tile_start, cls);
-          }
-        }
-      } else {
-        for (int32_t p = lo + lane; p < hi; p += 32) {
-          const uint32_t qpos = match ? y + (uint32_t)(p - x) : y;
-          const uint32_t q = qpos < lq ? qual[qpos] : 0u;
-          if ((int)q >= a.min_bq) {
-            int cls;
-            if (p == last && ind != 0) {
-              cls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-            } else if (match) {
-              uint32_t code = 15u;
-              if (qpos < lq) {
-                const uint32_t b = seq4[qpos >> 1];
-                code = (qpos & 1u) ? (b & 15u) : (b >> 4);
-              }
-              cls = class_of_code(code);
-            } else {
-              cls = LS_CLASS_O;
-            }
-            if (cls != LS_CLASS_NA) {
-              if (COUNTED)
-                add_entry<PACKED, SEEN>(sm, seen, p - tile_start, cls, q, strand);
-              else
-                add_uncounted<PACKED>(sm, p - tile_start, cls);
-            }
-          }
-        }
-      }
-    }
-    if (match) {
-      x += len;
-      y += (uint32_t)len;
-    } else if (op == OP_D || op == OP_N) {
-      x += len;
-    } else if (op == OP_I || op == OP_S) {
-      y += (uint32_t)len;
-    }
-  }
-}
-
 __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
   const Segment sg = a.segs[a.vals[i]];
   SegMeta m;
@@ -238,224 +147,112 @@ __device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
   return r;
 }
 
-// ---- phase 2: one 32-bit word (4 query bases, or 4 deletion columns) of one unit ---------------
-template <bool PACKED, bool SEEN>
-__device__ __forceinline__ void process_word(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen, const Unit u,
-                                             uint32_t wl, uint32_t w, uint32_t h) {
-  const int strand = (int)(u.flags & UF_STRAND);
-  const bool counted = (u.flags & UF_COUNTED) != 0;
-  const int lastcls = (u.flags >> 3) & 3;  // 0 none, 1 D, 2 I
-  const int indcls = lastcls == 1 ? LS_CLASS_D : LS_CLASS_I;
-  if (!(u.flags & UF_DEL)) {
-    const uint32_t a0 = (uint32_t)(u.qaddr & 3ull);  // first base's offset inside its word
-    const int rel0 = (int)(4u * wl) - (int)a0;       // unit-relative index of this word's first base
-    const int n = (int)u.n;
-    const bool full = rel0 >= 0 && rel0 + 4 <= n;
-    const int dl = lastcls ? (n - 1 - rel0) : -1;    // == j for the base that carries the indel
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t q = (w >> (8 * j)) & 255u;
-      bool ok = (int)q >= a.min_bq;
-      if (!full) ok = ok && (rel0 + j >= 0) && (rel0 + j < n);
-      const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
-      int cls = (int)((K1_CLASS_LUT >> (4 * code)) & 15ull);
-      if (dl == j) cls = indcls;
-      if (ok && cls != LS_CLASS_NA) {
-        const int s = (int)u.sbase + rel0 + j;
-        if (counted)
-          add_entry<PACKED, SEEN>(sm, seen, s, cls, q, strand);
-        else
-          add_uncounted<PACKED>(sm, s, cls);
-      }
-    }
-  } else {
-    const int n = (int)u.n;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = (int)(4u * wl) + j;
-      if (col < n) {
-        const int cls = (lastcls && col == n - 1) ? indcls : LS_CLASS_O;
-        const int s = (int)u.sbase + col;
-        if (counted)
-          add_entry<PACKED, SEEN>(sm, seen, s, cls, (uint32_t)u.q, strand);
-        else
-          add_uncounted<PACKED>(sm, s, cls);
-      }
-    }
-  }
-}
-
-// find the unit that owns flattened word index wi: largest u with pre[u] <= wi
-__device__ __forceinline__ int find_unit(const uint32_t *pre, int U, uint32_t wi) {
-  int lo = 0, hi = U;
-  while (hi - lo > 1) {
-    const int m = (lo + hi) >> 1;
-    if (pre[m] <= wi)
-      lo = m;
-    else
-      hi = m;
-  }
-  return lo;
-}
-
-// Process the segments held by the lanes with `active` set (lane j: metadata mm).  Warp-cooperative.
-template <bool PACKED, bool SEEN>
-__device__ __forceinline__ void process_lanes(const CountArgs &a, TileSmemT<PACKED> &sm, int warp, int lane,
-                                              bool active, bool counted, SegMeta mm, int32_t tile_start,
-                                              int32_t tile_end) {
-  Unit *units = sm.units[warp];
-  uint32_t *pre = sm.upre[warp];
-  uint32_t *seen = sm.seen[warp];
-  uint32_t *ucount = &sm.ucount[warp];
-  bool pending = active;
-  while (__any_sync(0xffffffffu, pending)) {
-    if (lane == 0) *ucount = 0;
-    __syncwarp();
-    // ---- phase 1: lane = segment; walk the CIGAR, queue op pieces --------------------------
-    bool slow = false;
-    if (pending) {
-      pending = false;
-      int32_t x = mm.x0;
-      uint32_t y = mm.y0;
-      uint32_t k = mm.cig;
-      const uint32_t fl = (uint32_t)mm.strand | (counted ? UF_COUNTED : 0u);
-      while (k < mm.kend && x < tile_end) {
-        const uint32_t c = a.cigar[k];
-        const uint32_t op = c & 15u;
-        const int32_t len = (int32_t)(c >> 4);
-        const bool match = op_is_match(op);
-        if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
-          const int32_t last = x + len - 1;
-          int ind = 0;
-          if (last >= tile_start && last < tile_end) ind = indel_after(a.cigar, k, mm.kend, op);
-          const int32_t lo = x > tile_start ? x : tile_start;
-          const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
-          const uint32_t lastbits = ind < 0 ? (1u << 3) : (ind > 0 ? (2u << 3) : 0u);
-          Unit u;
-          bool emit = false;
-          if (match) {
-            if (y + (uint32_t)len > mm.lq) {  // CIGAR outruns the stored sequence: exact slow path
-              slow = true;
-              break;
-            }
-            u.qaddr = mm.boff + (uint64_t)(y + (uint32_t)(lo - x));
-            u.n = (uint16_t)(hi - lo);
-            u.sbase = (uint16_t)(lo - tile_start);
-            u.flags = (uint8_t)(fl | lastbits);
-            u.q = 0;
-            emit = true;
-          } else {
-            const uint32_t q = y < mm.lq ? a.qual[mm.boff + y] : 0u;
-            if ((int)q >= a.min_bq) {
-              if (op == OP_D) {
-                u.n = (uint16_t)(hi - lo);
-                u.sbase = (uint16_t)(lo - tile_start);
-                emit = true;
-              } else if (ind != 0) {  // ref-skip whose last column carries a following indel
-                u.n = 1;
-                u.sbase = (uint16_t)(last - tile_start);
-                emit = true;
+// ---- fast path: one segment, warp-cooperative; CIGAR ops fetched 32 at a time, match ops consumed
+// 128 query bases per step (4 per lane, one 32-bit quality word + one 16-bit base word) -----------
+template <bool PACKED, bool SEEN, bool COUNTED>
+__device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen,
+                                                     const SegMeta m, int32_t tile_start, int32_t tile_end,
+                                                     int lane) {
+  const uint8_t *__restrict__ qual = a.qual + m.boff;
+  const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
+  const int strand = m.strand;
+  const uint32_t lq = m.lq;
+  int32_t x = m.x0;
+  uint32_t y = m.y0;
+  uint32_t k = m.cig;
+  while (k < m.kend && x < tile_end) {
+    const uint32_t kk = k + (uint32_t)lane;
+    const uint32_t c_l = kk < m.kend ? a.cigar[kk] : 0xfu;
+    const uint32_t c_n = kk + 1 < m.kend ? a.cigar[kk + 1] : 0xfu;
+    const int nwin = (int)((m.kend - k) < 32u ? (m.kend - k) : 32u);
+    for (int t = 0; t < nwin && x < tile_end; ++t) {
+      const uint32_t c = __shfl_sync(0xffffffffu, c_l, t);
+      const uint32_t cn = __shfl_sync(0xffffffffu, c_n, t);
+      const uint32_t op = c & 15u;
+      const int32_t len = (int32_t)(c >> 4);
+      const bool match = op_is_match(op);
+      if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
+        const int32_t last = x + len - 1;
+        int ind = 0;
+        if (last >= tile_start && last < tile_end) {
+          const uint32_t op2 = cn & 15u;
+          if (op2 == OP_D && op != OP_D)
+            ind = -1;
+          else if (op2 == OP_I)
+            ind = 1;
+          else if (op2 == OP_P)
+            ind = indel_after(a.cigar, k + (uint32_t)t, m.kend, op);
+        }
+        const int indcls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
+        const int32_t lo = x > tile_start ? x : tile_start;
+        const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
+        if (!match) {  // deletion / ref-skip: every column carries the quality of the next query base
+          const uint32_t q = y < lq ? qual[y] : 0u;
+          if ((int)q >= a.min_bq) {
+            if (op == OP_D) {
+              for (int32_t p = lo + lane; p < hi; p += 32) {
+                const int cls = (p == last && ind != 0) ? indcls : LS_CLASS_O;
+                if (COUNTED)
+                  add_entry<PACKED, SEEN>(sm, seen, p - tile_start, cls, q, strand);
+                else
+                  add_uncounted<PACKED>(sm, p - tile_start, cls);
               }
-              u.qaddr = 0;
-              u.flags = (uint8_t)(fl | UF_DEL | lastbits);
-              u.q = (uint8_t)q;
+            } else if (ind != 0 && lane == 0) {
+              if (COUNTED)
+                add_entry<PACKED, SEEN>(sm, seen, last - tile_start, indcls, q, strand);
+              else
+                add_uncounted<PACKED>(sm, last - tile_start, indcls);
             }
           }
-          if (emit) {
-            u.pad = 0;
-            const uint32_t slot = atomicAdd(ucount, 1u);
-            if (slot >= (uint32_t)K1_UNIT_CAP) {  // queue full: resume from this op in the next round
-              mm.cig = k;
-              mm.x0 = x;
-              mm.y0 = y;
-              pending = true;
-              break;
-            }
-            units[slot] = u;
-          }
-        }
-        if (match) {
-          x += len;
-          y += (uint32_t)len;
-        } else if (op == OP_D || op == OP_N) {
-          x += len;
-        } else if (op == OP_I || op == OP_S) {
-          y += (uint32_t)len;
-        }
-        ++k;
-      }
-      if (slow) {
-        mm.cig = k;
-        mm.x0 = x;
-        mm.y0 = y;
-      }
-    }
-    __syncwarp();
-    const int U = (int)min(*ucount, (uint32_t)K1_UNIT_CAP);
-    // ---- prefix of 32-bit words per unit ------------------------------------------------------
-    uint32_t carry = 0;
-    for (int base = 0; base < U; base += 32) {
-      const int ui = base + lane;
-      uint32_t nw = 0;
-      if (ui < U) {
-        const Unit u = units[ui];
-        nw = (u.flags & UF_DEL) ? (((uint32_t)u.n + 3u) >> 2)
-                                : ((((uint32_t)(u.qaddr & 3ull) + (uint32_t)u.n + 3u) >> 2));
-      }
-      uint32_t inc = nw;
+        } else {
+          const uint32_t ya = y + (uint32_t)(lo - x), yb = y + (uint32_t)(hi - x);  // query range inside the tile
+          const uint32_t ybl = yb < lq ? yb : lq;                                    // bases that exist
+          const int sbase = lo - tile_start;
+          const uint32_t ylast = (ind != 0) ? (y + (uint32_t)len - 1u) : 0xffffffffu;
+          for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < ybl; g += 128u) {
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
+            const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
+            const int sg = sbase + (int)(g - ya);  // site of the word's first base (-3..-1 possible in the head word)
+            const bool full = g >= ya && g + 4u <= ybl;
+            const uint32_t dl = ylast - g;  // == j for the base that carries the indel
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      if (ui < U) pre[ui] = carry + inc - nw;
-      carry += __shfl_sync(0xffffffffu, inc, 31);
-    }
-    if (lane == 0) pre[U] = carry;
-    __syncwarp();
-    const uint32_t W = carry;
-    // ---- phase 2: lane = word; two words in flight per lane -----------------------------------
-    for (uint32_t wbase = 0; wbase < W; wbase += 64u) {
-      const uint32_t wi0 = wbase + (uint32_t)lane, wi1 = wi0 + 32u;
-      Unit u0, u1;
-      uint32_t wl0 = 0, wl1 = 0, w0 = 0, h0 = 0, w1 = 0, h1 = 0;
-      const bool v0 = wi0 < W, v1 = wi1 < W;
-      if (v0) {
-        const int ui = find_unit(pre, U, wi0);
-        u0 = units[ui];
-        wl0 = wi0 - pre[ui];
-        if (!(u0.flags & UF_DEL)) {
-          const uint64_t g = (u0.qaddr & ~3ull) + 4ull * wl0;
-          w0 = *reinterpret_cast<const uint32_t *>(a.qual + g);
-          h0 = *reinterpret_cast<const uint16_t *>(a.seq4 + (g >> 1));
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t q = (w >> (8 * j)) & 255u;
+              bool ok = (int)q >= a.min_bq;
+              if (!full) ok = ok && (g + (uint32_t)j >= ya) && (g + (uint32_t)j < ybl);
+              const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
+              int cls = (int)((K1_CLASS_LUT >> (4 * code)) & 15ull);
+              if (dl == (uint32_t)j) cls = indcls;
+              if (ok && cls != LS_CLASS_NA) {
+                if (COUNTED)
+                  add_entry<PACKED, SEEN>(sm, seen, sg + j, cls, q, strand);
+                else
+                  add_uncounted<PACKED>(sm, sg + j, cls);
+              }
+            }
+          }
+          // query positions past the stored sequence (malformed record): base 'N', quality 0
+          if (yb > lq && a.min_bq <= 0) {
+            for (uint32_t qp = (ya > lq ? ya : lq) + (uint32_t)lane; qp < yb; qp += 32u) {
+              const int cls = (qp == ylast) ? indcls : LS_CLASS_N;
+              if (COUNTED)
+                add_entry<PACKED, SEEN>(sm, seen, sbase + (int)(qp - ya), cls, 0u, strand);
+              else
+                add_uncounted<PACKED>(sm, sbase + (int)(qp - ya), cls);
+            }
+          }
         }
       }
-      if (v1) {
-        const int ui = find_unit(pre, U, wi1);
-        u1 = units[ui];
-        wl1 = wi1 - pre[ui];
-        if (!(u1.flags & UF_DEL)) {
-          const uint64_t g = (u1.qaddr & ~3ull) + 4ull * wl1;
-          w1 = *reinterpret_cast<const uint32_t *>(a.qual + g);
-          h1 = *reinterpret_cast<const uint16_t *>(a.seq4 + (g >> 1));
-        }
+      if (match) {
+        x += len;
+        y += (uint32_t)len;
+      } else if (op == OP_D || op == OP_N) {
+        x += len;
+      } else if (op == OP_I || op == OP_S) {
+        y += (uint32_t)len;
       }
-      if (v0) process_word<PACKED, SEEN>(a, sm, seen, u0, wl0, w0, h0);
-      if (v1) process_word<PACKED, SEEN>(a, sm, seen, u1, wl1, w1, h1);
     }
-    __syncwarp();
-    // ---- exact slow path for the rare malformed record ---------------------------------------
-    uint32_t slowmask = __ballot_sync(0xffffffffu, slow);
-    while (slowmask) {
-      const int j = __ffs(slowmask) - 1;
-      slowmask &= slowmask - 1;
-      const SegMeta sm_j = shfl_meta(mm, j);
-      if (counted)
-        process_segment<PACKED, SEEN, true>(a, sm, seen, sm_j, tile_start, tile_end, lane);
-      else
-        process_segment<PACKED, SEEN, false>(a, sm, seen, sm_j, tile_start, tile_end, lane);
-    }
-    __syncwarp();
+    k += (uint32_t)nwin;
   }
 }
 
@@ -497,7 +294,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
   uint32_t *seen = sm.seen[warp];
   const uint32_t nmine = my_hi - my_lo;
   uint32_t chunk = (nmine + K1_WARPS - 1) / K1_WARPS;
-  chunk = chunk < 8u ? 8u : (chunk > 32u ? 32u : chunk);
+  chunk = chunk < 4u ? 4u : (chunk > 32u ? 32u : chunk);
   for (;;) {
     uint32_t g = 0;
     if (lane == 0) g = atomicAdd(&sm.next, chunk);
@@ -517,41 +314,31 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
       mm = load_meta(a, i);
     }
     const uint32_t startmask = __ballot_sync(0xffffffffu, start);
-    const uint32_t validmask = n >= 32 ? 0xffffffffu : ((1u << n) - 1u);
-    // a run that reaches the end of the chunk may continue into the following segments of the tile
-    const uint64_t lastkey = __shfl_sync(0xffffffffu, ck, n - 1);
-    uint32_t ext = 0;
-    if (lastkey != unc) {
-      while (cb + ext < slot_hi && (a.keys[cb + ext] & cmask) == lastkey) ++ext;
-    }
-    // lane j is a SINGLE run iff it starts a run and the next segment starts another one
-    const uint32_t next_start = (startmask >> 1) | ((n >= 32 || true) ? (ext == 0 ? (1u << (n - 1)) : 0u) : 0u);
-    const uint32_t singles = startmask & next_start & validmask;
-    const uint32_t unc_mask = __ballot_sync(0xffffffffu, lane < n && ck == unc);
-    // singles: counted first, then the (rare) visible-but-uncounted reads
-    if (singles & ~unc_mask)
-      process_lanes<PACKED, false>(a, sm, warp, lane, ((singles & ~unc_mask) >> lane) & 1u, true, mm, tile_start,
-                                   tile_end);
-    if (singles & unc_mask)
-      process_lanes<PACKED, false>(a, sm, warp, lane, ((singles & unc_mask) >> lane) & 1u, false, mm, tile_start,
-                                   tile_end);
-    // multi-segment runs that START in this chunk (leading lanes that continue an earlier run are skipped)
-    uint32_t rem = startmask & ~singles & validmask;
+    uint32_t rem = startmask;
     while (rem) {
       const int j0 = __ffs(rem) - 1;
       rem &= rem - 1;
-      const uint32_t later = startmask & ~((2u << j0) - 1u) & validmask;
-      const int j1 = later ? (__ffs(later) - 1) : n;
-      for (int q = lane; q < LS_TILE / 4; q += 32) seen[q] = 0u;
-      __syncwarp();
-      process_lanes<PACKED, true>(a, sm, warp, lane, lane >= j0 && lane < j1, true, mm, tile_start, tile_end);
-      if (j1 == n) {
-        for (uint32_t e0 = 0; e0 < ext; e0 += 32u) {
-          const bool act = e0 + (uint32_t)lane < ext;
-          SegMeta me = {};
-          if (act) me = load_meta(a, cb + e0 + (uint32_t)lane);
-          process_lanes<PACKED, true>(a, sm, warp, lane, act, true, me, tile_start, tile_end);
-        }
+      const int j1 = rem ? (__ffs(rem) - 1) : n;
+      const uint64_t rk = __shfl_sync(0xffffffffu, ck, j0);
+      const bool counted = rk != unc;
+      // a run that reaches the end of the chunk continues into the following segments of the tile
+      uint32_t ext = 0;
+      if (j1 == n && counted) {
+        while (cb + ext < slot_hi && (a.keys[cb + ext] & cmask) == rk) ++ext;
+      }
+      const uint32_t runlen = (uint32_t)(j1 - j0) + ext;
+      if (runlen == 1) {
+        if (counted)
+          process_segment_fast<PACKED, false, true>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane);
+        else
+          process_segment_fast<PACKED, false, false>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane);
+      } else {
+        for (int q = lane; q < LS_TILE / 4; q += 32) seen[q] = 0u;
+        __syncwarp();
+        for (int j = j0; j < j1; ++j)
+          process_segment_fast<PACKED, true, true>(a, sm, seen, shfl_meta(mm, j), tile_start, tile_end, lane);
+        for (uint32_t e = 0; e < ext; ++e)
+          process_segment_fast<PACKED, true, true>(a, sm, seen, load_meta(a, cb + e), tile_start, tile_end, lane);
       }
     }
   }
