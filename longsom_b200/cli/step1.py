@@ -1,0 +1,291 @@
+"""Drop-in BaseCellCalling.step1 (reference: workflow/scripts/SNVCalling/BaseCellCalling.step1.py).
+
+The reference streams the merged table and, per site and cell type, calls scipy's scalar
+betabinom.sf 2-12 times (~100 us each, :196,201,329-330).  Here the table is parsed once, every
+(k, n) query of the run is gathered into two arrays (read counts with alpha1/beta1, cell counts
+with alpha2/beta2), the tails are computed in two GPU launches (K2, ls_betabinom_sf), and the
+label cascade is applied on the rounded p-values exactly as the
+reference does.  Output bytes are identical, including its quirks (Q5-Q8)."""
+import argparse
+import sys
+import timeit
+
+import numpy as np
+
+from .. import bamio
+from ..engine import Engine
+from ..pipeline import devices_from_env
+
+ALLELES = ["A", "C", "T", "G", "I", "D", "N", "O"]  # step1.py:20 (the count vectors only carry the first six)
+
+INFO_HEADER = [  # step1.py:48-70
+    ('ALT', "##INFO=ALT,Description=Alternative alleles found"),
+    ('FILTER', "##INFO=FILTER,Description=Filter status of the variant site"),
+    ('Cell_types', "##INFO=Cell_types,Description=Cell type/s with the variant"),
+    ('Up_context', "##INFO=Up_context,Description=Up-stream bases in reference (4 bases)"),
+    ('Down_context', "##INFO=Down_context,Description=Down-stream bases in reference (4 bases)"),
+    ('N_ALT', "##INFO=N_ALT,Description=Cell type/s with the variant"),
+    ('Dp', "##INFO=Dp,Description=Depth of coverage (reads) in the cell type supporting the variant"),
+    ('Nc', "##INFO=Nc,Description=Number of distinct cells found in the cell type with the mutation"),
+    ('Bc', "##INFO=Bc,Description=Number of reads (base count) supporting the variants in the cell type with the mutation"),
+    ('Cc', "##INFO=Cc,Description=Number of distinct cells supporting the variant in the cell type with the mutation"),
+    ('VAF', "##INFO=VAF,Description=Variant allele frequency of variant in the cell type with the mutation"),
+    ('MCF', "##INFO=MCF,Description=Cancer cell fraction (fraction of ditinct cells) supporting the alternative allele in the cell type with the mutation"),
+    ('BCp', "##INFO=BCp,Description=Beta-binomial p-value for the variant allele (considering read counts)"),
+    ('CCp', "##INFO=CCp,Description=Beta-binomial p-value for the variant allele (considering cell counts)"),
+    ('Cell_types_min_BC', "##INFO=Cell_types_min_BC,Description=Number of cell types with a minimum number of reads covering a site"),
+    ('Cell_types_min_CC', "##INFO=Cell_types_min_CC,Description=Number of cell types with a minimum number of distinct cells found in a specific site"),
+    ('Rest_BC', "##INFO=Rest_BC,Description=Base counts (reads) supporting other alternative alleles in this site. BC;DP;P-value (betabin)"),
+    ('Rest_CC', "##INFO=Rest_CC,Description=Cell counts supporting other alternative alleles in this site. CC;NC;P-value (betabin)"),
+    ('Fisher_p', "##INFO=Fisher_p,Description=Strand bias test. Fisher exact test p-value between forward and reverse reads in variant and reference allele"),
+    ('Cell_type_Filter', "##INFO=Cell_type_Filter,Description=Filter status of the variant site in each cell type"),
+]
+
+
+def longest_run(s):
+    """Length of the longest run of equal characters (step1.py:478-483)."""
+    best, cur = 0, 0
+    prev = None
+    for ch in s:
+        cur = cur + 1 if ch == prev else 1
+        prev = ch
+        best = max(best, cur)
+    return best
+
+
+def homopolymer(context, alts, upstream):
+    """step1.py:511-529 (the second definition wins): longest run of context+alt >= 4."""
+    if context == '.':
+        return 0
+    m = max(longest_run(context + x) if upstream else longest_run(x + context) for x in alts)
+    return 1 if m >= 4 else 0
+
+
+class _TypeCall:
+    __slots__ = ("cell_type", "DP", "NC", "cand", "bc", "cc", "q_bc", "q_cc", "bcf", "REF")
+
+
+def _fisher_p(cand, bcf, REF):
+    # step1.py:228-231: forward and "reverse" vectors are both built from BCf, so the table is degenerate
+    import scipy.stats as stats
+    Fw = {ALLELES[x]: int(bcf[x]) for x in range(len(bcf))}
+    return "|".join(str(round(stats.fisher_exact([[Fw[x], Fw[x]], [Fw[REF], Fw[REF]]])[1], 4)) for x in cand)
+
+
+def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, min_ac_cells, min_ac_reads, min_cells,
+                          min_reads, min_cell_types, max_cell_types, fisher_cutoff, engine):
+    fa = bamio.Fasta(fasta) if fasta is not None else None
+    out_lines = []          # header lines written verbatim
+    rows = []               # per data row: dict with parsed pieces
+    q1k, q1n, q2k, q2n = [], [], [], []  # K2 queries: (bc, DP | alpha1,beta1) and (cc, NC | alpha2,beta2)
+    cell_types_idx = None
+    seen_header = False
+    with open(infile) as f:
+        for line in f:
+            if line.startswith('##'):
+                out_lines.append(line)
+                continue
+            if line.startswith('#CHROM') and not seen_header:
+                seen_header = True
+                elements = line.rstrip('\n').split('\t')
+                cell_types_idx = {x: elements[x] for x in range(len(elements)) if x > 4}
+                for _, text in INFO_HEADER:
+                    out_lines.append(text + '\n')
+                elements.insert(4, "\t".join(k for k, _ in INFO_HEADER))
+                out_lines.append('\t'.join(elements) + '\n')
+                continue
+            elements = line.rstrip('\n').split('\t')
+            CHROM, POS, REF = str(elements[0]), int(elements[1]), elements[3]
+            up_context = down_context = '.'
+            if fa is not None:
+                try:  # any failure (unknown contig, negative start) -> '.', like the bare except at :97-104
+                    context = fa.fetch(CHROM, POS - 6, POS + 5).upper()
+                    up_context, down_context = context[0:5], context[6:11]
+                except Exception:
+                    up_context = down_context = '.'
+            calls = []
+            n_qual = 0
+            Sum_alts_bc = Sum_alts_cc = Sum_dp = Sum_nc = 0
+            for ci in cell_types_idx:
+                INFO_i = elements[ci]
+                if INFO_i.startswith('NA'):
+                    continue
+                DP, NC, CC, BC, BQ, BCf, BCr = INFO_i.split('|')
+                DP, NC = int(DP), int(NC)
+                if not (DP >= min_reads and NC >= min_cells):
+                    continue
+                n_qual += 1
+                cc = [int(x) for x in CC.split(":")]
+                bc = [int(x) for x in BC.split(":")]
+                Sum_alts_bc += sum(bc[x] for x in range(len(bc)) if ALLELES[x] not in (REF, "O"))
+                Sum_alts_cc += sum(cc[x] for x in range(len(cc)) if ALLELES[x] not in (REF, "O"))
+                Sum_dp += DP
+                Sum_nc += NC
+                alt_bc = {ALLELES[x]: bc[x] for x in range(len(bc)) if ALLELES[x] not in (REF, "I", "D", "N", "O") and bc[x] > 0}
+                alt_cc = {ALLELES[x]: cc[x] for x in range(len(cc)) if ALLELES[x] not in (REF, "I", "D", "N", "O") and cc[x] > 0}
+                cand = sorted(alt_bc)
+                if not cand:
+                    continue
+                t = _TypeCall()
+                t.cell_type, t.DP, t.NC, t.cand, t.bc, t.cc, t.REF = cell_types_idx[ci], DP, NC, cand, alt_bc, alt_cc, REF
+                t.bcf = BCf.split(":")
+                t.q_bc = {a: len(q1k) + i for i, a in enumerate(alt_bc)}
+                for a in alt_bc:
+                    q1k.append(alt_bc[a])
+                    q1n.append(DP)
+                t.q_cc = {a: len(q2k) + i for i, a in enumerate(alt_cc)}
+                for a in alt_cc:
+                    q2k.append(alt_cc[a])
+                    q2n.append(NC)
+                b0 = sum(alt_bc[x] for x in cand)
+                c0 = sum(alt_cc[x] for x in cand)  # KeyError here == the reference's own failure mode (bc>0 but cc==0 cannot happen)
+                Sum_dp -= b0
+                Sum_nc -= c0
+                Sum_alts_bc -= b0
+                Sum_alts_cc -= c0
+                calls.append(t)
+            row = dict(elements=elements, up=up_context, down=down_context, calls=calls, n_qual=n_qual,
+                       sums=(Sum_alts_bc, Sum_alts_cc, Sum_dp, Sum_nc), rest=None)
+            if Sum_alts_bc > 0:  # noise test queries (:328-330 / :426-428)
+                row["rest"] = (len(q1k), len(q2k))
+                q1k.append(Sum_alts_bc)
+                q1n.append(Sum_dp)
+                q2k.append(Sum_alts_cc)
+                q2n.append(Sum_nc)
+            rows.append(row)
+
+    # ---- all beta-binomial tails of the run: two GPU launches ----------------------------------
+    p1 = engine.betabinom_sf(np.array(q1k, np.int32), np.array(q1n, np.int32), alpha1, beta1)
+    p2 = engine.betabinom_sf(np.array(q2k, np.int32), np.array(q2n, np.int32), alpha2, beta2)
+    r1 = np.round(p1, 4)  # == round(np.float64, 4) of the reference, element-wise
+    r2 = np.round(p2, 4)
+
+    with open(outfile, 'w') as out:
+        out.writelines(out_lines)
+        for row in rows:
+            elements, calls = row["elements"], row["calls"]
+            Sum_alts_bc, Sum_alts_cc, Sum_dp, Sum_nc = row["sums"]
+            if row["rest"] is not None:
+                BC_noise_p, CC_noise_p = r1[row["rest"][0]], r2[row["rest"][1]]
+            else:
+                BC_noise_p, CC_noise_p = 1, 1  # plain ints, printed as '1' (:334-335)
+            rest_BC = ";".join([str(Sum_alts_bc), str(Sum_dp), str(BC_noise_p)])
+            rest_CC = ";".join([str(Sum_alts_cc), str(Sum_nc), str(CC_noise_p)])
+            n_qual = str(row["n_qual"])
+            if calls:
+                Alts, Cell_types, DPs, NCs, BCs, CCs, BCp, CCp, VAF, MCF, Filter, Fisher_p = ([] for _ in range(12))
+                for t in calls:
+                    cand = t.cand
+                    Alts.append("|".join(cand))
+                    Cell_types.append(t.cell_type)
+                    DPs.append(str(t.DP))
+                    NCs.append(str(t.NC))
+                    P_BC = [r1[i] for i in t.q_bc.values()]
+                    P_CC = [r2[i] for i in t.q_cc.values()]
+                    fisher_p = None
+                    if fisher_cutoff != 1:
+                        fisher_p = _fisher_p(cand, t.bcf, t.REF)
+                        Fisher_p.append(fisher_p)
+                    b = "|".join(str(t.bc[x]) for x in cand)
+                    c = "|".join(str(t.cc[x]) for x in cand)
+                    BCs.append(b)
+                    CCs.append(c)
+                    BCp.append("|".join(str(r1[t.q_bc[x]]) for x in cand))
+                    CCp.append("|".join(str(r2[t.q_cc[x]]) for x in cand))
+                    VAF.append("|".join(str(round(t.bc[x] / float(t.DP), 4)) for x in cand))
+                    MCF.append("|".join(str(round(t.cc[x] / float(t.NC), 4)) for x in cand))
+                    mb, mc = min(P_BC), min(P_CC)
+                    if mb >= 0.05 or mc >= 0.05:
+                        Filter.append('Non-Significant')
+                    elif 0.001 < mb < 0.05 or 0.001 < mc < 0.05:
+                        Filter.append('Low-Significance')
+                    elif len(cand) > 1:
+                        Filter.append('Multi-allelic')
+                    elif int(c) < min_ac_cells:
+                        Filter.append('Low_cells')
+                    elif int(b) < min_ac_reads:
+                        Filter.append('Low_reads')
+                    elif fisher_cutoff != 1:
+                        if float(fisher_p) < fisher_cutoff:  # may append nothing (Q8)
+                            Filter.append('Fisher')
+                    else:
+                        Filter.append('PASS')
+                FILTER = []
+                n_pass = sum(1 for x in Filter if x == 'PASS')
+                n_nonsig = sum(1 for x in Filter if x == 'Non-Significant')
+                if n_pass > max_cell_types:
+                    FILTER.append('Multiple_cell_types')
+                LEN_Alts = len(set(Alts))
+                if LEN_Alts > 1 or 'Multi-allelic' in Filter:
+                    FILTER.append('Multi-allelic')
+                if row["n_qual"] < min_cell_types:
+                    FILTER.append('Min_cell_types')
+                if len(Filter) - n_pass - n_nonsig > 0:
+                    FILTER.append('Cell_type_noise')
+                if BC_noise_p < 0.05 or CC_noise_p < 0.05:
+                    FILTER.append('Noisy_site')
+                if homopolymer(row["up"], Alts, True) == 1:
+                    FILTER.append("LC_Upstream")
+                if homopolymer(row["down"], Alts, False) == 1:
+                    FILTER.append("LC_Downstream")
+                if len(FILTER) == 0:
+                    FILTER = 'PASS' if 'PASS' in Filter else ",".join(Filter)
+                else:
+                    FILTER = ",".join(FILTER)
+                INFO = [",".join(Alts), FILTER, ",".join(Cell_types), row["up"], row["down"], str(LEN_Alts), ",".join(DPs),
+                        ",".join(NCs), ",".join(BCs), ",".join(CCs), ",".join(VAF), ",".join(MCF), ",".join(BCp),
+                        ",".join(CCp), n_qual, n_qual, rest_BC, rest_CC,
+                        ",".join(Fisher_p) if fisher_cutoff != 1 else '.', ",".join(Filter)]
+            else:
+                FILTER = 'Noisy_site' if (BC_noise_p < 0.001 or CC_noise_p < 0.001) else '.'
+                INFO = [".", FILTER, ".", row["up"], row["down"], ".", ".", ".", ".", ".", ".", ".", ".", ".", n_qual, n_qual,
+                        rest_BC, rest_CC, '.', '.']
+            elements.insert(4, "\t".join(INFO))
+            out.write('\t'.join(elements) + '\n')
+    if fa is not None:
+        fa.close()
+    return len(rows), len(q1k) + len(q2k)
+
+
+def initialize_parser():
+    # flags, types and defaults of step1.py:585-604
+    p = argparse.ArgumentParser(description='Script to perform the scRNA somatic variant calling')
+    p.add_argument('--infile', type=str, help='Input file with all samples merged in a single tsv', required=True)
+    p.add_argument('--outfile', type=str, help='Output file prefix', required=True)
+    p.add_argument('--ref', type=str, help='Reference fasta file (*fai must exist)', required=True)
+    p.add_argument('--editing', type=str, help='RNA editing file to be used to remove RNA-diting sites', required=False)
+    p.add_argument('--pon', type=str, help='Panel of normals (PoN) file to be used to remove germline and false positive calls', required=False)
+    p.add_argument('--min_cov', type=int, default=5, help='Minimum depth of coverage to consider a sample. [Default: 5]', required=False)
+    p.add_argument('--min_cells', type=int, default=5, help='Minimum number of cells covering a site to consider a sample. [Default: 5]', required=False)
+    p.add_argument('--min_ac_cells', type=int, default=2, help='Minimum number of cells supporting the alternative allele to consider a mutation. [Default: 2]', required=False)
+    p.add_argument('--min_ac_reads', type=int, default=3, help='Minimum number of reads supporting the alternative allele to consider a mutation. [Default: 3]', required=False)
+    p.add_argument('--max_cell_types', type=int, default=1, help='Maximum number of cell types carrying a mutation to make a somatic call. [Default: 1]', required=False)
+    p.add_argument('--min_cell_types', type=int, default=2, help='Minimum number of cell types with enough coverage and cell to consider a site as callable [Default: 2]', required=False)
+    p.add_argument('--fisher_cutoff', type=float, default=1, help='P-value cutoff for the Fisher exact test performed to detect strand bias. By default, this test is switched off with a value of 1 [Default: 1]', required=False)
+    p.add_argument('--min_distance', type=int, default=5, help='Minimum distance allowed between potential somatic variants [Default: 5]', required=False)
+    p.add_argument('--alpha1', type=float, default=0.21356677091082193, help='Alpha parameter for Beta-binomial distribution of read counts.', required=False)
+    p.add_argument('--beta1', type=float, default=104.95163748636298, help='Beta parameter for Beta-binomial distribution of read counts.', required=False)
+    p.add_argument('--alpha2', type=float, default=0.2474528917555431, help='Alpha parameter for Beta-binomial distribution of cell counts.', required=False)
+    p.add_argument('--beta2', type=float, default=162.03696139428595, help='Beta parameter for Beta-binomial distribution of cell counts.', required=False)
+    return p
+
+
+def main(argv=None):
+    args = initialize_parser().parse_args(argv)
+    start = timeit.default_timer()
+    print('\n------------------------------')
+    print('Variant calling')
+    print('------------------------------\n')
+    print('- Variant calling step 1\n')
+    outfile1 = args.outfile + ".calling.step1.tsv"
+    with Engine(devices_from_env()[0]) as eng:
+        n_rows, n_q = variant_calling_step1(args.infile, outfile1, args.ref, args.alpha1, args.beta1, args.alpha2,
+                                            args.beta2, args.min_ac_cells, args.min_ac_reads, args.min_cells,
+                                            args.min_cov, args.min_cell_types, args.max_cell_types, args.fisher_cutoff,
+                                            eng)
+    print('Step 1 variant calling: %d positions processed, %d beta-binomial tails on the GPU' % (n_rows, n_q))
+    print('\nTotal computing time: ' + str(round(timeit.default_timer() - start, 2)) + ' seconds')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1:])

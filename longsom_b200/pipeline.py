@@ -1,0 +1,179 @@
+"""Host-side orchestration shared by the drop-in CLIs: BAM -> ReadBatch, barcode -> cell ids,
+window pruning, per-GPU sharding (no collective) and the BaseCellCounter TSV writer.
+
+Reference counterparts: BaseCellCounter.main / run_interval / concatenate_sort_temp_files_and_write
+(BaseCellCounter.py:22-79,182-320,344-409).  GPU selection cannot be a CLI flag (the Snakemake
+rules stay unchanged), so it comes from the environment: LONGSOM_GPUS="0,1,2,3" or LONGSOM_GPUS=4.
+"""
+import os
+import threading
+import time
+
+import numpy as np
+
+from . import bamio
+from .batch import ReadBatch, SiteCounts, Windows
+from .engine import CountParams, Engine
+from .sharding import balanced_window_shards
+
+INFO_FIELD = "DP|NC|CC|BC|BQ|BCf|BCr"
+COUNTER_CONCEPTS = (
+    '##INFO=DP,Description="Depth of coverage">\n'
+    '##INFO=NC,Description="Number of different cells">\n'
+    '##INFO=CC,Description="Cell counts [A:C:T:G:I:D:N:O], where D means deletion, I insertion and O other type of character">\n'
+    '##INFO=BC,Description="Base counts [A:C:T:G:I:D:N:O], where D means deletion, I insertion and O other type of character">\n'
+    '##INFO=BQ,Description="Base quality sums [A:C:T:G:I:D:N:O], where D means deletion, I insertion and O other type of character">\n'
+    '##INFO=BCf,Description="Base counts in forward reads [A:C:T:G:I:D:N:O], where D means deletion, I insertion and O other type of character">\n'
+    '##INFO=BCr,Description="Base counts in reverse reads [A:C:T:G:I:D:N:O], where D means deletion, I insertion and O other type of character">'
+)
+
+
+def devices_from_env():
+    v = os.environ.get("LONGSOM_GPUS", "").strip()
+    if not v:
+        return [0]
+    if "," in v:
+        return [int(x) for x in v.split(",") if x.strip() != ""]
+    n = int(v)
+    return list(range(n)) if n > 0 else [0]
+
+
+def read_ends(batch: ReadBatch):
+    """Exclusive reference end of every read (pos + M/D/N/=/X lengths)."""
+    if batch.n_reads == 0:
+        return np.zeros(0, np.int64)
+    op = batch.cigar & 15
+    ln = np.where(np.isin(op, (0, 2, 3, 7, 8)), batch.cigar >> 4, 0).astype(np.int64)
+    csum = np.concatenate([[0], np.cumsum(ln)])
+    span = csum[batch.cigar_off[1:].astype(np.int64)] - csum[batch.cigar_off[:-1].astype(np.int64)]
+    return batch.pos.astype(np.int64) + span
+
+
+def clean_barcodes_split(raw):
+    """BaseCellCounter / SingleCellGenotype: barcode = CB.split('-')[0] (BaseCellCounter.py:246)."""
+    return [b.split("-")[0] for b in raw]
+
+
+def dense_ids(strings):
+    """Map a list of strings to dense ids in first-appearance order; returns (ids array, unique list)."""
+    table, ids, uniq = {}, np.zeros(len(strings), np.int32), []
+    for i, s in enumerate(strings):
+        j = table.get(s)
+        if j is None:
+            j = len(uniq)
+            table[s] = j
+            uniq.append(s)
+        ids[i] = j
+    return ids, uniq
+
+
+def prune_and_sort_windows(named_windows, bam_names, batch, ends):
+    """named_windows: [(chrom, start, end)].  Keeps windows whose contig is in the BAM and that at least one
+    read overlaps (others cannot emit a site); returns them as (tid, start, end) sorted by (tid, start)."""
+    tid_of = {n: i for i, n in enumerate(bam_names)}
+    iv = sorted((tid_of[c], s, e) for c, s, e in named_windows if c in tid_of and e > s)
+    if not iv or batch.n_reads == 0:
+        return []
+    rk_lo = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
+    rk_hi = (batch.tid.astype(np.int64) << 32) | np.maximum(ends, batch.pos.astype(np.int64) + 1)
+    run_max = np.maximum.accumulate(rk_hi)
+    wk_lo = np.array([(t << 32) | s for t, s, e in iv], np.int64)
+    wk_hi = np.array([(t << 32) | e for t, s, e in iv], np.int64)
+    nb = np.searchsorted(rk_lo, wk_hi, side="left")
+    covered = (nb > 0) & (run_max[np.maximum(nb - 1, 0)] > wk_lo)
+    return [iv[j] for j in np.nonzero(covered)[0]]
+
+
+def count_sites(batch, windows_iv, contig_seq, params: CountParams, devices=None, stats_out=None):
+    """Pileup counts for windows_iv = [(tid, start, end)] (sorted, disjoint).  One Engine per device,
+    windows sharded by aligned-base weight; results concatenated in window order."""
+    devices = devices or [0]
+    if not windows_iv:
+        return SiteCounts.empty(0)
+    ends = read_ends(batch)
+    if len(devices) == 1:
+        shards = [(0, len(windows_iv))]
+    else:
+        wk_hi = np.array([(t << 32) | e for t, s, e in windows_iv], np.int64)
+        rk = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
+        idx = np.minimum(np.searchsorted(wk_hi, rk, side="right"), len(windows_iv) - 1)
+        w = np.zeros(len(windows_iv))
+        np.add.at(w, idx, batch.l_qseq.astype(np.float64))
+        shards = balanced_window_shards(w, len(devices))
+    results = [None] * len(shards)
+    errors = []
+
+    def work(k, dev, lo, hi):
+        try:
+            if hi <= lo:
+                results[k] = SiteCounts.empty(0)
+                return
+            sub_iv = windows_iv[lo:hi]
+            if len(shards) > 1:
+                lo_key = (sub_iv[0][0] << 32) | sub_iv[0][1]
+                hi_key = (sub_iv[-1][0] << 32) | sub_iv[-1][2]
+                rk_lo = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
+                rk_hi = (batch.tid.astype(np.int64) << 32) | np.maximum(ends, batch.pos.astype(np.int64) + 1)
+                sel = np.nonzero((rk_lo < hi_key) & (rk_hi > lo_key))[0]
+                sub = batch.select(sel)
+            else:
+                sub = batch
+            win = Windows.from_intervals(sub_iv, contig_seq)
+            with Engine(dev) as eng:
+                results[k] = eng.pileup_count(sub, win, params)
+                if stats_out is not None:
+                    stats_out.append(dict(device=dev, **eng.last_stats))
+        except Exception as e:  # surfaced below: the reference silently drops failed windows, we do not
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(k, devices[k], lo, hi)) for k, (lo, hi) in enumerate(shards)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+    return SiteCounts(np.concatenate([r.tid for r in results]), np.concatenate([r.pos for r in results]),
+                      np.concatenate([r.ref for r in results]), np.concatenate([r.counts for r in results], axis=0))
+
+
+def format_counter_lines(chrom, pos, ref, counts):
+    """TSV lines of BaseCellCounter.run_interval (:297-309) for one contig."""
+    lines = []
+    posl = (pos + 1).tolist()
+    refl = ref.tobytes().decode("latin-1")
+    c = counts.tolist()
+    for i in range(len(posl)):
+        r = c[i]
+        cc, f, rv, bq = r[2:8], r[8:14], r[14:20], r[20:26]
+        lines.append("%s\t%d\t%s\t%s\t%d|%d|%s|%s|%s|%s|%s\n" % (
+            chrom, posl[i], refl[i], INFO_FIELD, r[0], r[1], ":".join(map(str, cc)),
+            ":".join(str(a + b) for a, b in zip(f, rv)), ":".join(map(str, bq)), ":".join(map(str, f)),
+            ":".join(map(str, rv))))
+    return lines
+
+
+def write_counter_tsv(out_file, ID, sites: SiteCounts, bam_names):
+    """Final file of concatenate_sort_temp_files_and_write (:22-79): header, then window blocks ordered by
+    (chrom lexicographic, start).  Returns False (and writes nothing) when no site passed, like the
+    reference ('No temporary files found')."""
+    if sites.n_sites == 0:
+        print("No temporary files found")
+        return False
+    with open(out_file, "w") as out:
+        out.write("##fileDate=%s\n" % time.strftime("%d/%m/%Y"))
+        out.write(COUNTER_CONCEPTS + "\n")
+        out.write("\t".join(["#CHROM", "POS", "REF", "INFO", str(ID)]) + "\n")
+        tids = np.unique(sites.tid)
+        for t in sorted(tids.tolist(), key=lambda t: bam_names[t]):
+            m = sites.tid == t
+            out.writelines(format_counter_lines(bam_names[t], sites.pos[m], sites.ref[m], sites.counts[m]))
+    return True
+
+
+def load_bam_for_counting(bam_path, mode="split"):
+    """Decode a BAM and map CB tags to dense cell ids.
+    mode 'split': cell = CB.split('-')[0] (BaseCellCounter.py:246).  Returns (BamData, ReadBatch, cell names)."""
+    bd = bamio.read_bam(bam_path)
+    cleaned = clean_barcodes_split(bd.barcodes)
+    ids, uniq = dense_ids(cleaned)
+    return bd, bd.with_cells(ids), uniq

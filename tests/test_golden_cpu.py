@@ -1,0 +1,221 @@
+"""CPU suite: pins the oracle and the host logic to the REFERENCE's own outputs.
+
+tests/golden/<case>/*.gz were produced by the unmodified reference scripts (oracle/make_golden.py,
+run in the build container over oracle/shims).  Here, without a GPU:
+  * the C oracle (oracle/pileup_oracle.c) must reproduce the reference's BaseCellCounter tables
+    byte for byte  -> the oracle is pinned;
+  * the host side of every drop-in CLI (parsing, label cascades, row order, formatting) must
+    reproduce the reference's merged / step1 / step2 / genotype files byte for byte when the GPU
+    calls are answered by the oracle (C pileup, scipy beta-binomial, numpy set membership).
+The GPU suite (test_cli_gpu.py) then runs the same CLIs with the real CUDA engine."""
+import gzip
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = [c for c in ("g1", "g2") if os.path.isdir(os.path.join(GOLD, c))]
+
+
+def gold_lines(case, name):
+    with gzip.open(os.path.join(GOLD, case, name + ".gz"), "rt") as f:
+        return [l for l in f if not l.startswith("##fileDate")]
+
+
+def file_lines(path):
+    with open(path) as f:
+        return [l for l in f if not l.startswith("##fileDate")]
+
+
+def assert_same(got, want, what):
+    assert len(got) == len(want), "%s: %d lines vs %d" % (what, len(got), len(want))
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a == b, "%s differs at line %d:\n got: %s\nwant: %s" % (what, i, a[:400], b[:400])
+
+
+@pytest.fixture(scope="module", params=CASES)
+def work(request, tmp_path_factory, built):
+    import pipeline_inputs as pi
+    case = request.param
+    d = tmp_path_factory.mktemp("in_" + case)
+    paths, data = pi.write_inputs(case, str(d))
+    # golden intermediate files, so that each stage is tested in isolation
+    for name in ("counts.Cancer.tsv", "counts.Non-Cancer.tsv", "merged.tsv", "step1.tsv", "candidates.tsv"):
+        with gzip.open(os.path.join(GOLD, case, name + ".gz"), "rb") as f, open(os.path.join(str(d), name), "wb") as o:
+            o.write(f.read())
+    return case, str(d), paths, data
+
+
+class OracleEngine:
+    """Answers the Engine calls of the CLIs with the CPU oracle (test infrastructure)."""
+
+    def __init__(self, *a, **k):
+        self.batch = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        pass
+
+    def close(self):
+        pass
+
+    def upload(self, batch, windows=None):
+        self.batch = batch
+
+    def pileup_count(self, batch, windows, params):
+        import oracle
+        return oracle.pileup_count(batch, windows, params, threads=4)[0]
+
+    def genotype_count(self, st, sp, ac, n_cells, **kw):
+        import oracle
+        return oracle.genotype_count(self.batch, st, sp, ac, n_cells, **kw)
+
+    def betabinom_sf(self, k, n, a, b):
+        from scipy.stats import betabinom
+        k, n = np.asarray(k), np.asarray(n)
+        return betabinom.sf(k - 0.1, n, a, b) if len(k) else np.zeros(0)
+
+    def site_mask(self, keys, query):
+        return np.isin(query, keys).astype(np.uint8)
+
+
+def _count_with_oracle(bam, ref, chrom, bin_size, prm, ID, out):
+    from longsom_b200 import bamio
+    from longsom_b200.batch import Windows
+    from longsom_b200.pipeline import load_bam_for_counting, prune_and_sort_windows, read_ends, write_counter_tsv
+    from longsom_b200.windows import make_windows
+    import oracle
+    fa = bamio.Fasta(ref)
+    named = make_windows(fa.references, fa.lengths, chrom, bin_size)
+    bd, batch, _ = load_bam_for_counting(bam)
+    iv = prune_and_sort_windows(named, bd.contig_names, batch, read_ends(batch))
+    win = Windows.from_intervals(iv, {t: fa.contig(bd.contig_names[t]) for t in {w[0] for w in iv}})
+    sc, _ = oracle.pileup_count(batch, win, prm, threads=4)
+    write_counter_tsv(out, ID, sc, bd.contig_names)
+
+
+def test_oracle_pileup_matches_reference_tables(work):
+    from longsom_b200.engine import CountParams
+    case, d, p, data = work
+    for name, bam in (("Cancer", p["cancer"]), ("Non-Cancer", p["normal"])):
+        out = os.path.join(d, "o_%s.tsv" % name)
+        _count_with_oracle(bam, p["ref"], "all", 50000, CountParams(min_bq=20, min_mq=60), "s." + name, out)
+        assert_same(file_lines(out), gold_lines(case, "counts.%s.tsv" % name), "BaseCellCounter " + name)
+    out = os.path.join(d, "o_ac.tsv")
+    _count_with_oracle(p["full"], p["ref"], data.contig_names[0], 30000,
+                       CountParams(min_bq=30, min_mq=0, min_ac=2, min_dp=3, min_cc=2), "full.ac", out)
+    assert_same(file_lines(out), gold_lines(case, "counts.full_ac.tsv"), "BaseCellCounter --min_ac 2")
+
+
+def test_merge_matches_reference(work):
+    from longsom_b200.cli.merge import merge_cell_types_files
+    case, d, p, data = work
+    want = gold_lines(case, "merged.tsv")
+    order = want[7].rstrip("\n").split("\t")[5:]  # the reference's glob order decides the column order (Q10)
+    folder = os.path.join(d, "mc")
+    os.makedirs(folder, exist_ok=True)
+    files = []
+    for t in order:
+        fp = os.path.join(folder, "s.%s.tsv" % t)
+        with gzip.open(os.path.join(GOLD, case, "counts.%s.tsv.gz" % t), "rb") as f, open(fp, "wb") as o:
+            o.write(f.read())
+        files.append(fp)
+    out = os.path.join(d, "merged_mine.tsv")
+    merge_cell_types_files(files, out)
+    assert_same(file_lines(out), want, "MergeBaseCellCounts")
+
+
+def test_step1_host_logic_matches_reference(work):
+    import pipeline_inputs as pi
+    from longsom_b200.cli.step1 import variant_calling_step1
+    case, d, p, data = work
+    out = os.path.join(d, "step1_mine.tsv")
+    variant_calling_step1(os.path.join(d, "merged.tsv"), out, p["ref"], pi.ALPHA1, pi.BETA1, pi.ALPHA2, pi.BETA2, 2, 3, 5, 5,
+                          2, 1, 1, OracleEngine())
+    assert_same(file_lines(out), gold_lines(case, "step1.tsv"), "BaseCellCalling.step1")
+
+
+def test_step2_host_logic_matches_reference(work):
+    from longsom_b200.cli.step2 import variant_calling_step2
+    case, d, p, data = work
+    out = os.path.join(d, "step2_mine.tsv")
+    variant_calling_step2(os.path.join(d, "step1.tsv"), 0, p["editing"], p["pon_sr"], p["pon_lr"], p["gnomad"], 0.01, out,
+                          OracleEngine())
+    assert_same(file_lines(out), gold_lines(case, "step2.tsv"), "BaseCellCalling.step2")
+    out = os.path.join(d, "step2gz_mine.tsv")
+    variant_calling_step2(os.path.join(d, "step1.tsv"), 5, p["editing_gz"], p["pon_sr"], "", p["gnomad"], 0.01, out,
+                          OracleEngine())
+    assert_same(file_lines(out), gold_lines(case, "step2_gz.tsv"), "BaseCellCalling.step2 (gz editing list)")
+
+
+class _GenoOracleEngine(OracleEngine):
+    def betabinom_sf(self, k, n, a, b):
+        from scipy.stats import betabinom
+        k, n = np.asarray(k), np.asarray(n)
+        return betabinom.sf(k - 0.001, n, a, b) if len(k) else np.zeros(0)
+
+
+def test_genotype_host_logic_matches_reference(work, monkeypatch):
+    import pipeline_inputs as pi
+    import longsom_b200.cli.genotype as G
+    case, d, p, data = work
+    monkeypatch.setattr(G, "Engine", _GenoOracleEngine)
+    for flag in ("All", "Alt"):
+        pre = os.path.join(d, "geno_" + flag)
+        G.main(["--bam", p["full"], "--infile", os.path.join(d, "candidates.tsv"), "--ref", p["ref"], "--meta", p["meta"],
+                "--fusions", "--outfile", pre, "--alt_flag", flag, "--min_mq", "60", "--alpha2", str(pi.ALPHA2), "--beta2",
+                str(pi.BETA2), "--tmp_dir", os.path.join(d, "tmpg")])
+        for suf in ("SingleCellGenotype", "DpMatrix", "AltMatrix", "VAFMatrix", "BinaryMatrix"):
+            assert_same(file_lines("%s.%s.tsv" % (pre, suf)), gold_lines(case, "geno_%s.%s.tsv" % (flag, suf)),
+                        "SingleCellGenotype %s %s" % (flag, suf))
+    out = os.path.join(d, "hccv_mine.tsv")
+    G.main(["--bam", p["full"], "--infile", os.path.join(d, "candidates.tsv"), "--ref", p["ref"], "--meta", p["meta"],
+            "--outfile", out, "--alt_flag", "All", "--min_mq", "60", "--tmp_dir", os.path.join(d, "tmph")], hccv=True)
+    assert_same(file_lines(out), gold_lines(case, "hccv.tsv"), "HCCVSingleCellGenotype")
+
+
+def test_shim_engine_matches_c_oracle_on_corner_cases(built):
+    """The literal htslib-engine restatement (oracle/shims/pysam) and the C oracle agree on the
+    hand-built CIGAR corner cases, independently of the reference scripts."""
+    import pipeline_inputs as pi
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
+    import importlib
+    pysam = importlib.import_module("pysam")
+    from longsom_b200 import bamio
+    from longsom_b200.batch import Windows
+    from longsom_b200.engine import CountParams
+    import oracle
+    import tempfile
+    d = pi.build_batch("g2")
+    tmp = tempfile.mkdtemp()
+    bam = os.path.join(tmp, "x.bam")
+    bamio.write_bam(bam, d.contig_names, d.contig_lens, d.batch, pi.cb_text(d, ""))
+    lo, hi = 250, 520
+    win = Windows.from_intervals([(0, lo, hi)], d.contig_seqs())
+    prm = CountParams(min_bq=20, min_mq=60, min_dp=1, min_cc=1)
+    sc, _ = oracle.pileup_count(d.batch, win, prm)
+    dp_oracle = dict(zip(sc.pos.tolist(), sc.counts[:, 0].tolist()))
+    a = pysam.AlignmentFile(bam)
+    dp_shim = {}
+    for col in a.pileup(d.contig_names[0], lo, hi, min_base_quality=20, min_mapping_quality=60, ignore_overlaps=False,
+                        max_depth=200000):
+        if not (lo <= col.pos < hi):
+            continue
+        n = 0
+        for s, pr in zip(col.get_query_sequences(mark_matches=True, add_indels=True), col.pileups):
+            al = pr.alignment
+            if "CB" not in al.tags or al.is_supplementary:
+                continue
+            u = s.upper()
+            if u in ("A", "C", "G", "T", "N") or (len(s) > 1 and s[1] in "+-") or s == "*":
+                n += 1
+        if n and chr(d.contig_seq(0)[col.pos]).upper() != "N":
+            dp_shim[col.pos] = n
+    assert dp_shim == dp_oracle
+    assert len(dp_shim) > 50
