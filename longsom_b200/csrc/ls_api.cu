@@ -156,7 +156,7 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
   UP(wtid, w ? w->tid : nullptr, (size_t)nw * 4);
   UP(wstart, w ? w->start : nullptr, (size_t)nw * 4);
   UP(wend, w ? w->end : nullptr, (size_t)nw * 4);
-  UP(wref_off, w ? w->ref_off : nullptr, (size_t)(nw + 1) * 8);
+  UP(wref_off, w ? w->ref_off : nullptr, (size_t)(nw > 0 ? (nw + 1) * 8 : 0));
   UP(ref, w ? w->ref : nullptr, (size_t)(nw ? w->ref_off[nw] : 0));
   UP(wtile_base, ctx->h_wtile_base.data(), (size_t)(nw + 1) * 8);
   LS_CK(cudaStreamSynchronize(st));
