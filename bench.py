@@ -381,6 +381,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    # torchrun pins OMP_NUM_THREADS=1; the (untimed) synthetic generator and the CPU oracle are OpenMP code
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world)))
     if world != args.gpus and world > 1:
         log("warning: WORLD_SIZE=%d but --gpus %d" % (world, args.gpus))
     if args.impl == "reference":

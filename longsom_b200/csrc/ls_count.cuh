@@ -85,15 +85,22 @@ __device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t ti
   return lo;
 }
 
+// shared-memory reduction on a 32-bit shared-window address (no generic->shared conversion per base)
+__device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+// hs = shared address of hist[strand][0]: the (class, strand) row of class c starts 2*LS_TILE words further per class
 template <bool PACKED, bool SEEN>
 __device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint32_t *seen, int s, int cls, uint32_t q,
-                                          int strand) {
+                                          uint32_t hs) {
   const int sidx = swz(s);
+  const uint32_t addr = hs + (uint32_t)(cls * (2 * LS_TILE) + sidx) * 4u;
   if (PACKED) {
-    atomicAdd(&sm.hist[cls * 2 + strand][sidx], (1u << K1_CNT_SHIFT) | q);
+    red_shared_add(addr, (1u << K1_CNT_SHIFT) | q);
   } else {
-    atomicAdd(&sm.hist[cls * 2 + strand][sidx], 1u);
-    atomicAdd(&sm.hist[16 + cls * 2 + strand][sidx], q);
+    red_shared_add(addr, 1u);
+    red_shared_add(addr + 16u * LS_TILE * 4u, q);
   }
   if (SEEN) {
     const int sh = 8 * (s & 3);
@@ -135,6 +142,22 @@ __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
   return m;
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Lane-parallel L2 prefetch of everything the warp will read for this segment (its CIGAR window and the
+// quality / base bytes of the piece inside the tile): the per-segment loads that follow are then L2 hits
+// instead of serialized DRAM round trips.
+__device__ __forceinline__ void prefetch_segment(const CountArgs &a, const SegMeta &m, int32_t tile_start) {
+  prefetch_l2(a.cigar + m.cig);
+  const uint64_t y = m.boff + m.y0 + (uint64_t)(m.x0 < tile_start ? tile_start - m.x0 : 0);
+  const uint8_t *q = a.qual + (y & ~127ull);
+#pragma unroll
+  for (int i = 0; i < 5; ++i) prefetch_l2(q + 128 * i);
+  const uint8_t *sq = a.seq4 + ((y >> 1) & ~127ull);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) prefetch_l2(sq + 128 * i);
+}
+
 __device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
   SegMeta r;
   r.cig = __shfl_sync(0xffffffffu, m.cig, j);
@@ -152,10 +175,10 @@ __device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
 template <bool PACKED, bool SEEN, bool COUNTED>
 __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen,
                                                      const SegMeta m, int32_t tile_start, int32_t tile_end,
-                                                     int lane) {
+                                                     int lane, uint32_t hist_s) {
   const uint8_t *__restrict__ qual = a.qual + m.boff;
   const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
-  const int strand = m.strand;
+  const uint32_t strand = hist_s + (uint32_t)m.strand * (LS_TILE * 4u);  // shared address of hist[strand][0]
   const uint32_t lq = m.lq;
   int32_t x = m.x0;
   uint32_t y = m.y0;
@@ -221,7 +244,8 @@ __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSme
               bool ok = (int)q >= a.min_bq;
               if (!full) ok = ok && (g + (uint32_t)j >= ya) && (g + (uint32_t)j < ybl);
               const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
-              int cls = (int)((K1_CLASS_LUT >> (4 * code)) & 15ull);
+              const uint32_t lut = (code & 8u) ? 0x68888882u : 0x88838108u;  // K1_CLASS_LUT halves
+              int cls = (int)((lut >> (4u * (code & 7u))) & 15u);
               if (dl == (uint32_t)j) cls = indcls;
               if (ok && cls != LS_CLASS_NA) {
                 if (COUNTED)
@@ -257,7 +281,7 @@ __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSme
 }
 
 template <bool PACKED>
-__global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a) {
+__global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
   const uint32_t part = blockIdx.x;
@@ -292,8 +316,9 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
   const uint64_t cmask = (1ull << a.cell_bits) - 1ull;
   const uint64_t unc = (uint64_t)a.uncounted_key;
   uint32_t *seen = sm.seen[warp];
+  const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(&sm.hist[0][0]);
   const uint32_t nmine = my_hi - my_lo;
-  uint32_t chunk = (nmine + K1_WARPS - 1) / K1_WARPS;
+  uint32_t chunk = (nmine + 3 * K1_WARPS - 1) / (3 * K1_WARPS);  // ~3 grabs per warp: dynamic balance inside the CTA
   chunk = chunk < 4u ? 4u : (chunk > 32u ? 32u : chunk);
   for (;;) {
     uint32_t g = 0;
@@ -312,6 +337,7 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
       ck = a.keys[i] & cmask;
       start = (i == slot_lo) || ck == unc || (a.keys[i - 1] & cmask) != ck;
       mm = load_meta(a, i);
+      prefetch_segment(a, mm, tile_start);
     }
     const uint32_t startmask = __ballot_sync(0xffffffffu, start);
     uint32_t rem = startmask;
@@ -329,16 +355,16 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
       const uint32_t runlen = (uint32_t)(j1 - j0) + ext;
       if (runlen == 1) {
         if (counted)
-          process_segment_fast<PACKED, false, true>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane);
+          process_segment_fast<PACKED, false, true>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane, hist_s);
         else
-          process_segment_fast<PACKED, false, false>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane);
+          process_segment_fast<PACKED, false, false>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane, hist_s);
       } else {
         for (int q = lane; q < LS_TILE / 4; q += 32) seen[q] = 0u;
         __syncwarp();
         for (int j = j0; j < j1; ++j)
-          process_segment_fast<PACKED, true, true>(a, sm, seen, shfl_meta(mm, j), tile_start, tile_end, lane);
+          process_segment_fast<PACKED, true, true>(a, sm, seen, shfl_meta(mm, j), tile_start, tile_end, lane, hist_s);
         for (uint32_t e = 0; e < ext; ++e)
-          process_segment_fast<PACKED, true, true>(a, sm, seen, load_meta(a, cb + e), tile_start, tile_end, lane);
+          process_segment_fast<PACKED, true, true>(a, sm, seen, load_meta(a, cb + e), tile_start, tile_end, lane, hist_s);
       }
     }
   }

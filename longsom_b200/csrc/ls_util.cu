@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
   __shared__ uint32_t wcnt[RS_WARPS][256];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * G + blockIdx.x];
+  base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * G + blockIdx.x] + hist_scanned[(int64_t)256 * G + threadIdx.x];
   int64_t lo = (int64_t)blockIdx.x * per_block;
   int64_t hi = lo + per_block < n ? lo + per_block : n;
   for (int64_t chunk = lo; chunk < hi; chunk += RS_CHUNK) {
@@ -177,21 +177,29 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
   }
 }
 
-__global__ void __launch_bounds__(1024) rs_scan_hist(uint32_t *__restrict__ hist, int total) {
-  // exclusive scan over `total` entries (digit-major, block-minor), single block
-  __shared__ uint32_t sm[1024 / 32 + 1];
-  int per = (total + 1023) / 1024;
-  int lo = threadIdx.x * per;
-  int hi = lo + per < total ? lo + per : total;
-  uint32_t s = 0;
-  for (int i = lo; i < hi; ++i) s += hist[i];
-  uint32_t tot;
-  uint32_t ex = block_excl_scan<1024>(s, &tot, sm);
-  for (int i = lo; i < hi; ++i) {
-    uint32_t t = hist[i];
-    hist[i] = ex;
-    ex += t;
+// exclusive scan of the (digit-major, block-minor) histogram in two tiny kernels:
+// one CTA per digit scans its G entries and records the digit total, one CTA scans the 256 totals.
+__global__ void __launch_bounds__(256) rs_scan_digit(uint32_t *__restrict__ hist, int G, uint32_t *__restrict__ totals) {
+  __shared__ uint32_t sm[256 / 32 + 1];
+  uint32_t *h = hist + (size_t)blockIdx.x * G;
+  uint32_t carry = 0;
+  for (int base = 0; base < G; base += 256) {
+    const int i = base + threadIdx.x;
+    const uint32_t v = i < G ? h[i] : 0u;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan<256>(v, &tot, sm);
+    if (i < G) h[i] = carry + ex;
+    carry += tot;
   }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(256) rs_scan_totals(uint32_t *__restrict__ totals) {
+  __shared__ uint32_t sm[256 / 32 + 1];
+  uint32_t tot;
+  const uint32_t v = totals[threadIdx.x];
+  const uint32_t ex = block_excl_scan<256>(v, &tot, sm);
+  totals[threadIdx.x] = ex;
 }
 
 template <bool HAS_VALS>
@@ -206,17 +214,18 @@ cudaError_t radix_sort_impl(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a
   int64_t nchunks = (n + RS_CHUNK - 1) / RS_CHUNK;
   int G = (int)(nchunks < (int64_t)num_sms * 4 ? nchunks : (int64_t)num_sms * 4);
   int64_t per_block = ((nchunks + G - 1) / G) * RS_CHUNK;
-  cudaError_t e = hist.ensure((size_t)256 * G * sizeof(uint32_t));
+  cudaError_t e = hist.ensure(((size_t)256 * G + 256) * sizeof(uint32_t));
   if (e != cudaSuccess) return e;
   uint64_t *kin = keys_a, *kout = keys_b;
   uint32_t *vin = vals_a, *vout = vals_b;
   for (int p = 0; p < passes; ++p) {
     int shift = p * 8;
     rs_hist<<<G, RS_THREADS, 0, st>>>(kin, n, per_block, shift, hist.as<uint32_t>(), G);
-    rs_scan_hist<<<1, 1024, 0, st>>>(hist.as<uint32_t>(), 256 * G);
+    rs_scan_digit<<<256, 256, 0, st>>>(hist.as<uint32_t>(), G, hist.as<uint32_t>() + (size_t)256 * G);
+    rs_scan_totals<<<1, 256, 0, st>>>(hist.as<uint32_t>() + (size_t)256 * G);
     rs_scatter<HAS_VALS><<<G, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, per_block, shift, hist.as<uint32_t>(), G,
                                                    p == 0 ? 1 : 0);
-    if (launches) *launches += 3;
+    if (launches) *launches += 4;
     uint64_t *tk = kin;
     kin = kout;
     kout = tk;
