@@ -142,22 +142,6 @@ __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
   return m;
 }
 
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Lane-parallel L2 prefetch of everything the warp will read for this segment (its CIGAR window and the
-// quality / base bytes of the piece inside the tile): the per-segment loads that follow are then L2 hits
-// instead of serialized DRAM round trips.
-__device__ __forceinline__ void prefetch_segment(const CountArgs &a, const SegMeta &m, int32_t tile_start) {
-  prefetch_l2(a.cigar + m.cig);
-  const uint64_t y = m.boff + m.y0 + (uint64_t)(m.x0 < tile_start ? tile_start - m.x0 : 0);
-  const uint8_t *q = a.qual + (y & ~127ull);
-#pragma unroll
-  for (int i = 0; i < 5; ++i) prefetch_l2(q + 128 * i);
-  const uint8_t *sq = a.seq4 + ((y >> 1) & ~127ull);
-#pragma unroll
-  for (int i = 0; i < 3; ++i) prefetch_l2(sq + 128 * i);
-}
-
 __device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
   SegMeta r;
   r.cig = __shfl_sync(0xffffffffu, m.cig, j);
@@ -337,7 +321,6 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
       ck = a.keys[i] & cmask;
       start = (i == slot_lo) || ck == unc || (a.keys[i - 1] & cmask) != ck;
       mm = load_meta(a, i);
-      prefetch_segment(a, mm, tile_start);
     }
     const uint32_t startmask = __ballot_sync(0xffffffffu, start);
     uint32_t rem = startmask;
