@@ -302,12 +302,19 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
   uint32_t *seen = sm.seen[warp];
   const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(&sm.hist[0][0]);
   const uint32_t nmine = my_hi - my_lo;
-  uint32_t chunk = (nmine + 3 * K1_WARPS - 1) / (3 * K1_WARPS);  // ~3 grabs per warp: dynamic balance inside the CTA
-  chunk = chunk < 4u ? 4u : (chunk > 32u ? 32u : chunk);
   for (;;) {
-    uint32_t g = 0;
-    if (lane == 0) g = atomicAdd(&sm.next, chunk);
+    // guided self-scheduling: grab ~1/(2*warps) of what is left (<= 32 segments, >= 2), so that the
+    // last grabs are small and the warps of the CTA reach the barrier together
+    uint32_t g = 0, chunk = 0;
+    if (lane == 0) {
+      const uint32_t seen_next = *(volatile uint32_t *)&sm.next;
+      const uint32_t left = seen_next < nmine ? nmine - seen_next : 0u;
+      chunk = left / (2u * K1_WARPS);
+      chunk = chunk < 2u ? 2u : (chunk > 32u ? 32u : chunk);
+      g = atomicAdd(&sm.next, chunk);
+    }
     g = __shfl_sync(0xffffffffu, g, 0);
+    chunk = __shfl_sync(0xffffffffu, chunk, 0);
     if (g >= nmine) break;
     const uint32_t ca = my_lo + g;
     const uint32_t cb = (ca + chunk) < my_hi ? (ca + chunk) : my_hi;
