@@ -27,6 +27,9 @@ constexpr int K1_THREADS = 256;
 constexpr int K1_WARPS = K1_THREADS / 32;
 constexpr int K1_PART_SEGS = 2048;       // nominal segments per part
 constexpr int K1_MAX_RUN_PACKED = 2039;  // packed counters (12-bit) need: part segs + run extension <= 4095
+constexpr int K1_ROWS = 18;               // 9 row pairs: 8 classes + the dump pair
+constexpr uint32_t K1_CLASS_STRIDE = 2u * LS_TILE * 4u;  // bytes between the row pairs of consecutive classes
+constexpr uint32_t K1_DUMP_OFF = 8u * K1_CLASS_STRIDE;
 constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
 
 static_assert(LS_TILE % 128 == 0 && LS_TILE % K1_THREADS == 0 && LS_TILE <= 65536, "tile / block shape");
@@ -64,8 +67,11 @@ struct CountArgs {
 
 template <bool PACKED>
 struct TileSmemT {
-  uint32_t hist[PACKED ? 16 : 32][LS_TILE];  // PACKED: [cls*2+strand] = cnt<<20|bq ; else [0..15] cnt, [16..31] bq
-  uint32_t dupcc[6][LS_TILE];                // entries whose (cell, class) was already seen at the site
+  // rows [cls*2+strand], cls 0..7 real classes, cls 8 = "dump" rows that absorb invisible / ignored bases so that
+  // the 4-base step needs no branches.  PACKED: cnt<<20|bq; else rows [0..17] counts, [18..35] quality sums.
+  uint32_t hist[PACKED ? K1_ROWS : 2 * K1_ROWS][LS_TILE];
+  uint32_t dupcc[3][LS_TILE];                // (cell, class) already seen at the site: class c in half-word c/3 of row c%3
+  uint32_t lut2[256];                        // BAM base byte (2 nibbles) -> two 16-bit byte offsets of the class row pair
   uint32_t dupnc[LS_TILE];                   // entries whose cell was already seen at the site (any class)
   uint32_t acx[LS_TILE];                     // alt entries of visible-but-uncounted reads (--min_ac > 0)
   uint32_t seen[K1_WARPS][LS_TILE / 4];      // per warp: class bits (1 byte per site) of the current same-cell run
@@ -91,25 +97,26 @@ __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
 }
 
 // hs = shared address of hist[strand][0]: the (class, strand) row of class c starts 2*LS_TILE words further per class
+template <bool PACKED>
+__device__ __forceinline__ void note_seen(TileSmemT<PACKED> &sm, uint32_t *seen, int s, int cls) {
+  const int sidx = swz(s);
+  const int sh = 8 * (s & 3);
+  const uint32_t old = (atomicOr(&seen[s >> 2], (1u << cls) << sh) >> sh) & 255u;
+  if (((old >> cls) & 1u) && cls < 6) atomicAdd(&sm.dupcc[cls % 3][sidx], 1u << (16 * (cls / 3)));
+  if (old) atomicAdd(&sm.dupnc[sidx], 1u);
+}
+
 template <bool PACKED, bool SEEN>
 __device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint32_t *seen, int s, int cls, uint32_t q,
                                           uint32_t hs) {
-  const int sidx = swz(s);
-  const uint32_t addr = hs + (uint32_t)(cls * (2 * LS_TILE) + sidx) * 4u;
+  const uint32_t addr = hs + (uint32_t)cls * K1_CLASS_STRIDE + (uint32_t)swz(s) * 4u;
   if (PACKED) {
     red_shared_add(addr, (1u << K1_CNT_SHIFT) | q);
   } else {
     red_shared_add(addr, 1u);
-    red_shared_add(addr + 16u * LS_TILE * 4u, q);
+    red_shared_add(addr + (uint32_t)K1_ROWS * LS_TILE * 4u, q);
   }
-  if (SEEN) {
-    const int sh = 8 * (s & 3);
-    const uint32_t old = (atomicOr(&seen[s >> 2], (1u << cls) << sh) >> sh) & 255u;
-    if ((old >> cls) & 1u) {
-      if (cls < 6) atomicAdd(&sm.dupcc[cls][sidx], 1u);
-    }
-    if (old) atomicAdd(&sm.dupnc[sidx], 1u);
-  }
+  if (SEEN) note_seen<PACKED>(sm, seen, s, cls);
 }
 
 template <bool PACKED>
@@ -216,27 +223,78 @@ __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSme
           const uint32_t ybl = yb < lq ? yb : lq;                                    // bases that exist
           const int sbase = lo - tile_start;
           const uint32_t ylast = (ind != 0) ? (y + (uint32_t)len - 1u) : 0xffffffffu;
-          for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < ybl; g += 128u) {
-            const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
-            const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
-            const int sg = sbase + (int)(g - ya);  // site of the word's first base (-3..-1 possible in the head word)
-            const bool full = g >= ya && g + 4u <= ybl;
-            const uint32_t dl = ylast - g;  // == j for the base that carries the indel
+          // the base that carries a following indel is handled on its own (below); the word loop stops before it
+          const uint32_t yw = (ind != 0 && ylast < ybl) ? ylast : ybl;
+          if (COUNTED && a.min_bq >= 0 && a.min_bq <= 128) {
+            // Branch-free 4-base step.  Class decode = one shared lookup per base byte (2 bases); bases that must
+            // not count (quality below min_bq, ignored code, outside [ya, yw)) are steered to the dump rows instead
+            // of being branched around.  (site & 3) of byte j is identical for all lanes and steps, so the
+            // swizzled column of byte j is colb[j] + 4 * (site_of_byte0 >> 2) with colb[] warp-uniform.
+            const int a4 = (sbase - (int)(ya & 3u)) & 3;
+            uint32_t colb[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t q = (w >> (8 * j)) & 255u;
-              bool ok = (int)q >= a.min_bq;
-              if (!full) ok = ok && (g + (uint32_t)j >= ya) && (g + (uint32_t)j < ybl);
-              const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
-              const uint32_t lut = (code & 8u) ? 0x68888882u : 0x88838108u;  // K1_CLASS_LUT halves
-              int cls = (int)((lut >> (4u * (code & 7u))) & 15u);
-              if (dl == (uint32_t)j) cls = indcls;
-              if (ok && cls != LS_CLASS_NA) {
-                if (COUNTED)
-                  add_entry<PACKED, SEEN>(sm, seen, sg + j, cls, q, strand);
-                else
-                  add_uncounted<PACKED>(sm, sg + j, cls);
+            for (int j = 0; j < 4; ++j) colb[j] = (uint32_t)((((a4 + j) & 3) * (LS_TILE / 4)) + ((a4 + j) >> 2)) * 4u;
+            const uint32_t mq4 = (uint32_t)a.min_bq * 0x01010101u;
+            for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < yw; g += 128u) {
+              const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
+              const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
+              const int d0 = (int)(g - ya);  // index inside the piece of this word's byte 0 (< 0 in the head word)
+              // bit 8j+7 <=> quality of byte j >= min_bq   ((q|0x80) >= 128 >= min_bq: no borrow between bytes)
+              uint32_t okm = (((w | 0x80808080u) - mq4) | w) & 0x80808080u;
+              const int hi = (int)(yw - g);
+              if (d0 < 0 || hi < 4) {  // head / tail word
+                uint32_t m = 0xffffffffu;
+                if (d0 < 0) m <<= 8 * (-d0);
+                if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
+                okm &= m;
               }
+              const uint32_t l0 = sm.lut2[h & 255u], l1 = sm.lut2[h >> 8];
+              const uint32_t rowb = strand + (uint32_t)((sbase + d0) >> 2) * 4u;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t lw = (j < 2) ? l0 : l1;
+                uint32_t off = (j & 1) ? (lw >> 16) : (lw & 0xffffu);
+                if (!((okm >> (8 * j + 7)) & 1u)) off = K1_DUMP_OFF;
+                const uint32_t q = (w >> (8 * j)) & 255u;
+                const uint32_t addr = rowb + colb[j] + off;
+                if (PACKED) {
+                  red_shared_add(addr, (1u << K1_CNT_SHIFT) | q);
+                } else {
+                  red_shared_add(addr, 1u);
+                  red_shared_add(addr + (uint32_t)K1_ROWS * LS_TILE * 4u, q);
+                }
+                if (SEEN) {
+                  if (off != K1_DUMP_OFF) note_seen<PACKED>(sm, seen, sbase + d0 + j, (int)(off / K1_CLASS_STRIDE));
+                }
+              }
+            }
+          } else {
+            for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < yw; g += 128u) {
+              const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
+              const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
+              const int sg = sbase + (int)(g - ya);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t q = (w >> (8 * j)) & 255u;
+                const bool ok = (int)q >= a.min_bq && (g + (uint32_t)j >= ya) && (g + (uint32_t)j < yw);
+                const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
+                const int cls = class_of_code(code);
+                if (ok && cls != LS_CLASS_NA) {
+                  if (COUNTED)
+                    add_entry<PACKED, SEEN>(sm, seen, sg + j, cls, q, strand);
+                  else
+                    add_uncounted<PACKED>(sm, sg + j, cls);
+                }
+              }
+            }
+          }
+          if (ind != 0 && ylast < ybl && lane == 0) {  // last base of the op, followed by an insertion / deletion
+            const uint32_t q = qual[ylast];
+            if ((int)q >= a.min_bq) {
+              if (COUNTED)
+                add_entry<PACKED, SEEN>(sm, seen, sbase + (int)(ylast - ya), indcls, q, strand);
+              else
+                add_uncounted<PACKED>(sm, sbase + (int)(ylast - ya), indcls);
             }
           }
           // query positions past the stored sequence (malformed record): base 'N', quality 0
@@ -285,10 +343,19 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
 
   {  // zero the accumulators, stage the reference bases
     uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
-    constexpr int NZ = ((PACKED ? 16 : 32) + 6 + 1 + 1) * LS_TILE;
+    constexpr int NZ = ((PACKED ? K1_ROWS : 2 * K1_ROWS) + 3) * LS_TILE;  // hist + dupcc (dupnc / acx zeroed below)
     for (int i = threadIdx.x; i < NZ; i += K1_THREADS) z[i] = 0u;
-    for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS)
+    for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS) {
       sm.ref[i] = (tile_start + i < tile_end) ? upper_ascii(a.ref[ref_base + i]) : (uint8_t)'N';
+      sm.dupnc[i] = 0u;
+      sm.acx[i] = 0u;
+    }
+    for (int i = threadIdx.x; i < 256; i += K1_THREADS) {
+      // byte = (base g: high nibble, base g+1: low nibble); ignored codes -> the dump rows (class 8)
+      const uint32_t o0 = (uint32_t)class_of_code((uint32_t)i >> 4) * K1_CLASS_STRIDE;
+      const uint32_t o1 = (uint32_t)class_of_code((uint32_t)i & 15u) * K1_CLASS_STRIDE;
+      sm.lut2[i] = o0 | (o1 << 16);
+    }
     if (threadIdx.x == 0) {
       sm.next = 0;
       sm.npass = 0;
@@ -393,14 +460,14 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
           } else {
             f[k] = sm.hist[k * 2][sidx];
             r[k] = sm.hist[k * 2 + 1][sidx];
-            if (k < 6) bq[k] = sm.hist[16 + k * 2][sidx] + sm.hist[16 + k * 2 + 1][sidx];
+            if (k < 6) bq[k] = sm.hist[K1_ROWS + k * 2][sidx] + sm.hist[K1_ROWS + k * 2 + 1][sidx];
           }
           dp += f[k] + r[k];
         }
         nev += dp;
         nc = dp - sm.dupnc[sidx];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cc[k] = f[k] + r[k] - sm.dupcc[k][sidx];
+        for (int k = 0; k < 6; ++k) cc[k] = f[k] + r[k] - ((sm.dupcc[k % 3][sidx] >> (16 * (k / 3))) & 0xffffu);
         if (a.min_ac > 0) {
           ac = sm.acx[sidx] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
           const int base_cls[5] = {LS_CLASS_A, LS_CLASS_C, LS_CLASS_T, LS_CLASS_G, LS_CLASS_N};
