@@ -26,6 +26,8 @@ CASES = [
     dict(seed=2, contig_lens=[120000, 90000, 70000], n_genes=30, n_reads=8000, n_cells=50),
     dict(seed=3, contig_lens=[200000], n_genes=6, n_reads=30000, n_cells=1000, n_hot_genes=2, hot_fraction=0.9),
     dict(seed=4, contig_lens=[100000], n_genes=5, n_reads=300, n_cells=20),
+    # indel every ~25 bases: dozens of CIGAR pieces per (read, tile) segment (piece-queue overflow path)
+    dict(seed=7, contig_lens=[100000], n_genes=5, n_reads=3000, n_cells=30, p_ins=0.02, p_del=0.02),
 ]
 
 
