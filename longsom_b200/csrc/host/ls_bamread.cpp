@@ -17,6 +17,7 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <thread>
@@ -315,3 +316,81 @@ const void *ls_bam_array(void *h, int which) {
 }
 
 }  // extern "C"
+
+// ---- BaseCellCounter TSV writer --------------------------------------------------------------
+// Formats the per-site table of ls_pileup_count as the reference prints it
+// (BaseCellCounter.py:297-309): chrom, pos+1, REF, "DP|NC|CC|BC|BQ|BCf|BCr", and the seven
+// '|'-joined fields with ':'-joined allele vectors (BC = BCf + BCr).  Threads format disjoint row
+// ranges into private buffers which are then written in order.
+namespace {
+inline char *put_u32(char *p, uint32_t v) {
+  char tmp[12];
+  int n = 0;
+  do {
+    tmp[n++] = (char)('0' + v % 10);
+    v /= 10;
+  } while (v);
+  while (n) *p++ = tmp[--n];
+  return p;
+}
+inline char *put_vec6(char *p, const uint32_t *v) {
+  for (int i = 0; i < 6; ++i) {
+    p = put_u32(p, v[i]);
+    *p++ = i == 5 ? '|' : ':';
+  }
+  return p;
+}
+}  // namespace
+
+extern "C" int ls_write_counter_rows(const char *path, const char *chrom, const int32_t *pos, const uint8_t *ref,
+                                     const uint32_t *counts, int64_t n, int threads, int append) {
+  FILE *f = fopen(path, append ? "ab" : "wb");
+  if (!f) return -1;
+  if (threads < 1) threads = 1;
+  const size_t clen = strlen(chrom);
+  const int64_t CH = 1 << 16;
+  const int64_t nch = (n + CH - 1) / CH;
+  int rc = 0;
+  for (int64_t c0 = 0; c0 < nch; c0 += threads) {
+    const int nt = (int)std::min<int64_t>(threads, nch - c0);
+    std::vector<std::string> bufs(nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) {
+      th.emplace_back([&, t]() {
+        const int64_t lo = (c0 + t) * CH, hi = std::min(n, lo + CH);
+        std::string &out = bufs[t];
+        out.resize((size_t)(hi - lo) * (clen + 420));
+        char *p = &out[0];
+        for (int64_t i = lo; i < hi; ++i) {
+          const uint32_t *r = counts + i * 26;
+          memcpy(p, chrom, clen);
+          p += clen;
+          *p++ = '\t';
+          p = put_u32(p, (uint32_t)(pos[i] + 1));
+          *p++ = '\t';
+          *p++ = (char)ref[i];
+          memcpy(p, "\tDP|NC|CC|BC|BQ|BCf|BCr\t", 24);
+          p += 24;
+          p = put_u32(p, r[0]);
+          *p++ = '|';
+          p = put_u32(p, r[1]);
+          *p++ = '|';
+          p = put_vec6(p, r + 2);  // CC
+          uint32_t bc[6];
+          for (int k = 0; k < 6; ++k) bc[k] = r[8 + k] + r[14 + k];
+          p = put_vec6(p, bc);      // BC
+          p = put_vec6(p, r + 20);  // BQ
+          p = put_vec6(p, r + 8);   // BCf
+          p = put_vec6(p, r + 14);  // BCr
+          p[-1] = '\n';
+        }
+        out.resize((size_t)(p - &out[0]));
+      });
+    }
+    for (auto &t : th) t.join();
+    for (int t = 0; t < nt; ++t)
+      if (fwrite(bufs[t].data(), 1, bufs[t].size(), f) != bufs[t].size()) rc = -2;
+  }
+  fclose(f);
+  return rc;
+}

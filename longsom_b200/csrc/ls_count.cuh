@@ -93,7 +93,8 @@ __device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t ti
 
 // shared-memory reduction on a 32-bit shared-window address (no generic->shared conversion per base)
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
-  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+  // no "memory" clobber: nothing reads the accumulators before the CTA barrier, so loads may move across
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
 
 // hs = shared address of hist[strand][0]: the (class, strand) row of class c starts 2*LS_TILE words further per class

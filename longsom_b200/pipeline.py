@@ -5,6 +5,7 @@ Reference counterparts: BaseCellCounter.main / run_interval / concatenate_sort_t
 (BaseCellCounter.py:22-79,182-320,344-409).  GPU selection cannot be a CLI flag (the Snakemake
 rules stay unchanged), so it comes from the environment: LONGSOM_GPUS="0,1,2,3" or LONGSOM_GPUS=4.
 """
+import ctypes as C
 import os
 import threading
 import time
@@ -163,10 +164,21 @@ def write_counter_tsv(out_file, ID, sites: SiteCounts, bam_names):
         out.write("##fileDate=%s\n" % time.strftime("%d/%m/%Y"))
         out.write(COUNTER_CONCEPTS + "\n")
         out.write("\t".join(["#CHROM", "POS", "REF", "INFO", str(ID)]) + "\n")
-        tids = np.unique(sites.tid)
-        for t in sorted(tids.tolist(), key=lambda t: bam_names[t]):
-            m = sites.tid == t
-            out.writelines(format_counter_lines(bam_names[t], sites.pos[m], sites.ref[m], sites.counts[m]))
+    host = bamio._load_host()
+    host.ls_write_counter_rows.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int, C.c_int]
+    host.ls_write_counter_rows.restype = C.c_int
+    tids = np.unique(sites.tid)
+    for t in sorted(tids.tolist(), key=lambda t: bam_names[t]):
+        # rows of one contig are contiguous (sites are ordered by window = (tid, start)) -> native formatter
+        lo, hi = int(np.searchsorted(sites.tid, t, "left")), int(np.searchsorted(sites.tid, t, "right"))
+        pos = np.ascontiguousarray(sites.pos[lo:hi])
+        ref = np.ascontiguousarray(sites.ref[lo:hi])
+        cnt = np.ascontiguousarray(sites.counts[lo:hi])
+        rc = host.ls_write_counter_rows(os.fsencode(out_file), bam_names[t].encode(), pos.ctypes.data, ref.ctypes.data,
+                                        cnt.ctypes.data, hi - lo, min(16, os.cpu_count() or 1), 1)
+        if rc != 0:
+            raise IOError("ls_write_counter_rows(%s) failed: %d" % (out_file, rc))
     return True
 
 
