@@ -71,7 +71,7 @@ struct TileSmemT {
   // the 4-base step needs no branches.  PACKED: cnt<<20|bq; else rows [0..17] counts, [18..35] quality sums.
   uint32_t hist[PACKED ? K1_ROWS : 2 * K1_ROWS][LS_TILE];
   uint32_t dupcc[3][LS_TILE];                // (cell, class) already seen at the site: class c in half-word c/3 of row c%3
-  uint32_t lut2[256];                        // BAM base byte (2 nibbles) -> two 16-bit byte offsets of the class row pair
+  uint32_t lut2[16];                         // BAM nibble code -> byte offset of the class row pair (dump rows if ignored)
   uint32_t dupnc[LS_TILE];                   // entries whose cell was already seen at the site (any class)
   uint32_t acx[LS_TILE];                     // alt entries of visible-but-uncounted reads (--min_ac > 0)
   uint32_t seen[K1_WARPS][LS_TILE / 4];      // per warp: class bits (1 byte per site) of the current same-cell run
@@ -249,12 +249,12 @@ __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSme
                 if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
                 okm &= m;
               }
-              const uint32_t l0 = sm.lut2[h & 255u], l1 = sm.lut2[h >> 8];
-              const uint32_t rowb = strand + (uint32_t)((sbase + d0) >> 2) * 4u;
+              const int c4 = (sbase + d0) >> 2;  // site of byte 0, divided by 4 (arithmetic shift: -1 in the head word)
+              const uint32_t rowb = strand + (uint32_t)c4 * 4u;
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const uint32_t lw = (j < 2) ? l0 : l1;
-                uint32_t off = (j & 1) ? (lw >> 16) : (lw & 0xffffu);
+                // 16-entry table: every lane pair reads the same word (broadcast) or different banks -> conflict-free
+                uint32_t off = sm.lut2[(h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u];
                 if (!((okm >> (8 * j + 7)) & 1u)) off = K1_DUMP_OFF;
                 const uint32_t q = (w >> (8 * j)) & 255u;
                 const uint32_t addr = rowb + colb[j] + off;
@@ -265,7 +265,16 @@ __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSme
                   red_shared_add(addr + (uint32_t)K1_ROWS * LS_TILE * 4u, q);
                 }
                 if (SEEN) {
-                  if (off != K1_DUMP_OFF) note_seen<PACKED>(sm, seen, sbase + d0 + j, (int)(off / K1_CLASS_STRIDE));
+                  if (off != K1_DUMP_OFF) {  // same-cell duplicate marks; (site & 3) and the column are warp-uniform per j
+                    const int tj = a4 + j;
+                    const int sh = 8 * (tj & 3);
+                    const uint32_t cls = off / K1_CLASS_STRIDE;
+                    const uint32_t bit = (1u << cls) << sh;
+                    const uint32_t old = atomicOr(&seen[c4 + (tj >> 2)], bit);
+                    const uint32_t dcol = (uint32_t)(c4 + (int)(colb[j] >> 2));
+                    if ((old & bit) && cls < 6u) atomicAdd(&sm.dupcc[0][0] + (cls % 3u) * LS_TILE + dcol, 1u << (16u * (cls / 3u)));
+                    if ((old >> sh) & 255u) atomicAdd(&sm.dupnc[dcol], 1u);
+                  }
                 }
               }
             }
@@ -351,12 +360,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
       sm.dupnc[i] = 0u;
       sm.acx[i] = 0u;
     }
-    for (int i = threadIdx.x; i < 256; i += K1_THREADS) {
-      // byte = (base g: high nibble, base g+1: low nibble); ignored codes -> the dump rows (class 8)
-      const uint32_t o0 = (uint32_t)class_of_code((uint32_t)i >> 4) * K1_CLASS_STRIDE;
-      const uint32_t o1 = (uint32_t)class_of_code((uint32_t)i & 15u) * K1_CLASS_STRIDE;
-      sm.lut2[i] = o0 | (o1 << 16);
-    }
+    if (threadIdx.x < 16)  // BAM nibble code -> byte offset of the class row pair; ignored codes -> dump rows (class 8)
+      sm.lut2[threadIdx.x] = (uint32_t)class_of_code((uint32_t)threadIdx.x) * K1_CLASS_STRIDE;
     if (threadIdx.x == 0) {
       sm.next = 0;
       sm.npass = 0;
