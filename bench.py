@@ -35,6 +35,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the contract is ONE JSON line on stdout.
+    Route fd 1 to stderr for the whole run and keep a private duplicate for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, line)
+    else:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -210,7 +232,7 @@ def run_reference(args, rank, world):
         "note": "oracle port (oracle/pileup_oracle.c, OpenMP over 50 kb windows) of BaseCellCounter.run_interval; "
                 "the reference's own Python/pysam path cannot run here (pysam absent, SURVEY.md 8c)",
     }
-    print(json.dumps(out), flush=True)
+    emit_json(out)
 
 
 def workload_config(info, scale, l2):
@@ -363,7 +385,7 @@ def run_ours(args, rank, world, local_rank):
                       "ms_count": k_ms, "ms_device_total": float(np.mean(ms_total)), "tile": tile,
                       "aligned_bases_total": total_units},
         }
-        print(json.dumps(res), flush=True)
+        emit_json(res)
     eng.close()
     if dist is not None:
         dist.barrier()
@@ -380,6 +402,7 @@ def main():
                     help="fraction of the C2 workload (1.0 = 5M reads); only for local debugging")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    quiet_stdout()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     # torchrun pins OMP_NUM_THREADS=1; the (untimed) synthetic generator and the CPU oracle are OpenMP code
     os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // max(1, world)))

@@ -70,9 +70,9 @@ def test_betabinom_sf_vs_scipy(engine, ab):
         small = n <= 10000
         # tolerance of SURVEY.md 8(c): |dp| <= 1e-9*p + 1e-12 (scipy itself carries 1e-13..1e-16
         # absolute cancellation noise in 1-cdf); for n > 1e4 the reference's lgam amplifies a
-        # 1-ulp log() difference to ~1e-10 absolute, so the absolute term is 1e-9 there.
+        # 1-ulp log() difference; measured max deviation there is 5e-13 (profiles/README.md), bound 1e-11.
         assert np.all(np.abs(p[small] - ref[small]) <= 1e-9 * ref[small] + 1e-12), np.abs(p - ref)[small].max()
-        assert np.all(np.abs(p[~small] - ref[~small]) <= 1e-9 * ref[~small] + 1e-9), np.abs(p - ref)[~small].max()
+        assert np.all(np.abs(p[~small] - ref[~small]) <= 1e-9 * ref[~small] + 1e-11), np.abs(p - ref)[~small].max()
         assert np.array_equal(np.round(p, 4), np.round(ref, 4))
 
 
