@@ -337,9 +337,10 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
   const uint32_t part = blockIdx.x;
-  if (part >= *a.n_parts) return;
+  const uint32_t pslot = a.part_slot[part];
+  if (pslot == 0xffffffffu) return;  // unused entry between the heavy (front) and light (back) parts
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t slot = a.part_slot[part];
+  const int64_t slot = pslot;
   const uint32_t pk = a.part_k[part];
   const uint32_t nparts = a.slot_nparts[slot];
   const int64_t tile = a.slot_tile[slot];
@@ -526,12 +527,13 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
   if (last_part && threadIdx.x == 0) a.npass[slot] = sm.npass;
 }
 
-// One CTA per slot: split the slot into parts, register them, and zero the HBM slot of
+// One CTA per slot: split the slot into parts, register them (part_slot[] pre-set to 0xffffffff), zero the HBM slot of
 // multi-part tiles (their parts merge with atomics).
 __global__ void __launch_bounds__(128) part_build_kernel(const uint32_t *__restrict__ slot_lo, int64_t n_slots,
                                                          uint32_t *__restrict__ part_slot, uint32_t *__restrict__ part_k,
                                                          uint32_t *__restrict__ slot_nparts, uint32_t *__restrict__ slot_done,
-                                                         uint32_t *__restrict__ n_parts, uint32_t *__restrict__ out,
+                                                         uint32_t *__restrict__ n_parts, uint32_t *__restrict__ n_light,
+                                                         uint32_t max_parts, uint32_t *__restrict__ out,
                                                          uint32_t *__restrict__ acbuf) {
   const int64_t slot = blockIdx.x;
   if (slot >= n_slots) return;
@@ -539,7 +541,11 @@ __global__ void __launch_bounds__(128) part_build_kernel(const uint32_t *__restr
   const uint32_t np = n == 0 ? 1u : (n + K1_PART_SEGS - 1) / K1_PART_SEGS;
   __shared__ uint32_t base;
   if (threadIdx.x == 0) {
-    base = atomicAdd(n_parts, np);
+    // deep tiles first: their parts sit at the front of the grid, shallow tiles fill in behind (no long tail)
+    if (n >= (uint32_t)K1_PART_SEGS / 2)
+      base = atomicAdd(n_parts, np);
+    else
+      base = max_parts - np - atomicAdd(n_light, np);
     slot_nparts[slot] = np;
     slot_done[slot] = 0;
   }

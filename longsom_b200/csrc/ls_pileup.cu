@@ -326,6 +326,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   uint64_t *d_nslot_total = reinterpret_cast<uint64_t *>(d_aligned + 3);
   uint32_t *d_nparts = reinterpret_cast<uint32_t *>(d_aligned + 4);
   uint32_t *d_longrun = reinterpret_cast<uint32_t *>(d_aligned + 5);
+  uint32_t *d_nlight = reinterpret_cast<uint32_t *>(d_aligned + 6);
 
   LS_CK(cudaEventRecord(ctx->ev[0], st));
   uint64_t h_tot[6] = {0, 0, 0, 0, 0, 0};
@@ -423,9 +424,11 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     LS_CK(ctx->slot_nparts.ensure((size_t)n_slots * 4));
     LS_CK(ctx->slot_done.ensure((size_t)n_slots * 4));
     if (params->min_ac > 0) LS_CK(ctx->acbuf.ensure((size_t)n_slots * LS_TILE * 4));
+    LS_CK(cudaMemsetAsync(ctx->part_slot.p, 0xff, (size_t)max_parts * 4, st));
     part_build_kernel<<<(unsigned)n_slots, 128, 0, st>>>(
         ctx->slot_lo.as<uint32_t>(), n_slots, ctx->part_slot.as<uint32_t>(), ctx->part_k.as<uint32_t>(),
-        ctx->slot_nparts.as<uint32_t>(), ctx->slot_done.as<uint32_t>(), d_nparts, ctx->slot_out.as<uint32_t>(),
+        ctx->slot_nparts.as<uint32_t>(), ctx->slot_done.as<uint32_t>(), d_nparts, d_nlight, (uint32_t)max_parts,
+        ctx->slot_out.as<uint32_t>(),
         params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr);
     ++launches;
     CountArgs ca;
