@@ -39,7 +39,7 @@ def run_ref(script, args, log, produces=None):
 
 def candidates_from_step2(step2_path, out_path):
     """Deterministic candidate list for the genotype scripts: every PASS row plus every tenth other row
-    (the pipeline would use step3 output / HCCV, which are out of scope; same column layout)."""
+    (a wider set than step3's PASS rows, which are too few here to exercise the genotype kernels; same column layout)."""
     k = 0
     with open(step2_path) as f, open(out_path, "w") as o:
         for line in f:
@@ -50,6 +50,61 @@ def candidates_from_step2(step2_path, out_path):
             if cols[5] == "PASS" or k % 10 == 0:
                 o.write(line)
             k += 1
+
+
+# (name suffix, deltaVAF, deltaMCF, min_ac_reads, min_ac_cells, clust_dist): the workflow's LongSom settings
+# (config.yaml:81-83 with the 10 kb cluster distance) and a loose set that leaves PASS / clustered rows
+STEP3_PARAMS = (("step3", 0.05, 0.3, 3, 2, 10000), ("step3_loose", 0.05, 0.05, 1, 1, 50))
+
+
+def step3_stage(step2_path, out, log, param_sets=STEP3_PARAMS):
+    """BaseCellCalling.step3 (8f-1) on a step2 table -> {golden name: path}."""
+    res = {}
+    for name, dvaf, dmcf, mr, mc, cd in param_sets:
+        pre = os.path.join(out, name)
+        run_ref("SNVCalling/BaseCellCalling.step3.py", ["--infile", step2_path, "--outfile", pre, "--deltaVAF", dvaf,
+                "--deltaMCF", dmcf, "--min_ac_reads", mr, "--min_ac_cells", mc, "--clust_dist", cd], log)
+        res[name + ".tsv"] = pre + ".calling.step3.tsv"
+        res[name + ".unfiltered.tsv"] = pre + ".calling.step3.unfiltered.tsv"
+    return res
+
+
+def write_golden(gdir, res):
+    os.makedirs(gdir, exist_ok=True)
+    sizes = {}
+    for name, path in res.items():
+        data = open(path, "rb").read()
+        with gzip.GzipFile(os.path.join(gdir, name + ".gz"), "wb", mtime=0) as g:
+            g.write(data)
+        sizes[name] = len(data)
+    return sizes
+
+
+def step3_only(cases):
+    """`make_golden.py --step3 [case ...]`: (re)generate only the step3 goldens, from the committed step2
+    goldens (g1, g2) and from the fabricated branch-coverage table (s3); other golden files are untouched."""
+    import step3_inputs
+    for case in cases:
+        work = tempfile.mkdtemp(prefix="ls_golden_s3_")
+        log, gdir = [], os.path.join(ROOT, "tests", "golden", case)
+        if case == "s3":
+            table = step3_inputs.write_table(os.path.join(work, "step2_fabricated.tsv"))
+            res = {"step2_fabricated.tsv": table}
+            res.update(step3_stage(table, work, log, (("step3", 0.2, 0.25, 3, 2, 1000),)))
+            manifest = {"case": case, "generated_by": "oracle/make_golden.py --step3 (tests/support/step3_inputs.py -> "
+                        "reference BaseCellCalling.step3.py)"}
+        else:
+            table = os.path.join(work, "step2.tsv")
+            with gzip.open(os.path.join(gdir, "step2.tsv.gz"), "rb") as f, open(table, "wb") as o:
+                o.write(f.read())
+            res = step3_stage(table, work, log)
+            manifest = json.load(open(os.path.join(gdir, "manifest.json")))
+        sizes = write_golden(gdir, res)
+        manifest.setdefault("bytes", {}).update(sizes)
+        manifest["reference_commands"] = [c for c in manifest.get("reference_commands", []) if "step3" not in c] + log
+        json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, default=str)
+        print(case, "->", gdir, sizes)
+        shutil.rmtree(work, ignore_errors=True)
 
 
 def reference_pipeline(case, work, log):
@@ -88,6 +143,7 @@ def reference_pipeline(case, work, log):
             p["editing_gz"], "--pon_SR", p["pon_sr"], "--pon_LR", "--gnomAD_db", p["gnomad"], "--gnomAD_max", 0.01,
             "--min_distance", 5], log)  # script default: exercises the 3-row 'Clustered' logic
     res["step2_gz.tsv"] = step2gz
+    res.update(step3_stage(step2, out, log))
     cand = os.path.join(out, "candidates.tsv")
     candidates_from_step2(step2, cand)
     res["candidates.tsv"] = cand
@@ -109,6 +165,8 @@ def reference_pipeline(case, work, log):
 
 def main():
     import pipeline_inputs as pi
+    if sys.argv[1:2] == ["--step3"]:
+        return step3_only(sys.argv[2:] or list(pi.CASES) + ["s3"])
     cases = sys.argv[1:] or list(pi.CASES)
     for case in cases:
         work = os.path.join(tempfile.gettempdir(), "ls_golden_work_%s" % case)
@@ -116,13 +174,7 @@ def main():
         log = []
         res = reference_pipeline(case, work, log)
         gdir = os.path.join(ROOT, "tests", "golden", case)
-        os.makedirs(gdir, exist_ok=True)
-        sizes = {}
-        for name, path in res.items():
-            data = open(path, "rb").read()
-            with gzip.GzipFile(os.path.join(gdir, name + ".gz"), "wb", mtime=0) as g:
-                g.write(data)
-            sizes[name] = len(data)
+        sizes = write_golden(gdir, res)
         json.dump({"case": case, "synth": pi.CASES[case], "reference_commands": log, "bytes": sizes,
                    "generated_by": "oracle/make_golden.py (reference scripts from /root/reference over oracle/shims)"},
                   open(os.path.join(gdir, "manifest.json"), "w"), indent=1, default=str)

@@ -219,3 +219,38 @@ def test_shim_engine_matches_c_oracle_on_corner_cases(built):
             dp_shim[col.pos] = n
     assert dp_shim == dp_oracle
     assert len(dp_shim) > 50
+
+
+STEP3_SETS = {"g1": (("step2.tsv", "step3", 0.05, 0.3, 3, 2, 10000), ("step2.tsv", "step3_loose", 0.05, 0.05, 1, 1, 50)),
+              "g2": (("step2.tsv", "step3", 0.05, 0.3, 3, 2, 10000), ("step2.tsv", "step3_loose", 0.05, 0.05, 1, 1, 50)),
+              "s3": (("step2_fabricated.tsv", "step3", 0.2, 0.25, 3, 2, 1000),)}
+
+
+@pytest.mark.parametrize("case", [c for c in STEP3_SETS if os.path.isdir(os.path.join(GOLD, c))])
+def test_step3_matches_reference(case, tmp_path):
+    """the step3 drop-in (host only) against the reference script's two output files; case s3
+    is the fabricated table that reaches the chrM / multi-allelic / cluster branches."""
+    from longsom_b200.cli.step3 import main
+    for table, name, dvaf, dmcf, mr, mc, cd in STEP3_SETS[case]:
+        src = os.path.join(str(tmp_path), table)
+        with gzip.open(os.path.join(GOLD, case, table + ".gz"), "rb") as f, open(src, "wb") as o:
+            o.write(f.read())
+        pre = os.path.join(str(tmp_path), name)
+        main(["--infile", src, "--outfile", pre, "--deltaVAF", str(dvaf), "--deltaMCF", str(dmcf), "--min_ac_reads", str(mr),
+              "--min_ac_cells", str(mc), "--clust_dist", str(cd)])
+        assert_same(file_lines(pre + ".calling.step3.tsv"), gold_lines(case, name + ".tsv"), "step3 " + name)
+        assert_same(file_lines(pre + ".calling.step3.unfiltered.tsv"), gold_lines(case, name + ".unfiltered.tsv"),
+                    "step3 unfiltered " + name)
+
+
+def test_step3_wrapper_script_runs(tmp_path):
+    import subprocess
+    src = os.path.join(str(tmp_path), "in.tsv")
+    with gzip.open(os.path.join(GOLD, "s3", "step2_fabricated.tsv.gz"), "rb") as f, open(src, "wb") as o:
+        o.write(f.read())
+    pre = os.path.join(str(tmp_path), "w")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "workflow", "scripts", "SNVCalling", "BaseCellCalling.step3.py"),
+                        "--infile", src, "--outfile", pre, "--deltaVAF", "0.2", "--deltaMCF", "0.25", "--min_ac_reads", "3",
+                        "--min_ac_cells", "2", "--clust_dist", "1000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert_same(file_lines(pre + ".calling.step3.tsv"), gold_lines("s3", "step3.tsv"), "step3 wrapper")
