@@ -151,6 +151,24 @@ def clustered_indices(index_col, step3_col, clust_dist):
     return hit
 
 
+def _assign_rows(df, cols, values):
+    """df[cols] = per-row values.  On an EMPTY frame the reference's `df.apply(..., axis=1)` yields an empty
+    DataFrame and the assignment (or the next .str call) fails inside pandas; the same pandas call is made here so
+    that an input without any usable row ends the same way (non-zero exit, header-only outputs)."""
+    if len(df) == 0:
+        # pandas probes the row function with an empty Series; the reference's row functions raise on it
+        # (e.g. alt_dict[ALT[0]] on NaN), and pandas then hands back a copy of the (empty) frame -- same outcome here
+        probe = lambda x: x['__row_function_fails_on_the_probe__']
+        if isinstance(cols, list):
+            df[cols] = df.apply(probe, axis=1, result_type='expand')
+        else:
+            df[cols] = df.apply(probe, axis=1)
+    elif isinstance(cols, list):
+        df[cols] = pd.DataFrame(values, index=df.index, columns=cols)
+    else:
+        df[cols] = values
+
+
 def _contains_any(series, words):
     return series.map(lambda s: any(w in s for w in words)).astype(bool)
 
@@ -178,7 +196,7 @@ def variant_calling_step3(infile, out_prefix, deltaVAF, deltaMCF, chrM_conta, mi
     collapsed = [collapse_multiallelic(*row) for row in zip(
         df['REF'], df['ALT'], df['FILTER'], df['Cell_types'], df['Dp'], df['Nc'], df['Bc'], df['Cc'], df['VAF'],
         df['MCF'], df['Cancer'], df['Non-Cancer'])]
-    df[REPLACED] = pd.DataFrame(collapsed, index=df.index, columns=REPLACED)
+    _assign_rows(df, REPLACED, collapsed)
     df['INDEX'] = [('%s:%s:%s' % (c, s, a.split(',', 1)[0])) for c, s, a in zip(df['#CHROM'], df['Start'], df['ALT'])]
 
     is_mt = df['#CHROM'] == 'chrM'
@@ -190,18 +208,20 @@ def variant_calling_step3(infile, out_prefix, deltaVAF, deltaMCF, chrM_conta, mi
                              zip(mt['STEP3FILTER'], mt['Cell_types'], mt['Dp'], mt['VAF'], mt['MCF'])]
 
     df = df[~_contains_any(df['FILTER'], ('Min_cell_types',))]
-    df['STEP3FILTER'] = [cancer_support_verdict(f, a, ci, min_ac_reads, min_ac_cells)
-                         for f, a, ci in zip(df['STEP3FILTER'], df['ALT'], df['Cancer'])]
-    df['STEP3FILTER'] = [betabin_verdict(f, ct, cf)
-                         for f, ct, cf in zip(df['STEP3FILTER'], df['Cell_types'], df['Cell_type_Filter'])]
+    _assign_rows(df, 'STEP3FILTER', [cancer_support_verdict(f, a, ci, min_ac_reads, min_ac_cells)
+                                     for f, a, ci in zip(df['STEP3FILTER'], df['ALT'], df['Cancer'])])
+    _assign_rows(df, 'STEP3FILTER', [betabin_verdict(f, ct, cf) for f, ct, cf in
+                                     zip(df['STEP3FILTER'], df['Cell_types'], df['Cell_type_Filter'])])
     df = df[~_contains_any(df['FILTER'], ('Noisy_site', 'LC_Upstream', 'LC_Downstream', 'RNA_editing_db', 'PoN',
                                           'Cell_type_noise', 'gnomAD'))]
 
     df = pd.concat([df, mt])
     label = 'Clust_dist_%s' % clust_dist
     hit = clustered_indices(df['INDEX'], df['STEP3FILTER'], clust_dist)
-    df['STEP3FILTER'] = [(_tag(f, label) if ix in hit else f) for ix, f in zip(df['INDEX'], df['STEP3FILTER'])]
+    _assign_rows(df, 'STEP3FILTER', [(_tag(f, label) if ix in hit else f)
+                                     for ix, f in zip(df['INDEX'], df['STEP3FILTER'])])
     df.to_csv(unfiltered_path, sep='\t', index=False, mode='a')
+    df = df[~df['STEP3FILTER'].str.contains('dist', regex=True)]
     df[df['STEP3FILTER'] == 'PASS'].to_csv(final_path, sep='\t', index=False, mode='a')
     return df
 

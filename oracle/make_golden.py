@@ -69,6 +69,44 @@ def step3_stage(step2_path, out, log, param_sets=STEP3_PARAMS):
     return res
 
 
+# (name, min_dp, deltaVAF, deltaMCF, clust_dist): script defaults (= config.yaml CellTypeReannotation) and a loose set
+HCCV_PARAMS = (("hccv_variants", 20, 0.1, 0.4, 10000), ("hccv_variants_loose", 5, 0.05, 0.05, 30))
+
+
+def hccv_variants_stage(step2_path, out, log, param_sets=HCCV_PARAMS):
+    """HighConfidenceCancerVariants (8f-2) on a step2 table -> {golden name: path}.  A parameter set that leaves
+    no variant makes the reference fail inside pandas after writing its three files; that case is skipped here."""
+    res = {}
+    for name, min_dp, dvaf, dmcf, cd in param_sets:
+        pre = os.path.join(out, name)
+        try:
+            run_ref("CellTypeReannotation/HighConfidenceCancerVariants.py", ["--SNVs", step2_path, "--outfile", pre,
+                    "--min_dp", min_dp, "--deltaVAF", dvaf, "--deltaMCF", dmcf, "--clust_dist", cd], log)
+        except RuntimeError as e:
+            log.append("(reference failed, no golden) " + name + ": " + str(e).strip().splitlines()[-1][:120])
+            continue
+        for suf in ("", "2", "3"):
+            res[name + ".tsv" + suf] = pre + ".HCCV.tsv" + suf
+    return res
+
+
+REANNOT_PARAMS = (("reannot", 3, 0.2), ("reannot_loose", 1, 0.02), ("reannot_mid", 5, 0.03))   # (name, min_variants, min_frac)
+
+
+def reannotation_stage(hccv_genotypes, meta, out, log):
+    """CellTypeReannotation (8f-2) on the HCCV genotype table + a fabricated fusion table -> {golden name: path}."""
+    import step3_inputs
+    barcodes = [l.split("\t")[0] for l in open(meta)][1:]
+    fusions = step3_inputs.write_fusions(os.path.join(out, "reannot_fusions.tsv"), barcodes)
+    res = {"reannot_fusions.tsv": fusions}
+    for name, mv, mf in REANNOT_PARAMS:
+        dst = os.path.join(out, name + ".tsv")
+        run_ref("CellTypeReannotation/CellTypeReannotation.py", ["--SNVs", hccv_genotypes, "--fusions", fusions, "--outfile",
+                dst, "--meta", meta, "--min_variants", mv, "--min_frac", mf], log)
+        res[name + ".tsv"] = dst
+    return res
+
+
 def write_golden(gdir, res):
     os.makedirs(gdir, exist_ok=True)
     sizes = {}
@@ -81,8 +119,9 @@ def write_golden(gdir, res):
 
 
 def step3_only(cases):
-    """`make_golden.py --step3 [case ...]`: (re)generate only the step3 goldens, from the committed step2
-    goldens (g1, g2) and from the fabricated branch-coverage table (s3); other golden files are untouched."""
+    """`make_golden.py --step3 [case ...]`: (re)generate only the goldens of the host-only stages after the path
+    (step3, HighConfidenceCancerVariants, CellTypeReannotation) from the committed step2 / HCCV-genotype goldens
+    (g1, g2) and from the fabricated branch-coverage table (s3); other golden files are untouched."""
     import step3_inputs
     for case in cases:
         work = tempfile.mkdtemp(prefix="ls_golden_s3_")
@@ -91,6 +130,7 @@ def step3_only(cases):
             table = step3_inputs.write_table(os.path.join(work, "step2_fabricated.tsv"))
             res = {"step2_fabricated.tsv": table}
             res.update(step3_stage(table, work, log, (("step3", 0.2, 0.25, 3, 2, 1000),)))
+            res.update(hccv_variants_stage(table, work, log))
             manifest = {"case": case, "generated_by": "oracle/make_golden.py --step3 (tests/support/step3_inputs.py -> "
                         "reference BaseCellCalling.step3.py)"}
         else:
@@ -98,10 +138,17 @@ def step3_only(cases):
             with gzip.open(os.path.join(gdir, "step2.tsv.gz"), "rb") as f, open(table, "wb") as o:
                 o.write(f.read())
             res = step3_stage(table, work, log)
+            res.update(hccv_variants_stage(table, work, log))
+            import pipeline_inputs as pi
+            paths, _ = pi.write_inputs(case, work)
+            geno = os.path.join(work, "hccv.tsv")
+            with gzip.open(os.path.join(gdir, "hccv.tsv.gz"), "rb") as f, open(geno, "wb") as o:
+                o.write(f.read())
+            res.update(reannotation_stage(geno, paths["meta"], work, log))
             manifest = json.load(open(os.path.join(gdir, "manifest.json")))
         sizes = write_golden(gdir, res)
         manifest.setdefault("bytes", {}).update(sizes)
-        manifest["reference_commands"] = [c for c in manifest.get("reference_commands", []) if "step3" not in c] + log
+        manifest["reference_commands"] = [c for c in manifest.get("reference_commands", []) if not any(w in c for w in ("step3", "HighConfidence", "hccv_variants", "CellTypeReannotation.py"))] + log
         json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, default=str)
         print(case, "->", gdir, sizes)
         shutil.rmtree(work, ignore_errors=True)
@@ -144,6 +191,7 @@ def reference_pipeline(case, work, log):
             "--min_distance", 5], log)  # script default: exercises the 3-row 'Clustered' logic
     res["step2_gz.tsv"] = step2gz
     res.update(step3_stage(step2, out, log))
+    res.update(hccv_variants_stage(step2, out, log))
     cand = os.path.join(out, "candidates.tsv")
     candidates_from_step2(step2, cand)
     res["candidates.tsv"] = cand
@@ -160,6 +208,7 @@ def reference_pipeline(case, work, log):
             p["meta"], "--outfile", hccv, "--alt_flag", "All", "--nprocs", 1, "--min_mq", 60, "--pvalue", 0.01,
             "--chrM_contaminant", "True", "--tmp_dir", os.path.join(work, "tmp_h")], log)
     res["hccv.tsv"] = hccv
+    res.update(reannotation_stage(hccv, p["meta"], out, log))
     return res
 
 

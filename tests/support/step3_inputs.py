@@ -92,3 +92,18 @@ def write_table(path, seed=20260101, n=420):
         for r in rows(seed, n):
             o.write("\t".join(str(x) for x in r) + "\n")
     return path
+
+
+def write_fusions(path, barcodes, seed=7):
+    """Fabricated CTAT-fusion table for CellTypeReannotation: '#FusionName', 'BC' (+ one ignored column),
+    with repeated (fusion, barcode) pairs and barcodes that are absent from the genotype table."""
+    rng = random.Random(seed)
+    names = ["GENEA--GENEB", "GENEC--GENED", "GENEE--GENEF"]
+    with open(path, "w") as o:
+        o.write("#FusionName\tBC\tJunctionReadCount\n")
+        picks = [b for i, b in enumerate(barcodes) if i % 5 == 0]
+        for b in picks:
+            for _ in range(rng.choice([1, 1, 2, 3])):
+                o.write("%s\t%s\t%d\n" % (rng.choice(names), b, rng.randrange(1, 9)))
+        o.write("GENEA--GENEB\tNOT_A_KNOWN_BARCODE\t2\n")
+    return path

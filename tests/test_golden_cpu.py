@@ -254,3 +254,61 @@ def test_step3_wrapper_script_runs(tmp_path):
                         "--min_ac_cells", "2", "--clust_dist", "1000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     assert_same(file_lines(pre + ".calling.step3.tsv"), gold_lines("s3", "step3.tsv"), "step3 wrapper")
+
+
+HCCV_SETS = (("hccv_variants", 20, 0.1, 0.4, 10000), ("hccv_variants_loose", 5, 0.05, 0.05, 30))
+
+
+@pytest.mark.parametrize("case", [c for c in STEP3_SETS if os.path.isdir(os.path.join(GOLD, c))])
+def test_hccv_variants_match_reference(case, tmp_path):
+    """HighConfidenceCancerVariants drop-in (host only): the final table and the two intermediate
+    dumps (.tsv2 after the depth filter, .tsv3 with the verdict column) against the reference's."""
+    from longsom_b200.cli.hccv_variants import main
+    table = STEP3_SETS[case][0][0]
+    src = os.path.join(str(tmp_path), table)
+    with gzip.open(os.path.join(GOLD, case, table + ".gz"), "rb") as f, open(src, "wb") as o:
+        o.write(f.read())
+    for name, min_dp, dvaf, dmcf, cd in HCCV_SETS:
+        pre = os.path.join(str(tmp_path), name)
+        argv = ["--SNVs", src, "--outfile", pre, "--min_dp", str(min_dp), "--deltaVAF", str(dvaf), "--deltaMCF", str(dmcf),
+                "--clust_dist", str(cd)]
+        if not os.path.exists(os.path.join(GOLD, case, name + ".tsv.gz")):
+            # the reference dies inside pandas when no variant survives (g2 with the default thresholds);
+            # the drop-in must not turn that into a silent empty success
+            with pytest.raises((AttributeError, ValueError, KeyError)):
+                main(argv)
+            continue
+        main(argv)
+        for suf in ("", "2", "3"):
+            assert_same(file_lines(pre + ".HCCV.tsv" + suf), gold_lines(case, name + ".tsv" + suf), "HCCV %s%s" % (name, suf))
+
+
+def test_reannotation_matches_reference(work):
+    """CellTypeReannotation drop-in on the golden HCCV genotype table (K1' output), the case's barcode
+    table and the committed fabricated fusion table; three (min_variants, min_frac) settings."""
+    from longsom_b200.cli.reannotate import main
+    case, d, p, data = work
+    for name in ("hccv.tsv", "reannot_fusions.tsv"):
+        with gzip.open(os.path.join(GOLD, case, name + ".gz"), "rb") as f, open(os.path.join(d, name), "wb") as o:
+            o.write(f.read())
+    for name, mv, mf in (("reannot", 3, 0.2), ("reannot_loose", 1, 0.02), ("reannot_mid", 5, 0.03)):
+        out = os.path.join(d, name + "_mine.tsv")
+        main(["--SNVs", os.path.join(d, "hccv.tsv"), "--fusions", os.path.join(d, "reannot_fusions.tsv"), "--outfile", out,
+              "--meta", p["meta"], "--min_variants", str(mv), "--min_frac", str(mf)])
+        assert_same(file_lines(out), gold_lines(case, name + ".tsv"), "CellTypeReannotation " + name)
+
+
+def test_filters_fail_like_reference_on_empty_selection(tmp_path):
+    """Only 'Non-Cancer' rows: the reference's pandas calls raise ValueError after the header has been written."""
+    from longsom_b200.cli import hccv_variants, step3
+    src = os.path.join(str(tmp_path), "in.tsv")
+    with gzip.open(os.path.join(GOLD, "s3", "step2_fabricated.tsv.gz"), "rt") as f, open(src, "w") as o:
+        for line in f:
+            if line.startswith("#") or line.split("\t")[6] == "Non-Cancer":
+                o.write(line)
+    with pytest.raises(ValueError):
+        step3.main(["--infile", src, "--outfile", os.path.join(str(tmp_path), "e"), "--deltaVAF", "0.1", "--deltaMCF", "0.3"])
+    with pytest.raises(ValueError):
+        hccv_variants.main(["--SNVs", src, "--outfile", os.path.join(str(tmp_path), "e"), "--min_dp", "20", "--deltaVAF", "0.1",
+                            "--deltaMCF", "0.3"])
+    assert os.path.exists(os.path.join(str(tmp_path), "e.calling.step3.tsv"))
