@@ -1,0 +1,64 @@
+/* longsom_host.h -- C-ABI of liblongsom_host.so, the CPU-side BAM/TSV codec library next to the CUDA
+ * library (include/longsom_b200.h).  No CUDA, no torch types: plain pointers and sizes.
+ *
+ * It replaces, for the hot path and the steps on either side of it, what the reference does through
+ * pysam / htslib and Python string formatting:
+ *   ls_bam_read ...........  pysam.AlignmentFile(bam) + per-record accessors
+ *                            (SNVCalling/BaseCellCounter.py:190-191,225-262; CellClustering/SingleCellGenotype.py:123)
+ *   ls_write_counter_rows .  the per-site row formatting of BaseCellCounter.run_interval (:297-309)
+ *   ls_bam_split ..........  PreProcessing/SplitBamCellTypes.py:39-192 (fetch / filter / trim / write / pysam.index)
+ * Binding: longsom_b200/bamio.py, pipeline.py, cli/splitbam.py (ctypes).
+ */
+#ifndef LONGSOM_HOST_H
+#define LONGSOM_HOST_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- BAM -> structure-of-arrays (the layout of ls_read_batch in longsom_b200.h) ------------------- */
+/* Inflates the whole BGZF file with `threads` workers and parses every record.  Always returns a
+ * handle; ls_bam_error() is non-NULL when decoding failed.  CB:Z tags are interned: array 4 holds a
+ * dense barcode id per read (-1 = no tag), ls_bam_barcode(i) the raw tag text. */
+void *ls_bam_read(const char *path, int threads);
+const char *ls_bam_error(void *h);
+void ls_bam_free(void *h);
+int64_t ls_bam_n_reads(void *h);
+int64_t ls_bam_n_cigar(void *h);
+int64_t ls_bam_n_bases(void *h);
+int32_t ls_bam_n_contigs(void *h);
+const char *ls_bam_contig_name(void *h, int i);
+int32_t ls_bam_contig_len(void *h, int i);
+int32_t ls_bam_n_barcodes(void *h);
+const char *ls_bam_barcode(void *h, int i);
+const char *ls_bam_header_text(void *h);
+/* which: 0 tid(i32) 1 pos(i32) 2 flag(u16) 3 mapq(u8) 4 barcode id(i32) 5 cigar_off(u32, n+1) 6 cigar(u32)
+ *        7 base_off(u64, n+1, multiples of 16) 8 l_qseq(i32) 9 seq4(u8, 2 bases/byte) 10 qual(u8) */
+const void *ls_bam_array(void *h, int which);
+
+/* ---- BaseCellCounter rows ---------------------------------------------------------------------- */
+/* Appends (append != 0) or writes n rows "chrom\tpos+1\tref\tDP|NC|CC|BC|BQ|BCf|BCr\t..." to path;
+ * counts = n x 26 words in the order of ls_site_counts.  Returns 0, -1 when the file cannot be opened. */
+int ls_write_counter_rows(const char *path, const char *chrom, const int32_t *pos, const uint8_t *ref,
+                          const uint32_t *counts, int64_t n, int threads, int append);
+
+/* ---- SplitBamCellTypes --------------------------------------------------------------------------- */
+/* Routes every placed record of the coordinate-sorted BAM in_path to out_paths[type of its barcode]
+ * (+ ".bai" each).  Barcode table: n_bc keys, key i = bc_blob[bc_off[i] .. bc_off[i+1]), type bc_type[i];
+ * the key of a read is its CB:Z text before the first '-'.  max_nm / max_nh < 0 and min_mapq <= 0 switch
+ * the respective filter off; n_trim > 0 zeroes the base qualities of the read ends (soft clips extend the
+ * trim; a clip of 20..29 bases counts as 30).  counters[36]: Total_reads, Pass_reads, CB_not_found,
+ * CB_not_matched, then [4 + mask] = reads dropped for reason set mask (1 nM, 2 nM_not_found, 4 NH,
+ * 8 NH_not_found, 16 MAPQ); first_seen[32]: 1-based ordinal of the first read dropped for that set.
+ * Returns 0, or -1 with a message in err (errors the reference raises -- trim longer than a read, a read
+ * without qualities, a non-string CB -- are reported, not skipped). */
+int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths, const char *bc_blob,
+                 const uint32_t *bc_off, const int32_t *bc_type, int64_t n_bc, int min_mapq, int max_nm, int max_nh,
+                 int n_trim, int threads, int level, int64_t *counters, int64_t *first_seen, char *err, int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

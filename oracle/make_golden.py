@@ -107,6 +107,39 @@ def reannotation_stage(hccv_genotypes, meta, out, log):
     return res
 
 
+# (name, extra CLI arguments): defaults of the workflow (PreProcessing.smk passes --min_MQ and --n_trim) and a set
+# with every filter on
+SPLIT_PARAMS = (("split", ["--min_MQ", 60, "--n_trim", 5]),
+                ("split_all", ["--min_MQ", 30, "--n_trim", 0, "--max_nM", 5, "--max_NH", 1]))
+
+
+def splitbam_stage(case, work, log):
+    """SplitBamCellTypes (8f-3) over the shim's BAM writer -> {golden name: path}: per output BAM a text dump of
+    its records (tests/support/pipeline_inputs.dump_bam_records) and the report without its run-time column."""
+    import pipeline_inputs as pi
+    bam, meta = pi.write_split_input(case, work)
+    res = {}
+    for name, extra in SPLIT_PARAMS:
+        outdir = os.path.join(work, name)
+        os.makedirs(outdir, exist_ok=True)
+        run_ref("PreProcessing/SplitBamCellTypes.py", ["--bam", bam, "--meta", meta, "--id", "s", "--outdir", outdir] + extra, log)
+        for fn in sorted(os.listdir(outdir)):
+            if fn.endswith(".bam"):
+                dump = os.path.join(outdir, fn + ".records.txt")
+                with open(dump, "w") as o:
+                    o.write("\n".join(pi.dump_bam_records(os.path.join(outdir, fn))) + "\n")
+                res["%s.%s.records.txt" % (name, fn[:-4])] = dump
+                assert os.path.exists(os.path.join(outdir, fn + ".bai"))
+        rep = os.path.join(outdir, "s.report.txt")
+        rows = [l.rstrip("\n").split("\t") for l in open(rep)]
+        keep = [i for i, k in enumerate(rows[0]) if k != "Total_time"]
+        with open(rep + ".notime", "w") as o:
+            for r in rows:
+                o.write("\t".join(r[i] for i in keep) + "\n")
+        res[name + ".report.txt"] = rep + ".notime"
+    return res
+
+
 def write_golden(gdir, res):
     os.makedirs(gdir, exist_ok=True)
     sizes = {}
@@ -145,10 +178,11 @@ def step3_only(cases):
             with gzip.open(os.path.join(gdir, "hccv.tsv.gz"), "rb") as f, open(geno, "wb") as o:
                 o.write(f.read())
             res.update(reannotation_stage(geno, paths["meta"], work, log))
+            res.update(splitbam_stage(case, work, log))
             manifest = json.load(open(os.path.join(gdir, "manifest.json")))
         sizes = write_golden(gdir, res)
         manifest.setdefault("bytes", {}).update(sizes)
-        manifest["reference_commands"] = [c for c in manifest.get("reference_commands", []) if not any(w in c for w in ("step3", "HighConfidence", "hccv_variants", "CellTypeReannotation.py"))] + log
+        manifest["reference_commands"] = [c for c in manifest.get("reference_commands", []) if not any(w in c for w in ("step3", "HighConfidence", "hccv_variants", "CellTypeReannotation.py", "SplitBam"))] + log
         json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, default=str)
         print(case, "->", gdir, sizes)
         shutil.rmtree(work, ignore_errors=True)
@@ -209,6 +243,7 @@ def reference_pipeline(case, work, log):
             "--chrM_contaminant", "True", "--tmp_dir", os.path.join(work, "tmp_h")], log)
     res["hccv.tsv"] = hccv
     res.update(reannotation_stage(hccv, p["meta"], out, log))
+    res.update(splitbam_stage(case, work, log))
     return res
 
 

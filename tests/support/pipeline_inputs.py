@@ -167,3 +167,73 @@ def write_inputs(case, workdir):
                 ref = chr(d.contig_seq(int(t))[int(q)]).upper()
                 f.write("%s\t%d\t%s\t%s\t%g\n" % (d.contig_names[t], int(q) + 1, ref, chr(a), 0.2 if k % 8 == 0 else 0.001))
     return p, d
+
+
+# ---- SplitBamCellTypes inputs / record dumps ----------------------------------------------
+def write_split_input(case, workdir):
+    """<workdir>/split_in.bam: the case's full BAM with nM / NH aux tags (some absent), three trailing reads
+    without a reference, and <workdir>/split_meta.tsv whose cell types contain blanks and a repeated barcode.
+    Returns (bam path, meta path)."""
+    import struct
+    d = build_batch(case)
+    b = d.batch
+    n = b.n_reads
+    tid = b.tid.copy()
+    pos = b.pos.copy()
+    flag = b.flag.copy()
+    tid[n - 3:] = -1          # unplaced reads sit at the end of a coordinate-sorted BAM
+    pos[n - 3:] = -1
+    flag[n - 3:] |= 4
+    b2 = ReadBatch(tid, pos, flag, b.mapq, b.cell, b.cigar_off, b.cigar, b.base_off, b.l_qseq, b.seq4, b.qual)
+    suf = CB_SUFFIX.get(case, "-1")
+
+    def extra(i):
+        out = b""
+        if i % 11:
+            out += b"nMC" + bytes([(i * 7919) % 9])
+        if i % 13:
+            out += b"NHC" + bytes([1 if (i * 31) % 10 else 1 + (i % 3)])
+        if i % 5 == 0:
+            out += b"xfi" + struct.pack("<i", i)
+        return out
+    bam = os.path.join(workdir, "split_in.bam")
+    bamio.write_bam(bam, d.contig_names, d.contig_lens, b2, cb_text(d, suf), extra_tags=extra)
+    meta = os.path.join(workdir, "split_meta.tsv")
+    with open(meta, "w") as f:
+        f.write("Index\tCell_type\n")
+        for c in range(d.n_cells):
+            ct = d.cell_type(c)
+            if ct != "Cancer":
+                ct = "T cell" if c % 3 == 0 else "Non-Cancer"
+            f.write("%s%s\t%s\n" % (synth.barcode_of(c), suf, ct))
+        f.write("%s%s\t%s\n" % (synth.barcode_of(0), suf, "T cell"))   # repeated barcode: the later row wins
+    return bam, meta
+
+
+def dump_bam_records(path):
+    """One line per record: name, flag, tid, pos, mapq, qualities (phred+33) and the md5 of the raw record --
+    enough to see what differs, strict enough to prove byte-for-byte passthrough.  Independent BAM walk
+    (gzip module over the BGZF members), used on both the reference-side and the drop-in outputs."""
+    import gzip
+    import hashlib
+    import struct
+    with gzip.open(path, "rb") as f:
+        buf = f.read()
+    assert buf[:4] == b"BAM\1"
+    l_text = struct.unpack_from("<I", buf, 4)[0]
+    q = 8 + l_text
+    n_ref = struct.unpack_from("<I", buf, q)[0]
+    q += 4
+    for _ in range(n_ref):
+        q += 8 + struct.unpack_from("<I", buf, q)[0]
+    lines = ["#header_md5=%s" % hashlib.md5(buf[:q]).hexdigest()]
+    while q + 4 <= len(buf):
+        bs = struct.unpack_from("<I", buf, q)[0]
+        r0 = q + 4
+        tid, pos, l_name, mapq, _bin, n_cig, flag, l_seq = struct.unpack_from("<iiBBHHHI", buf, r0)
+        qo = r0 + 32 + l_name + 4 * n_cig + (l_seq + 1) // 2
+        qual = "".join(chr(min(x, 93) + 33) for x in buf[qo:qo + l_seq])
+        lines.append("%s\t%d\t%d\t%d\t%d\t%s\t%s" % (buf[r0 + 32:r0 + 32 + l_name - 1].decode(), flag, tid, pos, mapq, qual,
+                                                     hashlib.md5(buf[q:r0 + bs]).hexdigest()))
+        q = r0 + bs
+    return lines

@@ -23,6 +23,18 @@ def test_abi_exports_every_declared_symbol(built):
     assert lib.ls_abi_version() == 1
 
 
+def test_host_abi_exports_every_declared_symbol(built):
+    """include/longsom_host.h <-> liblongsom_host.so (BAM decoder, TSV row writer, BAM splitter)."""
+    from longsom_b200 import bamio
+    hdr = open(os.path.join(ROOT, "include", "longsom_host.h")).read()
+    body = hdr[hdr.index("extern \"C\""):]
+    declared = set(re.findall(r"\b(ls_[a-z0-9_]+)\s*\(", body))
+    assert len(declared) >= 15
+    lib = bamio._load_host()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+
+
 def test_no_cuda_device_fails_loudly(built):
     import torch
     if torch.cuda.is_available():

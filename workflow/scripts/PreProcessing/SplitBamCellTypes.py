@@ -1,0 +1,12 @@
+#!/usr/bin/env python
+"""Drop-in replacement of the reference's workflow/scripts/PreProcessing/SplitBamCellTypes.py (same CLI, same outputs),
+backed by the B200-native longsom_b200 package.  Copy this workflow/ tree over the reference's, or
+point the Snakemake rules' script path here; nothing else in workflow/rules changes."""
+import os
+import sys
+
+sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..")))
+from longsom_b200.cli.splitbam import main  # noqa: E402
+
+if __name__ == '__main__':
+    main(sys.argv[1:])
