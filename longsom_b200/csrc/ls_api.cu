@@ -41,7 +41,7 @@ extern "C" int ls_ctx_destroy(ls_ctx *ctx) {
   DBuf *bufs[] = {&ctx->tid,       &ctx->pos,       &ctx->flag,      &ctx->mapq,       &ctx->cell,     &ctx->cigar_off,
                   &ctx->cigar,     &ctx->base_off,  &ctx->lq,        &ctx->seq4,       &ctx->qual,     &ctx->wtid,
                   &ctx->wstart,    &ctx->wend,      &ctx->wref_off,  &ctx->ref,        &ctx->wtile_base, &ctx->nseg,
-                  &ctx->seg_off,   &ctx->segs,      &ctx->keys_a,    &ctx->keys_b,     &ctx->vals_a,   &ctx->vals_b,
+                  &ctx->seg_off,   &ctx->segs,      &ctx->pieces,      &ctx->keys_a,    &ctx->keys_b,     &ctx->vals_a,   &ctx->vals_b,
                   &ctx->rs_hist,   &ctx->scan_tmp,  &ctx->counters,  &ctx->tile_flag,  &ctx->tile_rank, &ctx->slot_tile,
                   &ctx->slot_lo,   &ctx->slot_out,  &ctx->slot_mask, &ctx->slot_npass, &ctx->slot_off, &ctx->drop_keys,
                   &ctx->out_tid,   &ctx->out_pos,   &ctx->out_ref,   &ctx->out_counts, &ctx->l2_scratch, &ctx->g_a,

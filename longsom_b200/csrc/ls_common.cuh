@@ -52,10 +52,23 @@ struct DBuf {
 // one (read, tile) work item of the pileup-count kernel
 struct __align__(16) Segment {
   uint32_t read;   // read index in the batch
-  uint32_t cig;    // absolute index (into cigar[]) of the first op with events in the tile
-  int32_t x0;      // reference position where that op starts
-  uint32_t y0;     // query index where that op starts
+  uint32_t p0;     // first piece of the segment in pieces[]
+  uint32_t np;     // number of pieces (consecutive: a read's CIGAR visits a tile once)
+  uint32_t pad;
 };
+
+// One CIGAR op clipped to one tile, produced by the segment builder so that the count kernel does not walk
+// CIGARs: a match piece covers query bases [ya, ya + n) at tile columns [col, col + n); a deletion piece covers
+// n columns that all carry the quality of query base ya (htslib: qpos of a deletion = the next query base).
+// `ind` marks a piece whose last column is the op's last column and is followed by an insertion (1) or a
+// deletion (2): that column's class becomes I / D.  A ref-skip followed by an indel is a 1-column deletion piece.
+struct __align__(8) Piece {
+  uint32_t ya;
+  uint32_t meta;  // col: bits 0-8, n (1..512): bits 9-18, deletion-like: bit 19, ind: bits 20-21
+};
+__host__ __device__ __forceinline__ uint32_t piece_meta(uint32_t col, uint32_t n, uint32_t del, uint32_t ind) {
+  return col | (n << 9) | (del << 19) | (ind << 20);
+}
 
 struct ls_ctx {
   int device = 0;
@@ -77,12 +90,12 @@ struct ls_ctx {
   // ---- run state ----
   bool have_run = false;
   ls_count_params params = {};
-  DBuf nseg, seg_off, segs, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
+  DBuf nseg, seg_off, segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;
   DBuf drop_keys, rend, wcount, part_slot, part_k, slot_nparts, slot_done, acbuf;
   int64_t n_drop = 0;
   bool k1_attr_set = false;
-  int64_t n_segments = 0, n_slots = 0, n_sites = 0;
+  int64_t n_segments = 0, n_pieces = 0, n_slots = 0, n_sites = 0;
   int cell_bits = 0;
   uint64_t *sorted_keys = nullptr;
   uint32_t *sorted_vals = nullptr;

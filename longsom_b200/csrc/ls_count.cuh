@@ -38,7 +38,7 @@ __host__ __device__ __forceinline__ int swz(int s) { return ((s & 3) * (LS_TILE 
 
 struct CountArgs {
   const uint16_t *flag;
-  const uint32_t *cigar_off, *cigar;
+  const Piece *pieces;
   const uint64_t *base_off;
   const int32_t *lq;
   const uint8_t *seq4, *qual;
@@ -131,8 +131,7 @@ __device__ __forceinline__ void add_uncounted(TileSmemT<PACKED> &sm, int s, int 
 #define K1_CLASS_LUT 0x6888888288838108ull
 
 struct SegMeta {
-  uint32_t cig, kend, y0, lq;
-  int32_t x0;
+  uint32_t p0, np, lq;
   uint64_t boff;
   int strand;
 };
@@ -140,10 +139,8 @@ struct SegMeta {
 __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
   const Segment sg = a.segs[a.vals[i]];
   SegMeta m;
-  m.cig = sg.cig;
-  m.x0 = sg.x0;
-  m.y0 = sg.y0;
-  m.kend = a.cigar_off[sg.read + 1];
+  m.p0 = sg.p0;
+  m.np = sg.np;
   m.boff = a.base_off[sg.read];
   m.lq = (uint32_t)a.lq[sg.read];
   m.strand = (a.flag[sg.read] & LS_FLAG_REVERSE) ? 1 : 0;
@@ -152,78 +149,53 @@ __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
 
 __device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
   SegMeta r;
-  r.cig = __shfl_sync(0xffffffffu, m.cig, j);
-  r.kend = __shfl_sync(0xffffffffu, m.kend, j);
-  r.y0 = __shfl_sync(0xffffffffu, m.y0, j);
+  r.p0 = __shfl_sync(0xffffffffu, m.p0, j);
+  r.np = __shfl_sync(0xffffffffu, m.np, j);
   r.lq = __shfl_sync(0xffffffffu, m.lq, j);
-  r.x0 = __shfl_sync(0xffffffffu, m.x0, j);
   r.boff = __shfl_sync(0xffffffffu, m.boff, j);
   r.strand = __shfl_sync(0xffffffffu, m.strand, j);
   return r;
 }
 
-// ---- fast path: one segment, warp-cooperative; CIGAR ops fetched 32 at a time, match ops consumed
-// 128 query bases per step (4 per lane, one 32-bit quality word + one 16-bit base word) -----------
+// ---- one segment, warp-cooperative: its pieces (CIGAR ops clipped to the tile, precomputed by the segment
+// builder) are fetched 32 at a time; a match piece is consumed 128 query bases per step (4 per lane, one 32-bit
+// quality word + one 16-bit base word) ----------------------------------------------------------------------
 template <bool PACKED, bool SEEN, bool COUNTED>
 __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen,
-                                                     const SegMeta m, int32_t tile_start, int32_t tile_end,
-                                                     int lane, uint32_t hist_s) {
+                                                     const SegMeta m, int lane, uint32_t hist_s) {
   const uint8_t *__restrict__ qual = a.qual + m.boff;
   const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
   const uint32_t strand = hist_s + (uint32_t)m.strand * (LS_TILE * 4u);  // shared address of hist[strand][0]
   const uint32_t lq = m.lq;
-  int32_t x = m.x0;
-  uint32_t y = m.y0;
-  uint32_t k = m.cig;
-  while (k < m.kend && x < tile_end) {
-    const uint32_t kk = k + (uint32_t)lane;
-    const uint32_t c_l = kk < m.kend ? a.cigar[kk] : 0xfu;
-    const uint32_t c_n = kk + 1 < m.kend ? a.cigar[kk + 1] : 0xfu;
-    const int nwin = (int)((m.kend - k) < 32u ? (m.kend - k) : 32u);
-    for (int t = 0; t < nwin && x < tile_end; ++t) {
-      const uint32_t c = __shfl_sync(0xffffffffu, c_l, t);
-      const uint32_t cn = __shfl_sync(0xffffffffu, c_n, t);
-      const uint32_t op = c & 15u;
-      const int32_t len = (int32_t)(c >> 4);
-      const bool match = op_is_match(op);
-      if ((match || op == OP_D || op == OP_N) && len > 0 && x + len > tile_start) {
-        const int32_t last = x + len - 1;
-        int ind = 0;
-        if (last >= tile_start && last < tile_end) {
-          const uint32_t op2 = cn & 15u;
-          if (op2 == OP_D && op != OP_D)
-            ind = -1;
-          else if (op2 == OP_I)
-            ind = 1;
-          else if (op2 == OP_P)
-            ind = indel_after(a.cigar, k + (uint32_t)t, m.kend, op);
-        }
-        const int indcls = ind < 0 ? LS_CLASS_D : LS_CLASS_I;
-        const int32_t lo = x > tile_start ? x : tile_start;
-        const int32_t hi = (x + len) < tile_end ? (x + len) : tile_end;
-        if (!match) {  // deletion / ref-skip: every column carries the quality of the next query base
-          const uint32_t q = y < lq ? qual[y] : 0u;
+  for (uint32_t pb = 0; pb < m.np; pb += 32u) {
+    Piece pc;
+    pc.ya = 0u;
+    pc.meta = 0u;
+    if (pb + (uint32_t)lane < m.np) pc = a.pieces[m.p0 + pb + (uint32_t)lane];
+    const int nloc = (int)((m.np - pb) < 32u ? (m.np - pb) : 32u);
+    for (int t = 0; t < nloc; ++t) {
+      const uint32_t y0 = __shfl_sync(0xffffffffu, pc.ya, t);
+      const uint32_t meta = __shfl_sync(0xffffffffu, pc.meta, t);
+      const int sbase = (int)(meta & 511u);
+      const uint32_t n = (meta >> 9) & 1023u;
+      const uint32_t ind = (meta >> 20) & 3u;
+      const int indcls = ind == 2u ? LS_CLASS_D : LS_CLASS_I;
+      {
+        if ((meta >> 19) & 1u) {  // deletion / ref-skip columns: every column carries the quality of the next query base
+          const uint32_t q = y0 < lq ? qual[y0] : 0u;
           if ((int)q >= a.min_bq) {
-            if (op == OP_D) {
-              for (int32_t p = lo + lane; p < hi; p += 32) {
-                const int cls = (p == last && ind != 0) ? indcls : LS_CLASS_O;
-                if (COUNTED)
-                  add_entry<PACKED, SEEN>(sm, seen, p - tile_start, cls, q, strand);
-                else
-                  add_uncounted<PACKED>(sm, p - tile_start, cls);
-              }
-            } else if (ind != 0 && lane == 0) {
+            for (uint32_t p = (uint32_t)lane; p < n; p += 32u) {
+              const int cls = (p == n - 1u && ind != 0u) ? indcls : LS_CLASS_O;
               if (COUNTED)
-                add_entry<PACKED, SEEN>(sm, seen, last - tile_start, indcls, q, strand);
+                add_entry<PACKED, SEEN>(sm, seen, sbase + (int)p, cls, q, strand);
               else
-                add_uncounted<PACKED>(sm, last - tile_start, indcls);
+                add_uncounted<PACKED>(sm, sbase + (int)p, cls);
             }
           }
         } else {
-          const uint32_t ya = y + (uint32_t)(lo - x), yb = y + (uint32_t)(hi - x);  // query range inside the tile
+          const uint32_t ya = y0, yb = y0 + n;                                       // query range inside the tile
           const uint32_t ybl = yb < lq ? yb : lq;                                    // bases that exist
-          const int sbase = lo - tile_start;
-          const uint32_t ylast = (ind != 0) ? (y + (uint32_t)len - 1u) : 0xffffffffu;
+          const uint32_t ylast = (ind != 0) ? (yb - 1u) : 0xffffffffu;
           // the base that carries a following indel is handled on its own (below); the word loop stops before it
           const uint32_t yw = (ind != 0 && ylast < ybl) ? ylast : ybl;
           if (COUNTED && a.min_bq >= 0 && a.min_bq <= 128) {
@@ -319,16 +291,7 @@ __device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSme
           }
         }
       }
-      if (match) {
-        x += len;
-        y += (uint32_t)len;
-      } else if (op == OP_D || op == OP_N) {
-        x += len;
-      } else if (op == OP_I || op == OP_S) {
-        y += (uint32_t)len;
-      }
     }
-    k += (uint32_t)nwin;
   }
 }
 
@@ -419,16 +382,16 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
       const uint32_t runlen = (uint32_t)(j1 - j0) + ext;
       if (runlen == 1) {
         if (counted)
-          process_segment_fast<PACKED, false, true>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane, hist_s);
+          process_segment_fast<PACKED, false, true>(a, sm, seen, shfl_meta(mm, j0), lane, hist_s);
         else
-          process_segment_fast<PACKED, false, false>(a, sm, seen, shfl_meta(mm, j0), tile_start, tile_end, lane, hist_s);
+          process_segment_fast<PACKED, false, false>(a, sm, seen, shfl_meta(mm, j0), lane, hist_s);
       } else {
         for (int q = lane; q < LS_TILE / 4; q += 32) seen[q] = 0u;
         __syncwarp();
         for (int j = j0; j < j1; ++j)
-          process_segment_fast<PACKED, true, true>(a, sm, seen, shfl_meta(mm, j), tile_start, tile_end, lane, hist_s);
+          process_segment_fast<PACKED, true, true>(a, sm, seen, shfl_meta(mm, j), lane, hist_s);
         for (uint32_t e = 0; e < ext; ++e)
-          process_segment_fast<PACKED, true, true>(a, sm, seen, load_meta(a, cb + e), tile_start, tile_end, lane, hist_s);
+          process_segment_fast<PACKED, true, true>(a, sm, seen, load_meta(a, cb + e), lane, hist_s);
       }
     }
   }

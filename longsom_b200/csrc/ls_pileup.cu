@@ -10,8 +10,8 @@
 // owned by exactly one CTA, so all accumulation is shared-memory atomics and the
 // result leaves the SM with plain coalesced stores (no global atomics, no
 // zero-initialised global histograms).
-//   1. seg_count / seg_fill : one thread per read walks its CIGAR once and emits one
-//      Segment per (read, tile) pair that has at least one pileup entry.
+//   1. seg_build_kernel (ls_segments.cuh): one thread per read walks its CIGAR and emits one Segment per
+//      (read, tile) pair that has at least one pileup entry, plus the segment's Pieces (ops clipped to the tile).
 //   2. radix sort of segments by (tile, cell)  -> same-cell segments of a tile are adjacent.
 //   3. pileup_count_kernel : CTA per non-empty tile; a warp owns a run of same-cell
 //      segments, lanes stride consecutive reference positions (coalesced seq4/qual
@@ -25,162 +25,7 @@
 #define LS_TILE 512
 #endif
 
-struct SegArgs {
-  int64_t n_reads;
-  const int32_t *tid, *pos, *cell;
-  const uint16_t *flag;
-  const uint8_t *mapq;
-  const uint32_t *cigar_off, *cigar;
-  int64_t n_windows;
-  const int32_t *wtid, *wstart, *wend;
-  const int64_t *wtile_base;
-  int min_mq, cell_bits, emit_uncounted;
-  uint32_t uncounted_key;
-  const uint64_t *drop_keys;  // sorted (window<<32 | read) pairs removed by the depth cap
-  int64_t n_drop;
-};
-
-__device__ __forceinline__ int64_t first_window(const SegArgs &a, int32_t tid, int32_t x) {
-  // first window w with (wtid, wend) > (tid, x)
-  int64_t lo = 0, hi = a.n_windows;
-  while (lo < hi) {
-    int64_t m = (lo + hi) >> 1;
-    int32_t t = a.wtid[m];
-    bool le = (t < tid) || (t == tid && a.wend[m] <= x);
-    if (le)
-      lo = m + 1;
-    else
-      hi = m;
-  }
-  return lo;
-}
-
-__device__ __forceinline__ bool is_dropped(const SegArgs &a, int64_t w, uint32_t r) {
-  if (a.n_drop == 0) return false;
-  uint64_t key = ((uint64_t)w << 32) | r;
-  int64_t lo = 0, hi = a.n_drop;
-  while (lo < hi) {
-    int64_t m = (lo + hi) >> 1;
-    if (a.drop_keys[m] < key)
-      lo = m + 1;
-    else
-      hi = m;
-  }
-  return lo < a.n_drop && a.drop_keys[lo] == key;
-}
-
-// Walk one read; EMIT(tile, k, xk, yk) is called once per (read, tile) with entries.
-template <typename EMIT>
-__device__ __forceinline__ uint32_t walk_read(const SegArgs &a, int64_t r, uint64_t *aligned, int32_t *end_out,
-                                              EMIT emit) {
-  const uint32_t k0 = a.cigar_off[r], kend = a.cigar_off[r + 1];
-  const int32_t tid = a.tid[r];
-  const uint32_t flag = a.flag[r];
-  int32_t x = a.pos[r];
-  uint32_t y = 0;
-  uint64_t al = 0;
-  const bool engine_ok = read_passes_engine(flag, a.mapq[r], a.min_mq) && tid >= 0;
-  const bool counted = a.cell[r] >= 0 && !(flag & LS_FLAG_SUPPL);
-  const bool want = engine_ok && (counted || a.emit_uncounted);
-  int64_t last_tile = -1;
-  int64_t w = -1;
-  uint32_t n = 0;
-  for (uint32_t k = k0; k < kend; ++k) {
-    const uint32_t c = a.cigar[k];
-    const uint32_t op = c & 15u;
-    const int32_t len = (int32_t)(c >> 4);
-    if (op_is_match(op)) al += (uint64_t)len;
-    if (want && len > 0) {
-      int32_t xa = 0, xb = 0;
-      if (op_is_match(op) || op == OP_D) {
-        xa = x;
-        xb = x + len;
-      } else if (op == OP_N && indel_after(a.cigar, k, kend, op) != 0) {
-        xa = x + len - 1;  // a ref-skip whose last column carries a following indel
-        xb = x + len;
-      }
-      if (xb > xa) {
-        if (w < 0) w = first_window(a, tid, xa);
-        while (w < a.n_windows && a.wtid[w] == tid && a.wend[w] <= xa) ++w;
-        int64_t ww = w;
-        while (ww < a.n_windows && a.wtid[ww] == tid && a.wstart[ww] < xb) {
-          int32_t lo = xa > a.wstart[ww] ? xa : a.wstart[ww];
-          int32_t hi = xb < a.wend[ww] ? xb : a.wend[ww];
-          if (lo < hi && !is_dropped(a, ww, (uint32_t)r)) {
-            int64_t t0 = a.wtile_base[ww] + (lo - a.wstart[ww]) / LS_TILE;
-            int64_t t1 = a.wtile_base[ww] + (hi - 1 - a.wstart[ww]) / LS_TILE;
-            for (int64_t t = t0; t <= t1; ++t) {
-              if (t != last_tile) {
-                emit(n, t, k, x, y);
-                ++n;
-                last_tile = t;
-              }
-            }
-          }
-          if (a.wend[ww] >= xb) break;
-          ++ww;
-        }
-      }
-    }
-    if (op_is_match(op)) {
-      x += len;
-      y += (uint32_t)len;
-    } else if (op == OP_D || op == OP_N) {
-      x += len;
-    } else if (op == OP_I || op == OP_S) {
-      y += (uint32_t)len;
-    }
-  }
-  *aligned = al;
-  *end_out = x;
-  return n;
-}
-
-__global__ void __launch_bounds__(256) seg_count_kernel(SegArgs a, uint32_t *__restrict__ nseg,
-                                                        unsigned long long *__restrict__ n_aligned,
-                                                        int32_t *__restrict__ rend, uint32_t *__restrict__ wcount) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t al = 0;
-  if (r < a.n_reads) {
-    int32_t end;
-    uint32_t n = walk_read(a, r, &al, &end, [](uint32_t, int64_t, uint32_t, int32_t, uint32_t) {});
-    nseg[r] = n;
-    rend[r] = end;
-    // records each pileup() call (window) would fetch: overlap of [pos, bam_endpos) with the window
-    const int32_t tid = a.tid[r], p0 = a.pos[r];
-    if (wcount && tid >= 0 && read_passes_engine(a.flag[r], a.mapq[r], a.min_mq)) {
-      const int32_t e = end > p0 ? end : p0 + 1;
-      for (int64_t w = first_window(a, tid, p0); w < a.n_windows && a.wtid[w] == tid && a.wstart[w] < e; ++w)
-        atomicAdd(&wcount[w], 1u);
-    }
-  }
-  // block reduce of aligned bases
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) al += __shfl_xor_sync(0xffffffffu, al, o);
-  if ((threadIdx.x & 31) == 0 && al) atomicAdd(n_aligned, (unsigned long long)al);
-}
-
-__global__ void __launch_bounds__(256) seg_fill_kernel(SegArgs a, const uint32_t *__restrict__ seg_off,
-                                                       Segment *__restrict__ segs, uint64_t *__restrict__ keys) {
-  int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= a.n_reads) return;
-  const uint32_t off = seg_off[r];
-  const int32_t cell = a.cell[r];
-  const bool counted = cell >= 0 && !(a.flag[r] & LS_FLAG_SUPPL);
-  const uint64_t ck = counted ? (uint64_t)(uint32_t)cell : (uint64_t)a.uncounted_key;
-  const int cb = a.cell_bits;
-  uint64_t al;
-  int32_t end;
-  walk_read(a, r, &al, &end, [&](uint32_t i, int64_t t, uint32_t k, int32_t xk, uint32_t yk) {
-    Segment s;
-    s.read = (uint32_t)r;
-    s.cig = k;
-    s.x0 = xk;
-    s.y0 = yk;
-    segs[off + i] = s;
-    keys[off + i] = ((uint64_t)t << cb) | ck;
-  });
-}
+#include "ls_segments.cuh"
 
 // tile boundaries in the sorted key array
 __global__ void __launch_bounds__(256) tile_flag_kernel(const uint64_t *__restrict__ keys, int64_t n, int cell_bits,
@@ -318,8 +163,8 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   const int tile_bits = ls_bits_for((uint64_t)(ctx->n_tiles_total > 0 ? ctx->n_tiles_total - 1 : 0));
   SegArgs sa = make_seg_args(ctx, *params, params->min_ac > 0);
 
-  LS_CK(ctx->counters.ensure(64));
-  LS_CK(cudaMemsetAsync(ctx->counters.p, 0, 64, st));
+  LS_CK(ctx->counters.ensure(128));
+  LS_CK(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
   unsigned long long *d_aligned = ctx->counters.as<unsigned long long>();
   unsigned long long *d_events = d_aligned + 1;
   uint64_t *d_nseg_total = reinterpret_cast<uint64_t *>(d_aligned + 2);
@@ -330,59 +175,78 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
 
   LS_CK(cudaEventRecord(ctx->ev[0], st));
   uint64_t h_tot[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t h_seg[2] = {0, 0};
+  uint64_t *d_seg_totals = reinterpret_cast<uint64_t *>(d_aligned + 8);  // [0] segments, [1] pieces
   if (n > 0 && ctx->n_windows > 0) {
-    LS_CK(ctx->nseg.ensure((size_t)n * 4));
-    LS_CK(ctx->seg_off.ensure((size_t)n * 4));
-    LS_CK(ctx->rend.ensure((size_t)n * 4));
-    LS_CK(ctx->wcount.ensure((size_t)ctx->n_windows * 4));
     ctx->n_drop = 0;
     sa.n_drop = 0;
     // the depth cap can only fire in a window that fetches more than max_depth records
     const bool cap_possible = params->max_depth > 0 && n > (int64_t)params->max_depth;
-    if (cap_possible) LS_CK(cudaMemsetAsync(ctx->wcount.p, 0, (size_t)ctx->n_windows * 4, st));
-    seg_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sa, ctx->nseg.as<uint32_t>(), d_aligned,
-                                                                   ctx->rend.as<int32_t>(),
-                                                                   cap_possible ? ctx->wcount.as<uint32_t>() : nullptr);
-    ++launches;
     if (cap_possible) {
-      std::vector<uint32_t> wc((size_t)ctx->n_windows);
-      LS_CK(cudaMemcpyAsync(wc.data(), ctx->wcount.p, wc.size() * 4, cudaMemcpyDeviceToHost, st));
+      LS_CK(ctx->rend.ensure((size_t)n * 4));
+      LS_CK(ctx->wcount.ensure((size_t)ctx->n_windows * 4));
+      LS_CK(cudaMemsetAsync(ctx->wcount.p, 0, (size_t)ctx->n_windows * 4, st));
+    }
+    // Output sizes are only known after the walk: start from the previous run's sizes (or an estimate) and
+    // relaunch with exact sizes if the reservation counters ran past the buffers.
+    uint64_t seg_need = ctx->n_segments > 0 ? (uint64_t)ctx->n_segments : (uint64_t)n * 5 + 1024;
+    uint64_t piece_need = ctx->n_pieces > 0 ? (uint64_t)ctx->n_pieces : (uint64_t)ctx->n_cigar + seg_need;
+    std::vector<uint32_t> wc;
+    bool want_wcount = cap_possible;
+    for (int attempt = 0;; ++attempt) {
+      LS_CK(ctx->segs.ensure((size_t)seg_need * sizeof(Segment)));
+      LS_CK(ctx->pieces.ensure((size_t)piece_need * sizeof(Piece)));
+      LS_CK(ctx->keys_a.ensure((size_t)seg_need * 8));
+      LS_CK(ctx->keys_b.ensure((size_t)seg_need * 8));
+      LS_CK(ctx->vals_a.ensure((size_t)seg_need * 4));
+      LS_CK(ctx->vals_b.ensure((size_t)seg_need * 4));
+      seg_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+          sa, ctx->segs.as<Segment>(), ctx->keys_a.as<uint64_t>(), ctx->pieces.as<Piece>(), seg_need, piece_need,
+          reinterpret_cast<unsigned long long *>(d_seg_totals), d_aligned, want_wcount ? ctx->rend.as<int32_t>() : nullptr,
+          want_wcount ? ctx->wcount.as<uint32_t>() : nullptr);
+      ++launches;
+      LS_CK(cudaGetLastError());
+      if (want_wcount) {
+        wc.resize((size_t)ctx->n_windows);
+        LS_CK(cudaMemcpyAsync(wc.data(), ctx->wcount.p, wc.size() * 4, cudaMemcpyDeviceToHost, st));
+      }
+      LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
+      LS_CK(cudaMemcpyAsync(h_seg, d_seg_totals, 16, cudaMemcpyDeviceToHost, st));
       LS_CK(cudaStreamSynchronize(st));
-      bool any = false;
-      for (uint32_t c : wc) any = any || (int64_t)c > (int64_t)params->max_depth;
-      if (any) {
-        int rc = ls_depth_cap_host(ctx, params->min_mq, params->max_depth, wc);
-        if (rc != LS_OK) return rc;
-        if (ctx->n_drop > 0) {  // redo the count with the dropped (window, read) pairs
-          sa = make_seg_args(ctx, *params, params->min_ac > 0);
-          LS_CK(cudaMemsetAsync(d_aligned, 0, 8, st));
-          seg_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sa, ctx->nseg.as<uint32_t>(), d_aligned,
-                                                                         ctx->rend.as<int32_t>(), nullptr);
-          ++launches;
+      bool again = false;
+      if (want_wcount) {
+        want_wcount = false;
+        bool any = false;
+        for (uint32_t c : wc) any = any || (int64_t)c > (int64_t)params->max_depth;
+        if (any) {
+          int rc = ls_depth_cap_host(ctx, params->min_mq, params->max_depth, wc);
+          if (rc != LS_OK) return rc;
+          if (ctx->n_drop > 0) {  // redo the walk without the dropped (window, read) pairs
+            sa = make_seg_args(ctx, *params, params->min_ac > 0);
+            again = true;
+          }
         }
       }
+      if (!again && (h_seg[0] > seg_need || h_seg[1] > piece_need)) {
+        seg_need = h_seg[0] > seg_need ? h_seg[0] : seg_need;
+        piece_need = h_seg[1] > piece_need ? h_seg[1] : piece_need;
+        again = true;
+      }
+      if (!again) break;
+      if (attempt >= 3) LS_FAIL(LS_E_STATE, "ls_pileup_run: segment builder did not converge");
+      LS_CK(cudaMemsetAsync(d_aligned, 0, 8, st));
+      LS_CK(cudaMemsetAsync(d_seg_totals, 0, 16, st));
     }
-    LS_CK(ls_scan_exclusive_u32(ctx->nseg.as<uint32_t>(), ctx->seg_off.as<uint32_t>(), n, d_nseg_total,
-                                ctx->scan_tmp, st));
-    launches += 3;
-    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
-    LS_CK(cudaStreamSynchronize(st));
   }
-  const int64_t nseg = (int64_t)h_tot[2];
-  if (nseg >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_pileup_run: more than 2^32 segments in one batch");
+  const int64_t nseg = (int64_t)h_seg[0];
+  if (nseg >= (int64_t)0xffffffffll || h_seg[1] >= 0xffffffffull)
+    LS_FAIL(LS_E_ARG, "ls_pileup_run: more than 2^32 segments or pieces in one batch");
   S.n_aligned = (int64_t)h_tot[0];
   S.n_segments = nseg;
   ctx->n_segments = nseg;
+  ctx->n_pieces = (int64_t)h_seg[1];
   int64_t n_slots = 0;
   if (nseg > 0) {
-    LS_CK(ctx->segs.ensure((size_t)nseg * sizeof(Segment)));
-    LS_CK(ctx->keys_a.ensure((size_t)nseg * 8));
-    LS_CK(ctx->keys_b.ensure((size_t)nseg * 8));
-    LS_CK(ctx->vals_a.ensure((size_t)nseg * 4));
-    LS_CK(ctx->vals_b.ensure((size_t)nseg * 4));
-    seg_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(sa, ctx->seg_off.as<uint32_t>(),
-                                                                 ctx->segs.as<Segment>(), ctx->keys_a.as<uint64_t>());
-    ++launches;
     LS_CK(cudaEventRecord(ctx->ev[1], st));
     LS_CK(ls_radix_sort_pairs(ctx->keys_a.as<uint64_t>(), ctx->keys_b.as<uint64_t>(), ctx->vals_a.as<uint32_t>(),
                               ctx->vals_b.as<uint32_t>(), nseg, tile_bits + ctx->cell_bits, ctx->rs_hist,
@@ -439,8 +303,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.n_parts = d_nparts;
     ca.acbuf = params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr;
     ca.flag = ctx->flag.as<uint16_t>();
-    ca.cigar_off = ctx->cigar_off.as<uint32_t>();
-    ca.cigar = ctx->cigar.as<uint32_t>();
+    ca.pieces = ctx->pieces.as<Piece>();
     ca.base_off = ctx->base_off.as<uint64_t>();
     ca.lq = ctx->lq.as<int32_t>();
     ca.seq4 = ctx->seq4.as<uint8_t>();

@@ -1,0 +1,271 @@
+// Segment builder: one thread per read walks its CIGAR and emits, per (read, tile) pair with pileup
+// entries, one Segment plus its Pieces (CIGAR ops clipped to the tile).  Included by ls_pileup.cu.
+//
+// One kernel, two walks per thread: the first counts segments / pieces, a warp-level prefix sum and
+// one atomicAdd pair per warp reserve the output ranges, the second walk (CIGAR now in L1) writes.
+// Output order across warps follows the atomics and is not deterministic; the (tile, cell) sort
+// and the commutative integer accumulation downstream make the results independent of it.
+#pragma once
+
+static_assert(LS_TILE == 512, "Piece::meta packs tile columns in 9 bits");
+
+struct SegArgs {
+  int64_t n_reads;
+  const int32_t *tid, *pos, *cell;
+  const uint16_t *flag;
+  const uint8_t *mapq;
+  const uint32_t *cigar_off, *cigar;
+  int64_t n_windows;
+  const int32_t *wtid, *wstart, *wend;
+  const int64_t *wtile_base;
+  int min_mq, cell_bits, emit_uncounted;
+  uint32_t uncounted_key;
+  const uint64_t *drop_keys;  // sorted (window<<32 | read) pairs removed by the depth cap
+  int64_t n_drop;
+};
+
+__device__ __forceinline__ int64_t first_window(const SegArgs &a, int32_t tid, int32_t x) {
+  // first window w with (wtid, wend) > (tid, x)
+  int64_t lo = 0, hi = a.n_windows;
+  while (lo < hi) {
+    int64_t m = (lo + hi) >> 1;
+    int32_t t = a.wtid[m];
+    bool le = (t < tid) || (t == tid && a.wend[m] <= x);
+    if (le)
+      lo = m + 1;
+    else
+      hi = m;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ bool is_dropped(const SegArgs &a, int64_t w, uint32_t r) {
+  if (a.n_drop == 0) return false;
+  uint64_t key = ((uint64_t)w << 32) | r;
+  int64_t lo = 0, hi = a.n_drop;
+  while (lo < hi) {
+    int64_t m = (lo + hi) >> 1;
+    if (a.drop_keys[m] < key)
+      lo = m + 1;
+    else
+      hi = m;
+  }
+  return lo < a.n_drop && a.drop_keys[lo] == key;
+}
+
+struct WalkOut {
+  uint32_t nseg, npiece;
+  uint64_t aligned;
+  int32_t end;
+};
+
+struct SegSink {
+  Segment *segs;
+  uint64_t *keys;
+  Piece *pieces;
+  uint32_t seg_base, piece_base;
+  uint64_t cell_key;
+  int cell_bits;
+};
+
+// A window cached in registers while the read stays inside it.
+struct WinCur {
+  int64_t w;
+  int32_t ws, we;
+  int64_t tb;
+  bool same_tid, dropped;
+};
+
+__device__ __forceinline__ void load_window(const SegArgs &a, WinCur &c, int32_t tid, uint32_t r) {
+  c.same_tid = c.w < a.n_windows && a.wtid[c.w] == tid;
+  if (c.same_tid) {
+    c.ws = a.wstart[c.w];
+    c.we = a.wend[c.w];
+    c.tb = a.wtile_base[c.w];
+    c.dropped = is_dropped(a, c.w, r);
+  }
+}
+
+template <bool EMIT>
+__device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const SegSink &sink) {
+  const uint32_t k0 = a.cigar_off[r], kend = a.cigar_off[r + 1];
+  const int32_t tid = a.tid[r];
+  const uint32_t flag = a.flag[r];
+  int32_t x = a.pos[r];
+  uint32_t y = 0;
+  WalkOut o;
+  o.nseg = 0;
+  o.npiece = 0;
+  o.aligned = 0;
+  const bool engine_ok = read_passes_engine(flag, a.mapq[r], a.min_mq) && tid >= 0;
+  const bool counted = a.cell[r] >= 0 && !(flag & LS_FLAG_SUPPL);
+  const bool want = engine_ok && (counted || a.emit_uncounted);
+  WinCur cur;
+  cur.w = -1;
+  cur.same_tid = false;
+  cur.dropped = false;
+  cur.ws = cur.we = 0;
+  cur.tb = 0;
+  int64_t last_tile = -1;
+  uint32_t seg_p0 = 0;
+  uint32_t cnext = k0 < kend ? a.cigar[k0] : 0xfu;
+  for (uint32_t k = k0; k < kend; ++k) {
+    const uint32_t c = cnext;
+    cnext = (k + 1 < kend) ? a.cigar[k + 1] : 0xfu;
+    const uint32_t op = c & 15u;
+    const int32_t len = (int32_t)(c >> 4);
+    const bool match = op_is_match(op);
+    if (match) o.aligned += (uint64_t)len;
+    if (want && len > 0 && (match || op == OP_D || op == OP_N)) {
+      // class of the op's last column when an indel follows (htslib resolve_cigar2)
+      const uint32_t op2 = cnext & 15u;
+      int ind = 0;
+      if (op2 == OP_D && op != OP_D)
+        ind = -1;
+      else if (op2 == OP_I)
+        ind = 1;
+      else if (op2 == OP_P)
+        ind = indel_after(a.cigar, k, kend, op);
+      const uint32_t indcode = ind > 0 ? 1u : (ind < 0 ? 2u : 0u);
+      int32_t xa = x, xb = x + len;
+      if (op == OP_N) {  // a ref-skip only matters through its last column, and only if an indel follows
+        xa = indcode ? x + len - 1 : xb;
+      }
+      if (xb > xa) {
+        if (cur.w < 0) {
+          cur.w = first_window(a, tid, xa);
+          load_window(a, cur, tid, (uint32_t)r);
+        }
+        while (cur.same_tid && cur.we <= xa) {
+          ++cur.w;
+          load_window(a, cur, tid, (uint32_t)r);
+        }
+        WinCur ww = cur;  // an op that crosses a window border visits the following windows too
+        while (ww.same_tid && ww.ws < xb) {
+          int32_t lo = xa > ww.ws ? xa : ww.ws;
+          const int32_t hi = xb < ww.we ? xb : ww.we;
+          if (lo < hi && !ww.dropped) {
+            while (lo < hi) {
+              const uint32_t trel = (uint32_t)(lo - ww.ws) / (uint32_t)LS_TILE;
+              const int32_t tstart = ww.ws + (int32_t)(trel * (uint32_t)LS_TILE);
+              const int32_t tend = (tstart + LS_TILE) < ww.we ? (tstart + LS_TILE) : ww.we;
+              const int32_t shi = hi < tend ? hi : tend;
+              const int64_t tile = ww.tb + (int64_t)trel;
+              if (tile != last_tile) {
+                if (EMIT) {
+                  if (o.nseg > 0) {
+                    Segment s;
+                    s.read = (uint32_t)r;
+                    s.p0 = sink.piece_base + seg_p0;
+                    s.np = o.npiece - seg_p0;
+                    s.pad = 0;
+                    sink.segs[sink.seg_base + o.nseg - 1] = s;
+                  }
+                  sink.keys[sink.seg_base + o.nseg] = ((uint64_t)tile << sink.cell_bits) | sink.cell_key;
+                }
+                seg_p0 = o.npiece;
+                ++o.nseg;
+                last_tile = tile;
+              }
+              if (EMIT) {
+                Piece p;
+                p.ya = match ? y + (uint32_t)(lo - x) : y;
+                p.meta = piece_meta((uint32_t)(lo - tstart), (uint32_t)(shi - lo), match ? 0u : 1u,
+                                    (shi == x + len) ? indcode : 0u);
+                sink.pieces[sink.piece_base + o.npiece] = p;
+              }
+              ++o.npiece;
+              lo = shi;
+            }
+          }
+          if (ww.we >= xb) break;
+          ++ww.w;
+          load_window(a, ww, tid, (uint32_t)r);
+        }
+      }
+    }
+    if (match) {
+      x += len;
+      y += (uint32_t)len;
+    } else if (op == OP_D || op == OP_N) {
+      x += len;
+    } else if (op == OP_I || op == OP_S) {
+      y += (uint32_t)len;
+    }
+  }
+  if (EMIT && o.nseg > 0) {
+    Segment s;
+    s.read = (uint32_t)r;
+    s.p0 = sink.piece_base + seg_p0;
+    s.np = o.npiece - seg_p0;
+    s.pad = 0;
+    sink.segs[sink.seg_base + o.nseg - 1] = s;
+  }
+  o.end = x;
+  return o;
+}
+
+// totals[0] = segments, totals[1] = pieces (both keep counting past the capacities, so that the host can
+// size the buffers exactly and relaunch); nothing is written by a warp whose range does not fit.
+__global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__restrict__ segs, uint64_t *__restrict__ keys,
+                                                        Piece *__restrict__ pieces, uint64_t seg_cap, uint64_t piece_cap,
+                                                        unsigned long long *__restrict__ totals,
+                                                        unsigned long long *__restrict__ n_aligned,
+                                                        int32_t *__restrict__ rend, uint32_t *__restrict__ wcount) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool live = r < a.n_reads;
+  SegSink sink;
+  sink.segs = segs;
+  sink.keys = keys;
+  sink.pieces = pieces;
+  sink.seg_base = sink.piece_base = 0;
+  sink.cell_key = 0;
+  sink.cell_bits = a.cell_bits;
+  WalkOut o;
+  o.nseg = o.npiece = 0;
+  o.aligned = 0;
+  o.end = 0;
+  if (live) {
+    o = walk_read<false>(a, r, sink);
+    if (rend) rend[r] = o.end;
+    // records each pileup() call (window) would fetch: overlap of [pos, bam_endpos) with the window
+    const int32_t tid = a.tid[r], p0 = a.pos[r];
+    if (wcount && tid >= 0 && read_passes_engine(a.flag[r], a.mapq[r], a.min_mq)) {
+      const int32_t e = o.end > p0 ? o.end : p0 + 1;
+      for (int64_t w = first_window(a, tid, p0); w < a.n_windows && a.wtid[w] == tid && a.wstart[w] < e; ++w)
+        atomicAdd(&wcount[w], 1u);
+    }
+  }
+  // warp prefix sums of the two counts, one reservation per warp
+  uint32_t ps = o.nseg, pp = o.npiece;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t ts = __shfl_up_sync(0xffffffffu, ps, d);
+    const uint32_t tp = __shfl_up_sync(0xffffffffu, pp, d);
+    if (lane >= d) {
+      ps += ts;
+      pp += tp;
+    }
+  }
+  const uint32_t wseg = __shfl_sync(0xffffffffu, ps, 31), wpiece = __shfl_sync(0xffffffffu, pp, 31);
+  unsigned long long bs = 0, bp = 0;
+  if (lane == 31 && wseg) {
+    bs = atomicAdd(&totals[0], (unsigned long long)wseg);
+    bp = atomicAdd(&totals[1], (unsigned long long)wpiece);
+  }
+  bs = __shfl_sync(0xffffffffu, bs, 31);
+  bp = __shfl_sync(0xffffffffu, bp, 31);
+  if (live && o.nseg && bs + wseg <= seg_cap && bp + wpiece <= piece_cap) {
+    sink.seg_base = (uint32_t)bs + (ps - o.nseg);
+    sink.piece_base = (uint32_t)bp + (pp - o.npiece);
+    const int32_t cell = a.cell[r];
+    const bool counted = cell >= 0 && !(a.flag[r] & LS_FLAG_SUPPL);
+    sink.cell_key = counted ? (uint64_t)(uint32_t)cell : (uint64_t)a.uncounted_key;
+    walk_read<true>(a, r, sink);
+  }
+  uint64_t al = o.aligned;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) al += __shfl_xor_sync(0xffffffffu, al, d);
+  if (lane == 0 && al) atomicAdd(n_aligned, (unsigned long long)al);
+}
