@@ -68,6 +68,15 @@ struct SegSink {
   int cell_bits;
 };
 
+// First-walk staging in thread-local memory: most reads fit, and then the second walk is a plain copy.
+constexpr int SEG_STAGE_PIECES = 40;
+constexpr int SEG_STAGE_SEGS = 12;
+struct SegStage {
+  Piece piece[SEG_STAGE_PIECES];
+  uint64_t tile[SEG_STAGE_SEGS];
+  uint32_t p0[SEG_STAGE_SEGS];  // first piece of the segment, relative to the read
+};
+
 // A window cached in registers while the read stays inside it.
 struct WinCur {
   int64_t w;
@@ -86,8 +95,9 @@ __device__ __forceinline__ void load_window(const SegArgs &a, WinCur &c, int32_t
   }
 }
 
+// EMIT = false: count, and stage the output in `stage` while it fits; EMIT = true: write to the sink.
 template <bool EMIT>
-__device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const SegSink &sink) {
+__device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const SegSink &sink, SegStage *stage) {
   const uint32_t k0 = a.cigar_off[r], kend = a.cigar_off[r + 1];
   const int32_t tid = a.tid[r];
   const uint32_t flag = a.flag[r];
@@ -162,17 +172,23 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const 
                     sink.segs[sink.seg_base + o.nseg - 1] = s;
                   }
                   sink.keys[sink.seg_base + o.nseg] = ((uint64_t)tile << sink.cell_bits) | sink.cell_key;
+                } else if (o.nseg < (uint32_t)SEG_STAGE_SEGS) {
+                  stage->tile[o.nseg] = (uint64_t)tile;
+                  stage->p0[o.nseg] = o.npiece;
                 }
                 seg_p0 = o.npiece;
                 ++o.nseg;
                 last_tile = tile;
               }
-              if (EMIT) {
+              if (EMIT || o.npiece < (uint32_t)SEG_STAGE_PIECES) {
                 Piece p;
                 p.ya = match ? y + (uint32_t)(lo - x) : y;
                 p.meta = piece_meta((uint32_t)(lo - tstart), (uint32_t)(shi - lo), match ? 0u : 1u,
                                     (shi == x + len) ? indcode : 0u);
-                sink.pieces[sink.piece_base + o.npiece] = p;
+                if (EMIT)
+                  sink.pieces[sink.piece_base + o.npiece] = p;
+                else
+                  stage->piece[o.npiece] = p;
               }
               ++o.npiece;
               lo = shi;
@@ -226,8 +242,9 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
   o.nseg = o.npiece = 0;
   o.aligned = 0;
   o.end = 0;
+  SegStage stage;
   if (live) {
-    o = walk_read<false>(a, r, sink);
+    o = walk_read<false>(a, r, sink, &stage);
     if (rend) rend[r] = o.end;
     // records each pileup() call (window) would fetch: overlap of [pos, bam_endpos) with the window
     const int32_t tid = a.tid[r], p0 = a.pos[r];
@@ -262,7 +279,20 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
     const int32_t cell = a.cell[r];
     const bool counted = cell >= 0 && !(a.flag[r] & LS_FLAG_SUPPL);
     sink.cell_key = counted ? (uint64_t)(uint32_t)cell : (uint64_t)a.uncounted_key;
-    walk_read<true>(a, r, sink);
+    if (o.nseg <= (uint32_t)SEG_STAGE_SEGS && o.npiece <= (uint32_t)SEG_STAGE_PIECES) {
+      for (uint32_t i = 0; i < o.npiece; ++i) pieces[sink.piece_base + i] = stage.piece[i];
+      for (uint32_t i = 0; i < o.nseg; ++i) {
+        Segment sg;
+        sg.read = (uint32_t)r;
+        sg.p0 = sink.piece_base + stage.p0[i];
+        sg.np = (i + 1 < o.nseg ? stage.p0[i + 1] : o.npiece) - stage.p0[i];
+        sg.pad = 0;
+        segs[sink.seg_base + i] = sg;
+        keys[sink.seg_base + i] = (stage.tile[i] << a.cell_bits) | sink.cell_key;
+      }
+    } else {
+      walk_read<true>(a, r, sink, nullptr);
+    }
   }
   uint64_t al = o.aligned;
 #pragma unroll

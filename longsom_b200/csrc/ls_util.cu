@@ -116,17 +116,24 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist(const uint64_t *__restrict
   hist[(int64_t)threadIdx.x * G + blockIdx.x] = h[threadIdx.x];
 }
 
+// One chunk (RS_CHUNK items) at a time: stable rank of every item inside its digit (match_any inside a warp,
+// per-warp digit counters across warps), then the chunk is laid out digit-major in shared memory and written
+// from there, so that each digit's items leave the CTA as one contiguous, coalesced run.
 template <bool HAS_VALS>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restrict__ keys_in,
                                                          const uint32_t *__restrict__ vals_in,
                                                          uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                                                          int64_t n, int64_t per_block, int shift,
                                                          const uint32_t *__restrict__ hist_scanned, int G, int first_pass) {
-  __shared__ uint32_t base[256];
-  __shared__ uint32_t wcnt[RS_WARPS][256];
+  __shared__ uint32_t gbase[256];            // running global offset of each digit for this CTA
+  __shared__ uint32_t lbase[256];            // offset of each digit inside the staged chunk
+  __shared__ uint32_t wcnt[RS_WARPS][256];   // per-warp digit counts, then per-warp offsets inside the digit
+  __shared__ uint32_t scan_sm[RS_THREADS / 32 + 1];
+  __shared__ uint64_t skey[RS_CHUNK];
+  __shared__ uint32_t sval[HAS_VALS ? RS_CHUNK : 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  base[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * G + blockIdx.x] + hist_scanned[(int64_t)256 * G + threadIdx.x];
+  gbase[threadIdx.x] = hist_scanned[(int64_t)threadIdx.x * G + blockIdx.x] + hist_scanned[(int64_t)256 * G + threadIdx.x];
   int64_t lo = (int64_t)blockIdx.x * per_block;
   int64_t hi = lo + per_block < n ? lo + per_block : n;
   for (int64_t chunk = lo; chunk < hi; chunk += RS_CHUNK) {
@@ -135,12 +142,18 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
     uint64_t key[RS_ROUNDS];
     uint32_t val[RS_ROUNDS];
     uint32_t rank[RS_ROUNDS];
+    // all loads of the chunk first: the ranking below has warp barriers the loads could not be hoisted across
 #pragma unroll
     for (int r = 0; r < RS_ROUNDS; ++r) {
       int64_t idx = chunk + (int64_t)w * (32 * RS_ROUNDS) + r * 32 + lane;
       bool valid = idx < hi;
       key[r] = valid ? keys_in[idx] : 0ull;
       if (HAS_VALS) val[r] = valid ? (first_pass ? (uint32_t)idx : vals_in[idx]) : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ROUNDS; ++r) {
+      int64_t idx = chunk + (int64_t)w * (32 * RS_ROUNDS) + r * 32 + lane;
+      bool valid = idx < hi;
       uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 256u;
       uint32_t peers = __match_any_sync(0xffffffffu, d);
       uint32_t before = __popc(peers & lt);
@@ -151,16 +164,22 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
       __syncwarp();
     }
     __syncthreads();
-    {  // exclusive scan across warps per digit, fold in the running block base
-      int d = threadIdx.x;
-      uint32_t run = base[d];
+    uint32_t dtot;
+    {  // per digit: exclusive scan across warps; then across digits for the staged layout
+      const int d = threadIdx.x;
+      uint32_t run = 0;
 #pragma unroll
       for (int ww = 0; ww < RS_WARPS; ++ww) {
         uint32_t t = wcnt[ww][d];
         wcnt[ww][d] = run;
         run += t;
       }
-      base[d] = run;
+      dtot = run;
+    }
+    {
+      uint32_t tot;
+      const uint32_t ex = block_excl_scan<RS_THREADS>(dtot, &tot, scan_sm);  // ends with a barrier
+      lbase[threadIdx.x] = ex;
     }
     __syncthreads();
 #pragma unroll
@@ -168,11 +187,22 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
       int64_t idx = chunk + (int64_t)w * (32 * RS_ROUNDS) + r * 32 + lane;
       if (idx < hi) {
         uint32_t d = (uint32_t)(key[r] >> shift) & 255u;
-        uint32_t p = wcnt[w][d] + rank[r];
-        keys_out[p] = key[r];
-        if (HAS_VALS) vals_out[p] = val[r];
+        uint32_t li = lbase[d] + wcnt[w][d] + rank[r];
+        skey[li] = key[r];
+        if (HAS_VALS) sval[li] = val[r];
       }
     }
+    __syncthreads();
+    const int cn = (int)((hi - chunk) < (int64_t)RS_CHUNK ? (hi - chunk) : (int64_t)RS_CHUNK);
+    for (int i = threadIdx.x; i < cn; i += RS_THREADS) {
+      const uint64_t k = skey[i];
+      const uint32_t d = (uint32_t)(k >> shift) & 255u;
+      const uint32_t pos = gbase[d] + ((uint32_t)i - lbase[d]);
+      keys_out[pos] = k;
+      if (HAS_VALS) vals_out[pos] = sval[i];
+    }
+    __syncthreads();
+    gbase[threadIdx.x] += dtot;
     __syncthreads();
   }
 }
