@@ -1,8 +1,10 @@
 // Segment builder: one thread per read walks its CIGAR and emits, per (read, tile) pair with pileup
 // entries, one Segment plus its Pieces (CIGAR ops clipped to the tile).  Included by ls_pileup.cu.
 //
-// One kernel, two walks per thread: the first counts segments / pieces, a warp-level prefix sum and
-// one atomicAdd pair per warp reserve the output ranges, the second walk (CIGAR now in L1) writes.
+// One kernel: each thread walks its read once, counting segments / pieces and staging them in thread-local
+// memory; a warp-level prefix sum and one atomicAdd pair per warp reserve the output ranges; the staged
+// output is copied out (reads that overflow the staging area are walked a second time).  The block's CIGAR
+// ops are first copied to shared memory with coalesced loads.
 // Output order across warps follows the atomics and is not deterministic; the (tile, cell) sort
 // and the commutative integer accumulation downstream make the results independent of it.
 #pragma once
@@ -71,6 +73,7 @@ struct SegSink {
 // First-walk staging in thread-local memory: most reads fit, and then the second walk is a plain copy.
 constexpr int SEG_STAGE_PIECES = 40;
 constexpr int SEG_STAGE_SEGS = 12;
+constexpr int SEG_CIG_SMEM = 6144;  // CIGAR ops of one block kept in shared memory (24 KB)
 struct SegStage {
   Piece piece[SEG_STAGE_PIECES];
   uint64_t tile[SEG_STAGE_SEGS];
@@ -97,7 +100,9 @@ __device__ __forceinline__ void load_window(const SegArgs &a, WinCur &c, int32_t
 
 // EMIT = false: count, and stage the output in `stage` while it fits; EMIT = true: write to the sink.
 template <bool EMIT>
-__device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const SegSink &sink, SegStage *stage) {
+__device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *__restrict__ cig, int64_t r,
+                                             const SegSink &sink, SegStage *stage) {
+  // cig: the CIGAR array, indexed like a.cigar (the kernel points it at its shared-memory copy when that fits)
   const uint32_t k0 = a.cigar_off[r], kend = a.cigar_off[r + 1];
   const int32_t tid = a.tid[r];
   const uint32_t flag = a.flag[r];
@@ -118,10 +123,10 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const 
   cur.tb = 0;
   int64_t last_tile = -1;
   uint32_t seg_p0 = 0;
-  uint32_t cnext = k0 < kend ? a.cigar[k0] : 0xfu;
+  uint32_t cnext = k0 < kend ? cig[k0] : 0xfu;
   for (uint32_t k = k0; k < kend; ++k) {
     const uint32_t c = cnext;
-    cnext = (k + 1 < kend) ? a.cigar[k + 1] : 0xfu;
+    cnext = (k + 1 < kend) ? cig[k + 1] : 0xfu;
     const uint32_t op = c & 15u;
     const int32_t len = (int32_t)(c >> 4);
     const bool match = op_is_match(op);
@@ -135,7 +140,7 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, int64_t r, const 
       else if (op2 == OP_I)
         ind = 1;
       else if (op2 == OP_P)
-        ind = indel_after(a.cigar, k, kend, op);
+        ind = indel_after(cig, k, kend, op);
       const uint32_t indcode = ind > 0 ? 1u : (ind < 0 ? 2u : 0u);
       int32_t xa = x, xb = x + len;
       if (op == OP_N) {  // a ref-skip only matters through its last column, and only if an indel follows
@@ -231,6 +236,20 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = r < a.n_reads;
+  // The CIGARs of the block's 256 consecutive reads are one contiguous range: copy it to shared memory with
+  // coalesced loads, so that the per-thread serial walks do not each pay global-memory latency per op.
+  __shared__ uint32_t scig[SEG_CIG_SMEM];
+  const uint32_t *cig = a.cigar;
+  {
+    const int64_t r0 = (int64_t)blockIdx.x * blockDim.x;
+    const int64_t r1 = (r0 + (int64_t)blockDim.x) < a.n_reads ? (r0 + (int64_t)blockDim.x) : a.n_reads;
+    const uint32_t c0 = a.cigar_off[r0], c1 = a.cigar_off[r1];
+    if (c1 - c0 <= (uint32_t)SEG_CIG_SMEM) {
+      for (uint32_t i = threadIdx.x; i < c1 - c0; i += blockDim.x) scig[i] = a.cigar[c0 + i];
+      cig = scig - c0;
+    }
+    __syncthreads();
+  }
   SegSink sink;
   sink.segs = segs;
   sink.keys = keys;
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
   o.end = 0;
   SegStage stage;
   if (live) {
-    o = walk_read<false>(a, r, sink, &stage);
+    o = walk_read<false>(a, cig, r, sink, &stage);
     if (rend) rend[r] = o.end;
     // records each pileup() call (window) would fetch: overlap of [pos, bam_endpos) with the window
     const int32_t tid = a.tid[r], p0 = a.pos[r];
@@ -291,7 +310,7 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
         keys[sink.seg_base + i] = (stage.tile[i] << a.cell_bits) | sink.cell_key;
       }
     } else {
-      walk_read<true>(a, r, sink, nullptr);
+      walk_read<true>(a, cig, r, sink, nullptr);
     }
   }
   uint64_t al = o.aligned;
