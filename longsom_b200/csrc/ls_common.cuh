@@ -53,9 +53,14 @@ struct DBuf {
 struct __align__(16) Segment {
   uint32_t read;   // read index in the batch
   uint32_t p0;     // first piece of the segment in pieces[]
-  uint32_t np;     // number of pieces (consecutive: a read's CIGAR visits a tile once)
-  uint32_t pad;
+  uint32_t np;     // bits 0-15: number of pieces (consecutive: a read's CIGAR visits a tile once);
+                   // bits 16-31: query bases spanned by the pieces (saturating), for prefetching
+  uint32_t y0;     // query index of the first piece
 };
+__host__ __device__ __forceinline__ uint32_t segment_np_word(uint32_t np, uint32_t y0, uint32_t y1) {
+  const uint32_t q = y1 > y0 ? y1 - y0 : 0u;
+  return np | ((q > 65535u ? 65535u : q) << 16);
+}
 
 // One CIGAR op clipped to one tile, produced by the segment builder so that the count kernel does not walk
 // CIGARs: a match piece covers query bases [ya, ya + n) at tile columns [col, col + n); a deletion piece covers

@@ -63,6 +63,7 @@ struct CountArgs {
   int cell_bits;
   uint32_t uncounted_key;
   int min_bq, min_dp, min_cc, min_ac;
+  int prefetch;
 };
 
 template <bool PACKED>
@@ -132,6 +133,7 @@ __device__ __forceinline__ void add_uncounted(TileSmemT<PACKED> &sm, int s, int 
 
 struct SegMeta {
   uint32_t p0, np, lq;
+  uint32_t y0, qlen;  // query extent of the segment (prefetch only; not shuffled)
   uint64_t boff;
   int strand;
 };
@@ -140,7 +142,9 @@ __device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
   const Segment sg = a.segs[a.vals[i]];
   SegMeta m;
   m.p0 = sg.p0;
-  m.np = sg.np;
+  m.np = sg.np & 0xffffu;
+  m.y0 = sg.y0;
+  m.qlen = sg.np >> 16;
   m.boff = a.base_off[sg.read];
   m.lq = (uint32_t)a.lq[sg.read];
   m.strand = (a.flag[sg.read] & LS_FLAG_REVERSE) ? 1 : 0;
@@ -365,6 +369,24 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
       ck = a.keys[i] & cmask;
       start = (i == slot_lo) || ck == unc || (a.keys[i - 1] & cmask) != ck;
       mm = load_meta(a, i);
+      // lane-parallel warm-up for the 32 segments of the chunk: the first piece, and the first lines of the
+      // qualities / bases it points at, are pulled towards the SM while earlier segments are being processed
+      if (a.prefetch) {
+        const uint64_t qb = mm.boff + (uint64_t)mm.y0;
+        const uint8_t *q = a.qual + qb;
+        const uint8_t *sq = a.seq4 + (qb >> 1);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(sq));
+        if (a.prefetch & 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pieces + mm.p0));
+        if (a.prefetch & 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pieces + mm.p0));
+        if ((a.prefetch & 15) >= 2) {
+          // the remaining lines of the segment's query bytes (typically ~200 qualities, ~100 base bytes)
+          const uint32_t qe = ((uint32_t)(qb & 127u) + mm.qlen) >> 7;          // extra quality lines
+          const uint32_t se = ((uint32_t)((qb >> 1) & 127u) + (mm.qlen >> 1)) >> 7;  // extra base lines
+          for (uint32_t l = 1; l <= qe && l <= (uint32_t)(a.prefetch & 15); ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128u * l));
+          for (uint32_t l = 1; l <= se && l <= (uint32_t)(a.prefetch & 15); ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(sq + 128u * l));
+        }
+      }
     }
     const uint32_t startmask = __ballot_sync(0xffffffffu, start);
     uint32_t rem = startmask;

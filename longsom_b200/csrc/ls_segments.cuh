@@ -78,6 +78,7 @@ struct SegStage {
   Piece piece[SEG_STAGE_PIECES];
   uint64_t tile[SEG_STAGE_SEGS];
   uint32_t p0[SEG_STAGE_SEGS];  // first piece of the segment, relative to the read
+  uint32_t y0[SEG_STAGE_SEGS], y1[SEG_STAGE_SEGS];  // query extent of the segment's pieces
 };
 
 // A window cached in registers while the read stays inside it.
@@ -122,7 +123,7 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
   cur.ws = cur.we = 0;
   cur.tb = 0;
   int64_t last_tile = -1;
-  uint32_t seg_p0 = 0;
+  uint32_t seg_p0 = 0, seg_y0 = 0, seg_y1 = 0;
   uint32_t cnext = k0 < kend ? cig[k0] : 0xfu;
   for (uint32_t k = k0; k < kend; ++k) {
     const uint32_t c = cnext;
@@ -172,16 +173,24 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
                     Segment s;
                     s.read = (uint32_t)r;
                     s.p0 = sink.piece_base + seg_p0;
-                    s.np = o.npiece - seg_p0;
-                    s.pad = 0;
+                    s.np = segment_np_word(o.npiece - seg_p0, seg_y0, seg_y1);
+                    s.y0 = seg_y0;
                     sink.segs[sink.seg_base + o.nseg - 1] = s;
                   }
                   sink.keys[sink.seg_base + o.nseg] = ((uint64_t)tile << sink.cell_bits) | sink.cell_key;
-                } else if (o.nseg < (uint32_t)SEG_STAGE_SEGS) {
-                  stage->tile[o.nseg] = (uint64_t)tile;
-                  stage->p0[o.nseg] = o.npiece;
+                } else {
+                  if (o.nseg > 0 && o.nseg <= (uint32_t)SEG_STAGE_SEGS) {
+                    stage->y0[o.nseg - 1] = seg_y0;
+                    stage->y1[o.nseg - 1] = seg_y1;
+                  }
+                  if (o.nseg < (uint32_t)SEG_STAGE_SEGS) {
+                    stage->tile[o.nseg] = (uint64_t)tile;
+                    stage->p0[o.nseg] = o.npiece;
+                  }
                 }
                 seg_p0 = o.npiece;
+                seg_y0 = match ? y + (uint32_t)(lo - x) : y;
+                seg_y1 = seg_y0;
                 ++o.nseg;
                 last_tile = tile;
               }
@@ -194,6 +203,10 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
                   sink.pieces[sink.piece_base + o.npiece] = p;
                 else
                   stage->piece[o.npiece] = p;
+              }
+              {
+                const uint32_t pe = match ? y + (uint32_t)(shi - x) : y + 1u;
+                seg_y1 = pe > seg_y1 ? pe : seg_y1;
               }
               ++o.npiece;
               lo = shi;
@@ -218,9 +231,13 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
     Segment s;
     s.read = (uint32_t)r;
     s.p0 = sink.piece_base + seg_p0;
-    s.np = o.npiece - seg_p0;
-    s.pad = 0;
+    s.np = segment_np_word(o.npiece - seg_p0, seg_y0, seg_y1);
+    s.y0 = seg_y0;
     sink.segs[sink.seg_base + o.nseg - 1] = s;
+  }
+  if (!EMIT && o.nseg > 0 && o.nseg <= (uint32_t)SEG_STAGE_SEGS) {
+    stage->y0[o.nseg - 1] = seg_y0;
+    stage->y1[o.nseg - 1] = seg_y1;
   }
   o.end = x;
   return o;
@@ -304,8 +321,8 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
         Segment sg;
         sg.read = (uint32_t)r;
         sg.p0 = sink.piece_base + stage.p0[i];
-        sg.np = (i + 1 < o.nseg ? stage.p0[i + 1] : o.npiece) - stage.p0[i];
-        sg.pad = 0;
+        sg.np = segment_np_word((i + 1 < o.nseg ? stage.p0[i + 1] : o.npiece) - stage.p0[i], stage.y0[i], stage.y1[i]);
+        sg.y0 = stage.y0[i];
         segs[sink.seg_base + i] = sg;
         keys[sink.seg_base + i] = (stage.tile[i] << a.cell_bits) | sink.cell_key;
       }
