@@ -174,9 +174,10 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   uint32_t *d_nparts = reinterpret_cast<uint32_t *>(d_aligned + 4);
   uint32_t *d_longrun = reinterpret_cast<uint32_t *>(d_aligned + 5);
   uint32_t *d_nlight = reinterpret_cast<uint32_t *>(d_aligned + 6);
+  uint32_t *d_capflag = reinterpret_cast<uint32_t *>(d_aligned + 7);
 
   LS_CK(cudaEventRecord(ctx->ev[0], st));
-  uint64_t h_tot[6] = {0, 0, 0, 0, 0, 0};
+  uint64_t h_tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t h_seg[2] = {0, 0};
   uint64_t *d_seg_totals = reinterpret_cast<uint64_t *>(d_aligned + 8);  // [0] segments, [1] pieces
   if (n > 0 && ctx->n_windows > 0) {
@@ -205,22 +206,19 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       seg_build_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
           sa, ctx->segs.as<Segment>(), ctx->keys_a.as<uint64_t>(), ctx->pieces.as<Piece>(), seg_need, piece_need,
           reinterpret_cast<unsigned long long *>(d_seg_totals), d_aligned, want_wcount ? ctx->rend.as<int32_t>() : nullptr,
-          want_wcount ? ctx->wcount.as<uint32_t>() : nullptr);
+          want_wcount ? ctx->wcount.as<uint32_t>() : nullptr, (uint32_t)params->max_depth, d_capflag);
       ++launches;
       LS_CK(cudaGetLastError());
-      if (want_wcount) {
-        wc.resize((size_t)ctx->n_windows);
-        LS_CK(cudaMemcpyAsync(wc.data(), ctx->wcount.p, wc.size() * 4, cudaMemcpyDeviceToHost, st));
-      }
-      LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
+      LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
       LS_CK(cudaMemcpyAsync(h_seg, d_seg_totals, 16, cudaMemcpyDeviceToHost, st));
       LS_CK(cudaStreamSynchronize(st));
       bool again = false;
       if (want_wcount) {
         want_wcount = false;
-        bool any = false;
-        for (uint32_t c : wc) any = any || (int64_t)c > (int64_t)params->max_depth;
+        const bool any = (h_tot[7] & 0xffffffffull) != 0;  // some window fetches more than max_depth records
         if (any) {
+          wc.resize((size_t)ctx->n_windows);
+          LS_CK(cudaMemcpy(wc.data(), ctx->wcount.p, wc.size() * 4, cudaMemcpyDeviceToHost));
           int rc = ls_depth_cap_host(ctx, params->min_mq, params->max_depth, wc);
           if (rc != LS_OK) return rc;
           if (ctx->n_drop > 0) {  // redo the walk without the dropped (window, read) pairs

@@ -59,6 +59,7 @@ struct WalkOut {
   uint32_t nseg, npiece;
   uint64_t aligned;
   int32_t end;
+  int64_t wfirst;  // first_window(tid, pos) when the walk happened to look it up, else -1
 };
 
 struct SegSink {
@@ -113,6 +114,7 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
   o.nseg = 0;
   o.npiece = 0;
   o.aligned = 0;
+  o.wfirst = -1;
   const bool engine_ok = read_passes_engine(flag, a.mapq[r], a.min_mq) && tid >= 0;
   const bool counted = a.cell[r] >= 0 && !(flag & LS_FLAG_SUPPL);
   const bool want = engine_ok && (counted || a.emit_uncounted);
@@ -150,6 +152,7 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
       if (xb > xa) {
         if (cur.w < 0) {
           cur.w = first_window(a, tid, xa);
+          if (xa == a.pos[r]) o.wfirst = cur.w;
           load_window(a, cur, tid, (uint32_t)r);
         }
         while (cur.same_tid && cur.we <= xa) {
@@ -249,7 +252,8 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
                                                         Piece *__restrict__ pieces, uint64_t seg_cap, uint64_t piece_cap,
                                                         unsigned long long *__restrict__ totals,
                                                         unsigned long long *__restrict__ n_aligned,
-                                                        int32_t *__restrict__ rend, uint32_t *__restrict__ wcount) {
+                                                        int32_t *__restrict__ rend, uint32_t *__restrict__ wcount,
+                                                        uint32_t max_depth, uint32_t *__restrict__ cap_flag) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = r < a.n_reads;
@@ -282,12 +286,34 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
   if (live) {
     o = walk_read<false>(a, cig, r, sink, &stage);
     if (rend) rend[r] = o.end;
-    // records each pileup() call (window) would fetch: overlap of [pos, bam_endpos) with the window
-    const int32_t tid = a.tid[r], p0 = a.pos[r];
-    if (wcount && tid >= 0 && read_passes_engine(a.flag[r], a.mapq[r], a.min_mq)) {
-      const int32_t e = o.end > p0 ? o.end : p0 + 1;
-      for (int64_t w = first_window(a, tid, p0); w < a.n_windows && a.wtid[w] == tid && a.wstart[w] < e; ++w)
-        atomicAdd(&wcount[w], 1u);
+  }
+  if (wcount) {
+    // records each pileup() call (window) would fetch: overlap of [pos, bam_endpos) with the window.  Reads are
+    // position-sorted, so the lanes of a warp mostly hit the same window: one atomic per distinct first window;
+    // cap_flag is raised by the add that takes a window past max_depth (only then does the host look at wcount).
+    int64_t w0 = -1;
+    int32_t tid = -1, e = 0;
+    if (live) {
+      tid = a.tid[r];
+      const int32_t p0 = a.pos[r];
+      if (tid >= 0 && read_passes_engine(a.flag[r], a.mapq[r], a.min_mq)) {
+        e = o.end > p0 ? o.end : p0 + 1;
+        w0 = o.wfirst >= 0 ? o.wfirst : first_window(a, tid, p0);
+        if (!(w0 < a.n_windows && a.wtid[w0] == tid && a.wstart[w0] < e)) w0 = -1;
+      }
+    }
+    const long long key = w0 >= 0 ? (long long)w0 : -1ll - (long long)lane;
+    const uint32_t peers = __match_any_sync(0xffffffffu, key);
+    if (w0 >= 0) {
+      if (lane == __ffs(peers) - 1) {
+        const uint32_t add = (uint32_t)__popc(peers);
+        const uint32_t old = atomicAdd(&wcount[w0], add);
+        if (old <= max_depth && old + add > max_depth) *cap_flag = 1u;
+      }
+      for (int64_t w = w0 + 1; w < a.n_windows && a.wtid[w] == tid && a.wstart[w] < e; ++w) {
+        const uint32_t old = atomicAdd(&wcount[w], 1u);
+        if (old == max_depth) *cap_flag = 1u;
+      }
     }
   }
   // warp prefix sums of the two counts, one reservation per warp
