@@ -10,8 +10,10 @@
 // Inside a part (CTA of 8 warps, tile accumulators in shared memory):
 //   * a warp grabs a chunk of <= 32 segments; lane j loads segment j's record and read
 //     metadata (one global-latency for the whole chunk instead of one per segment);
-//   * per segment the lanes fetch the next 32 CIGAR ops at once, then walk them warp-uniformly;
-//   * a match op is consumed 128 query bases per step: lane L loads one aligned 32-bit word of
+//     and L2-prefetches the query bytes / first piece line that segment will touch;
+//   * per segment the lanes fetch its pieces (CIGAR ops clipped to the tile, precomputed by the segment
+//     builder in ls_segments.cuh) 32 at a time and go through them warp-uniformly -- no CIGAR walk here;
+//   * a match piece is consumed 128 query bases per step: lane L loads one aligned 32-bit word of
 //     qualities and one 16-bit word of 4-bit bases (vectorised, coalesced), classifies its 4
 //     bases and issues ONE packed shared atomic per visible base (count<<20 | quality).
 // (A two-phase variant that flattens op pieces into a per-warp unit queue was measured 1.8x

@@ -147,6 +147,47 @@ __global__ void __launch_bounds__(256) read_end_kernel(int64_t n, const int32_t 
   rend[r] = x;
 }
 
+// Records each pileup() call (bin) would fetch.  Bins are disjoint and sorted by (tid, start).  A read can only be
+// dropped in a bin that fetches more than max_depth records (the rule needs max_depth accepted reads alive), so
+// the host pre-pass below is skipped unless the add that crosses the cap raises *over.
+__global__ void __launch_bounds__(256) bin_fetch_count_kernel(int64_t n, const int32_t *__restrict__ tid,
+                                                              const int32_t *__restrict__ pos,
+                                                              const uint16_t *__restrict__ flag,
+                                                              const uint8_t *__restrict__ mapq,
+                                                              const uint32_t *__restrict__ cigar_off,
+                                                              const uint32_t *__restrict__ cigar, int64_t n_bins,
+                                                              const int32_t *__restrict__ btid,
+                                                              const int32_t *__restrict__ bstart,
+                                                              const int32_t *__restrict__ bend, int min_mq,
+                                                              uint32_t max_depth, uint32_t *__restrict__ bincount,
+                                                              uint32_t *__restrict__ over) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int32_t t = tid[r];
+  if (t < 0 || !read_passes_engine(flag[r], mapq[r], min_mq)) return;
+  const int32_t p = pos[r];
+  int64_t lo = 0, hi = n_bins;  // first bin with (btid, bend) > (t, p)
+  while (lo < hi) {
+    const int64_t m = (lo + hi) >> 1;
+    const int32_t bt = btid[m];
+    if (bt < t || (bt == t && bend[m] <= p))
+      lo = m + 1;
+    else
+      hi = m;
+  }
+  if (lo >= n_bins || btid[lo] != t) return;
+  int32_t x = p;
+  for (uint32_t k = cigar_off[r]; k < cigar_off[r + 1]; ++k) {
+    const uint32_t c = cigar[k];
+    if (op_consumes_ref(c & 15u)) x += (int32_t)(c >> 4);
+  }
+  const int32_t e = x > p ? x : p + 1;
+  for (int64_t b = lo; b < n_bins && btid[b] == t && bstart[b] < e; ++b) {
+    const uint32_t old = atomicAdd(&bincount[b], 1u);
+    if (old == max_depth) *over = 1u;
+  }
+}
+
 // Depth cap per pileup() call of the genotype scripts: one call per 50 kb bin of candidate sites
 // over [min-1, max+1) (SingleCellGenotype.py:110-124).  Same rule as ls_depth_cap_host.
 static int geno_depth_cap(ls_ctx *ctx, const std::vector<int32_t> &btid, const std::vector<int32_t> &bstart,
@@ -155,6 +196,25 @@ static int geno_depth_cap(ls_ctx *ctx, const std::vector<int32_t> &btid, const s
   ctx->n_drop = 0;
   if (max_depth <= 0 || n <= (int64_t)max_depth) return LS_OK;
   cudaStream_t st = ctx->stream;
+  {  // device pre-count: does any bin fetch more than max_depth records at all?
+    const size_t nb = btid.size();
+    LS_CK(ctx->wcount.ensure(nb * 4 * 4 + 16));
+    int32_t *d_bt = ctx->wcount.as<int32_t>(), *d_bs = d_bt + nb, *d_be = d_bs + nb;
+    uint32_t *d_cnt = reinterpret_cast<uint32_t *>(d_be + nb);  // [nb] counts + 1 flag word
+    LS_CK(cudaMemcpyAsync(d_bt, btid.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaMemcpyAsync(d_bs, bstart.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaMemcpyAsync(d_be, bend.data(), nb * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaMemsetAsync(d_cnt, 0, nb * 4 + 4, st));
+    bin_fetch_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        n, ctx->tid.as<int32_t>(), ctx->pos.as<int32_t>(), ctx->flag.as<uint16_t>(), ctx->mapq.as<uint8_t>(),
+        ctx->cigar_off.as<uint32_t>(), ctx->cigar.as<uint32_t>(), (int64_t)nb, d_bt, d_bs, d_be, min_mq,
+        (uint32_t)max_depth, d_cnt, d_cnt + nb);
+    LS_CK(cudaGetLastError());
+    uint32_t over = 0;
+    LS_CK(cudaMemcpyAsync(&over, d_cnt + nb, 4, cudaMemcpyDeviceToHost, st));
+    LS_CK(cudaStreamSynchronize(st));
+    if (!over) return LS_OK;
+  }
   LS_CK(ctx->rend.ensure((size_t)n * 4));
   read_end_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, ctx->pos.as<int32_t>(), ctx->cigar_off.as<uint32_t>(),
                                                                ctx->cigar.as<uint32_t>(), ctx->rend.as<int32_t>());
