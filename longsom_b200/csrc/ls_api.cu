@@ -40,8 +40,8 @@ extern "C" int ls_ctx_destroy(ls_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   DBuf *bufs[] = {&ctx->tid,       &ctx->pos,       &ctx->flag,      &ctx->mapq,       &ctx->cell,     &ctx->cigar_off,
                   &ctx->cigar,     &ctx->base_off,  &ctx->lq,        &ctx->seq4,       &ctx->qual,     &ctx->wtid,
-                  &ctx->wstart,    &ctx->wend,      &ctx->wref_off,  &ctx->ref,        &ctx->wtile_base, &ctx->nseg,
-                  &ctx->seg_off,   &ctx->segs,      &ctx->pieces,      &ctx->keys_a,    &ctx->keys_b,     &ctx->vals_a,   &ctx->vals_b,
+                  &ctx->wstart,    &ctx->wend,      &ctx->wref_off,  &ctx->ref,        &ctx->wtile_base,
+                  &ctx->segs,      &ctx->pieces,      &ctx->keys_a,    &ctx->keys_b,     &ctx->vals_a,   &ctx->vals_b,
                   &ctx->rs_hist,   &ctx->scan_tmp,  &ctx->counters,  &ctx->tile_flag,  &ctx->tile_rank, &ctx->slot_tile,
                   &ctx->slot_lo,   &ctx->slot_out,  &ctx->slot_mask, &ctx->slot_npass, &ctx->slot_off, &ctx->drop_keys,
                   &ctx->out_tid,   &ctx->out_pos,   &ctx->out_ref,   &ctx->out_counts, &ctx->l2_scratch, &ctx->g_a,
@@ -176,7 +176,7 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
 // (= per window): the first kept record at a start position P is always accepted; a later
 // record at P is dropped iff 1 + #{accepted records of this call with end >= P} > maxcnt.
 // Only windows that fetch more than max_depth records can ever drop, so the common case
-// costs one device-side count (done inside seg_count_kernel) and nothing here.
+// costs one device-side count (done inside seg_build_kernel) and nothing here.
 int ls_depth_cap_host(ls_ctx *ctx, int min_mq, int max_depth, const std::vector<uint32_t> &wcount) {
   const int64_t n = ctx->n_reads, nw = ctx->n_windows;
   std::vector<int32_t> tid(n), pos(n), rend(n);

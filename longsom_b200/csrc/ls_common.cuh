@@ -95,7 +95,7 @@ struct ls_ctx {
   // ---- run state ----
   bool have_run = false;
   ls_count_params params = {};
-  DBuf nseg, seg_off, segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
+  DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;
   DBuf drop_keys, rend, wcount, part_slot, part_k, slot_nparts, slot_done, acbuf;
   int64_t n_drop = 0;

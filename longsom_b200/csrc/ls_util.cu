@@ -1,5 +1,5 @@
 // Device-wide exclusive scan and stable LSD radix sort (hand-written; no CUB / Thrust).
-// Both are plumbing for the pileup path: the scan turns per-read segment counts into
+// Both are plumbing for the pileup path: the scans turn tile flags / per-tile pass counts into
 // offsets, the sort groups (read, tile) segments by (tile, cell).
 #include "ls_common.cuh"
 
