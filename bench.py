@@ -355,9 +355,46 @@ def run_ours(args, rank, world, local_rank):
     dte = reduce_max(time.perf_counter() - t0)
     h2d = batch.nbytes() + sum(getattr(windows, f).nbytes for f in ("tid", "start", "end", "ref_off", "ref"))
     d2h = int(ns) * (4 + 4 + 1 + 104)
+    single_ms = 1e3 * dte / e2e_steps
     e2e = {"value": total_units / (dte / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(reduce_sum(float(h2d))),
-           "d2h_bytes_per_step": int(reduce_sum(float(d2h))), "steps": e2e_steps, "ms_per_step": 1e3 * dte / e2e_steps,
+           "d2h_bytes_per_step": int(reduce_sum(float(d2h))), "steps": e2e_steps, "ms_per_step": single_ms,
            "api": "ls_pileup_count (C-ABI, pinned host buffers)"}
+    # Pipelined variant (what the CLI-level pipeline offers for large inputs): the same batch cut into window shards,
+    # ls_pileup_count() per shard on `lanes` CUDA contexts of this GPU, so uploads, kernels and result copies of
+    # different shards overlap.  Every step still moves every input byte H2D and every result byte D2H.
+    if args.e2e_shards > 1:
+        from longsom_b200.pipeline import count_shards_pipelined, window_shards
+        del pb, pw, out
+        shards = [(ReadBatch(*[pin(getattr(b_, f)) for f in ("tid", "pos", "flag", "mapq", "cell", "cigar_off", "cigar",
+                                                             "base_off", "l_qseq", "seq4", "qual")]),
+                   Windows(*[pin(getattr(w_, f)) for f in ("tid", "start", "end", "ref_off", "ref")]))
+                  for b_, w_ in window_shards(batch, windows, args.e2e_shards)]
+        lanes = [Engine(local_rank) for _ in range(max(1, args.e2e_lanes))]  # own contexts: `eng` keeps the full batch
+        sizes = []
+        for b_, w_ in shards:  # sizing pass (not timed): sites per shard
+            lanes[0].upload(b_, w_)
+            sizes.append(int(lanes[0].run(prm)))
+        assert sum(sizes) == int(n_sites), "window shards must reproduce the site count (%d vs %d)" % (sum(sizes), n_sites)
+        outs = [SiteCounts(pin(np.zeros(max(c, 1), np.int32)), pin(np.zeros(max(c, 1), np.int32)),
+                           pin(np.zeros(max(c, 1), np.uint8)), pin(np.zeros((max(c, 1), 26), np.uint32))) for c in sizes]
+        count_shards_pipelined(shards, prm, outs, engines=lanes)  # warm
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            got = count_shards_pipelined(shards, prm, outs, engines=lanes)
+        barrier()
+        dtp = reduce_max(time.perf_counter() - t0)
+        assert sum(got) == int(n_sites)
+        h2d_p = sum(b_.nbytes() + sum(getattr(w_, f).nbytes for f in ("tid", "start", "end", "ref_off", "ref"))
+                    for b_, w_ in shards)
+        e2e = {"value": total_units / (dtp / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(reduce_sum(float(h2d_p))),
+               "d2h_bytes_per_step": int(reduce_sum(float(d2h))), "steps": e2e_steps, "ms_per_step": 1e3 * dtp / e2e_steps,
+               "api": "longsom_b200.pipeline.count_shards_pipelined: ls_pileup_count (C-ABI, pinned host buffers) per "
+                      "window shard, %d shards on %d CUDA contexts of the GPU" % (len(shards), len(lanes)),
+               "single_call_ms_per_step": single_ms, "single_call_value": total_units / (single_ms * 1e-3)}
+        for l in lanes:
+            l.close()
+        del shards, outs
 
     # ---- second half of BASELINE.json's metric: candidate sites genotyped / s (K1' + K2), N=1 only -----------------
     secondary = None
@@ -425,6 +462,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=float(os.environ.get("LS_BENCH_SCALE", "1.0")),
                     help="fraction of the C2 workload (1.0 = 5M reads); only for local debugging")
+    ap.add_argument("--e2e-shards", type=int, default=8, help="window shards of the pipelined end-to-end leg (1 = off)")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="CUDA contexts the pipelined end-to-end leg alternates on")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     quiet_stdout()

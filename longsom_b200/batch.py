@@ -74,6 +74,16 @@ class ReadBatch:
         return sum(getattr(self, f).nbytes for f in
                    ("tid", "pos", "flag", "mapq", "cell", "cigar_off", "cigar", "base_off", "l_qseq", "seq4", "qual"))
 
+    def slice(self, lo, hi):
+        """Sub-batch of the consecutive reads [lo, hi): array slices with rebased offsets (no per-read work)."""
+        lo, hi = int(lo), int(hi)
+        c0, c1 = int(self.cigar_off[lo]), int(self.cigar_off[hi])
+        b0, b1 = int(self.base_off[lo]), int(self.base_off[hi])
+        return ReadBatch(self.tid[lo:hi], self.pos[lo:hi], self.flag[lo:hi], self.mapq[lo:hi], self.cell[lo:hi],
+                         (self.cigar_off[lo:hi + 1] - np.uint32(c0)).astype(np.uint32), self.cigar[c0:c1],
+                         (self.base_off[lo:hi + 1] - np.uint64(b0)).astype(np.uint64), self.l_qseq[lo:hi],
+                         self.seq4[b0 // 2:b1 // 2], self.qual[b0:b1])
+
     def select(self, idx):
         """Sub-batch with the given (sorted) read indices; re-packs cigar / bases."""
         idx = np.asarray(idx, dtype=np.int64)
@@ -121,6 +131,13 @@ class Windows:
         for f in ("tid", "start", "end", "ref_off", "ref"):
             setattr(s, f, _ptr(getattr(self, f)))
         return s
+
+    def slice(self, lo, hi):
+        """Windows [lo, hi) with their reference bytes."""
+        lo, hi = int(lo), int(hi)
+        r0, r1 = int(self.ref_off[lo]), int(self.ref_off[hi])
+        return Windows(self.tid[lo:hi], self.start[lo:hi], self.end[lo:hi],
+                       (self.ref_off[lo:hi + 1] - np.uint64(r0)).astype(np.uint64), self.ref[r0:r1])
 
     @staticmethod
     def from_intervals(intervals, contig_seqs):

@@ -91,6 +91,13 @@ def count_sites(batch, windows_iv, contig_seq, params: CountParams, devices=None
     devices = devices or [0]
     if not windows_iv:
         return SiteCounts.empty(0)
+    per_gpu = int(os.environ.get("LONGSOM_SHARDS_PER_GPU", "1") or 1)
+    if len(devices) == 1 and per_gpu > 1:
+        # one GPU, large input: window shards on two CUDA contexts so that uploads, kernels and result copies overlap
+        win = Windows.from_intervals(windows_iv, contig_seq)
+        res = count_shards_pipelined(window_shards(batch, win, per_gpu), params, None, device=devices[0], lanes=2)
+        return SiteCounts(np.concatenate([r.tid for r in res]), np.concatenate([r.pos for r in res]),
+                          np.concatenate([r.ref for r in res]), np.concatenate([r.counts for r in res], axis=0))
     ends = read_ends(batch)
     if len(devices) == 1:
         shards = [(0, len(windows_iv))]
@@ -135,6 +142,64 @@ def count_sites(batch, windows_iv, contig_seq, params: CountParams, devices=None
         raise errors[0]
     return SiteCounts(np.concatenate([r.tid for r in results]), np.concatenate([r.pos for r in results]),
                       np.concatenate([r.ref for r in results]), np.concatenate([r.counts for r in results], axis=0))
+
+
+def window_shards(batch: ReadBatch, windows: Windows, n_shards):
+    """Cut (batch, windows) into n_shards consecutive window groups of similar aligned-base weight.  Each shard
+    gets the consecutive read range that can overlap its windows (reads are position-sorted; a read that spans a
+    cut is in both shards and each shard only emits the sites of its own windows).  Array slices, no copies."""
+    nw = windows.n_windows
+    if nw == 0 or batch.n_reads == 0 or n_shards <= 1:
+        return [(batch, windows)]
+    ends = read_ends(batch)
+    rk_lo = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
+    rk_hi = np.maximum.accumulate((batch.tid.astype(np.int64) << 32) | np.maximum(ends, batch.pos.astype(np.int64) + 1))
+    wk_lo = (windows.tid.astype(np.int64) << 32) | windows.start.astype(np.int64)
+    wk_hi = (windows.tid.astype(np.int64) << 32) | windows.end.astype(np.int64)
+    idx = np.minimum(np.searchsorted(wk_hi, rk_lo, side="right"), nw - 1)
+    weight = np.zeros(nw)
+    np.add.at(weight, idx, batch.l_qseq.astype(np.float64))
+    out = []
+    for lo, hi in balanced_window_shards(weight, n_shards):
+        if hi <= lo:
+            continue
+        r_lo = int(np.searchsorted(rk_hi, wk_lo[lo], side="right"))   # first read whose running end passes the shard
+        r_hi = int(np.searchsorted(rk_lo, wk_hi[hi - 1], side="left"))
+        out.append((batch.slice(r_lo, max(r_lo, r_hi)), windows.slice(lo, hi)))
+    return out
+
+
+def count_shards_pipelined(shards, params: CountParams, outs, device=0, lanes=2, engines=None):
+    """Runs ls_pileup_count() on every (batch, windows) shard with `lanes` CUDA contexts on ONE device, each in
+    its own host thread: while one lane computes or copies results back, another uploads its next shard, so the
+    PCIe transfers of a job overlap with each other (H2D / D2H are separate engines) and with the kernels.
+    outs[i] (preallocated, e.g. pinned) receives shard i's sites and the per-shard site counts are returned; with
+    outs=None each shard's SiteCounts is allocated after its run and the list of SiteCounts is returned."""
+    own = engines is None
+    engines = engines or [Engine(device) for _ in range(max(1, lanes))]
+    n_sites = [0] * len(shards)
+    errors = []
+
+    def work(e):
+        try:
+            for i in range(e, len(shards), len(engines)):
+                if outs is None:
+                    n_sites[i] = engines[e].pileup_count(shards[i][0], shards[i][1], params)
+                else:
+                    n_sites[i] = engines[e].pileup_count_e2e(shards[i][0], shards[i][1], params, outs[i])
+        except Exception as ex:
+            errors.append(ex)
+    threads = [threading.Thread(target=work, args=(e,)) for e in range(len(engines))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if own:
+        for eng in engines:
+            eng.close()
+    if errors:
+        raise errors[0]
+    return n_sites
 
 
 def format_counter_lines(chrom, pos, ref, counts):

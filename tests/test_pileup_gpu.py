@@ -125,3 +125,26 @@ def test_results_independent_of_batch_composition(engine):
     assert sum(x.n_sites for x in parts) == full.n_sites
     assert np.array_equal(np.concatenate([x.pos for x in parts]), full.pos)
     assert np.array_equal(np.concatenate([x.counts for x in parts]), full.counts)
+
+
+def test_pipelined_window_shards_match_single_call(engine):
+    """pipeline.count_shards_pipelined: window shards on two CUDA contexts of one GPU (overlapped transfers) give,
+    concatenated, exactly the single-call result; the shards are array slices of the batch."""
+    from longsom_b200.batch import SiteCounts
+    from longsom_b200.pipeline import count_shards_pipelined, window_shards
+    d = synth.generate(seed=21, contig_lens=[400000, 150000], n_genes=40, n_reads=40000, n_cells=300)
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    p = CountParams(min_bq=20, min_mq=60)
+    full = engine.pileup_count(d.batch, w, p)
+    shards = window_shards(d.batch, w, 5)
+    assert len(shards) >= 3
+    outs = [SiteCounts(np.zeros(full.n_sites, np.int32), np.zeros(full.n_sites, np.int32), np.zeros(full.n_sites, np.uint8),
+                       np.zeros((full.n_sites, 26), np.uint32)) for _ in shards]
+    for _ in range(2):  # second round: contexts reused
+        got = count_shards_pipelined(shards, p, outs, device=0, lanes=2)
+        assert sum(got) == full.n_sites
+        assert np.array_equal(np.concatenate([o.tid[:c] for o, c in zip(outs, got)]), full.tid)
+        assert np.array_equal(np.concatenate([o.pos[:c] for o, c in zip(outs, got)]), full.pos)
+        assert np.array_equal(np.concatenate([o.counts[:c] for o, c in zip(outs, got)]), full.counts)
+    res = count_shards_pipelined(shards, p, None, device=0, lanes=2)   # outputs allocated per shard after its run
+    assert np.array_equal(np.concatenate([r.counts for r in res]), full.counts)

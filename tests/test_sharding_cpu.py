@@ -92,3 +92,26 @@ def test_two_rank_gloo_shards_concatenate(built, tmp_path):
     port = 29600 + (os.getpid() % 200)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert open(os.path.join(str(tmp_path), "result")).read() == "ok"
+
+
+def test_window_shards_are_slices_and_reproduce_the_whole(built):
+    """pipeline.window_shards (the pipelined single-GPU path): consecutive read ranges + window ranges whose oracle
+    results concatenate to the unsharded result; a read spanning a cut is in both shards."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    import oracle
+    from longsom_b200 import synth
+    from longsom_b200.batch import Windows, make_windows
+    from longsom_b200.engine import CountParams
+    from longsom_b200.pipeline import window_shards
+    d = synth.generate(seed=5, contig_lens=[300000, 120000], n_genes=25, n_reads=6000, n_cells=60)
+    w = Windows.from_intervals(make_windows(d.contig_lens, 50000), d.contig_seqs())
+    p = CountParams(min_bq=20, min_mq=60, min_dp=2, min_cc=1)
+    full = oracle.pileup_count(d.batch, w, p)[0]
+    shards = window_shards(d.batch, w, 4)
+    assert sum(ws.n_windows for _, ws in shards) == w.n_windows
+    assert sum(b.n_reads for b, _ in shards) >= d.batch.n_reads * 0.9
+    parts = [oracle.pileup_count(b, ws, p)[0] for b, ws in shards]
+    assert sum(x.n_sites for x in parts) == full.n_sites
+    assert np.array_equal(np.concatenate([x.pos for x in parts]), full.pos)
+    assert np.array_equal(np.concatenate([x.counts for x in parts]), full.counts)
+    assert window_shards(d.batch, w, 1)[0][0] is d.batch
