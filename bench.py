@@ -9,8 +9,10 @@ batch, 5M reads x ~1.5 kb, 5k cells; at N > 1 the SAME batch is sharded by cover
 genomic bins across the GPUs (strong scaling, no collective on the data path).
 A "step" is one pass of the hot path over the resident batch: segment build -> (tile, cell)
 sort -> pileup-count kernel -> per-tile site tables in HBM.  `value` is device-resident
-throughput, `e2e` is the same metric through the single C-ABI call ls_pileup_count() with
-pinned HOST buffers (H2D of the batch and D2H of the compacted site table inside the timing).
+throughput, `e2e` is the same metric from pinned HOST buffers (H2D of the batch and D2H of the compacted
+site table inside the timing): the batch cut into --e2e-shards window shards, the C-ABI call ls_pileup_count()
+per shard on --e2e-lanes CUDA contexts of the GPU (pipeline.count_shards_pipelined), so that transfers and
+kernels of different shards overlap; the one-call figure is reported next to it (e2e.single_call_*).
 One JSON line on stdout (rank 0).
 """
 import argparse

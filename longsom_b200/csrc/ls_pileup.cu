@@ -13,7 +13,7 @@
 //   1. seg_build_kernel (ls_segments.cuh): one thread per read walks its CIGAR and emits one Segment per
 //      (read, tile) pair that has at least one pileup entry, plus the segment's Pieces (ops clipped to the tile).
 //   2. radix sort of segments by (tile, cell)  -> same-cell segments of a tile are adjacent.
-//   3. pileup_count_kernel : CTA per non-empty tile; a warp owns a run of same-cell
+//   3. pileup_count_kernel : CTA per part (<= 2048 sorted segments of one tile); a warp owns a run of same-cell
 //      segments, lanes stride consecutive reference positions (coalesced seq4/qual
 //      reads, conflict-free shared atomics); distinct-cell counts NC/CC are
 //      "reads minus same-cell duplicates", the duplicates found with a per-warp
