@@ -84,8 +84,6 @@ def test_bai_region_queries_equal_brute_force(split_runs):
         recs = [l.split("\t") for l in pi.dump_bam_records(path)[1:]]
         refs, n_no_coor = bai_query.read_bai(path + ".bai")
         assert n_no_coor == 0
-        import struct, gzip as gz
-        raw = gz.open(path, "rb").read()
         # brute force needs the reference span: take it from the product decoder
         from longsom_b200 import bamio
         from longsom_b200.pipeline import read_ends
