@@ -52,6 +52,7 @@ int ls_write_counter_rows(const char *path, const char *chrom, const int32_t *po
  * trim; a clip of 20..29 bases counts as 30).  counters[36]: Total_reads, Pass_reads, CB_not_found,
  * CB_not_matched, then [4 + mask] = reads dropped for reason set mask (1 nM, 2 nM_not_found, 4 NH,
  * 8 NH_not_found, 16 MAPQ); first_seen[32]: 1-based ordinal of the first read dropped for that set.
+ * Input and outputs are streamed (64 MB compressed input chunks, 16 MB of pending records per output).
  * Returns 0, or -1 with a message in err (errors the reference raises -- trim longer than a read, a read
  * without qualities, a non-string CB -- are reported, not skipped). */
 int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths, const char *bc_blob,

@@ -12,8 +12,12 @@
 //     20 <= L < 30 is treated as 30 (SplitBamCellTypes.py:140-160);
 //   * the record is appended, otherwise byte for byte, to the BAM of its cell type; outputs get the
 //     input's header, a BGZF EOF marker and a .bai index.
+// Streaming: the input is read in ~64 MB compressed chunks whose BGZF members are inflated in parallel;
+// each output keeps at most a few MB of pending records, deflates full 0xff00-byte members in parallel
+// and appends them to its file; the .bai is accumulated on uncompressed offsets and translated to
+// virtual offsets at the end.  Memory is bounded by the chunk sizes, not by the BAM.
 // Differences by construction: members are deflated in parallel (so the compressed bytes differ from
-// htslib's, the records do not) and the whole input is inflated in memory, like ls_bamread.cpp.
+// htslib's, the records do not).
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -29,6 +33,16 @@
 using namespace lsbgzf;
 
 namespace {
+
+// compressed bytes read per round / pending uncompressed bytes per output before a parallel deflate; the
+// environment overrides exist for the tests, which force many rounds and mid-stream flushes on small files
+static size_t env_size(const char *name, size_t dflt) {
+  const char *v = getenv(name);
+  if (!v || !*v) return dflt;
+  const long long x = atoll(v);
+  return x < 4096 ? (size_t)4096 : (size_t)x;
+}
+static const size_t kReadChunkDefault = 64u << 20, kFlushBytesDefault = 16u << 20;
 
 struct AuxHit {
   bool found = false;
@@ -92,12 +106,6 @@ static int reg2bin(int64_t beg, int64_t end) {
   return 0;
 }
 
-struct OutRec {
-  int32_t tid, beg, end;
-  uint64_t u0, u1;  // uncompressed stream offsets of the record
-  bool mapped;
-};
-
 static void put32(std::vector<uint8_t> &v, uint32_t x) {
   uint8_t b[4];
   wr32(b, x);
@@ -108,87 +116,213 @@ static void put64(std::vector<uint8_t> &v, uint64_t x) {
   put32(v, (uint32_t)(x >> 32));
 }
 
-// .bai of a coordinate-sorted record list (SAM spec 5.2), including the 37450 metadata bin samtools writes
-static bool build_bai(const std::vector<OutRec> &recs, int n_ref, const std::vector<uint64_t> &coff, std::vector<uint8_t> &bai,
-                      std::string &err) {
-  auto voff = [&](uint64_t u) { return (coff[u / kBlockPayload] << 16) | (u % kBlockPayload); };
-  bai.clear();
-  bai.insert(bai.end(), {'B', 'A', 'I', 1});
-  put32(bai, (uint32_t)n_ref);
-  size_t i = 0;
-  int32_t prev_tid = -1, prev_beg = -1;
-  for (const OutRec &r : recs) {
-    if (r.tid < prev_tid || (r.tid == prev_tid && r.beg < prev_beg)) {
-      err = "records are not sorted by coordinate: cannot index";
-      return false;
-    }
-    prev_tid = r.tid;
-    prev_beg = r.beg;
-  }
-  for (int t = 0; t < n_ref; ++t) {
+// .bai of a coordinate-sorted record stream (SAM spec 5.2, with the 37450 metadata bin samtools writes),
+// accumulated record by record on UNCOMPRESSED stream offsets; finish() maps them to virtual offsets.
+struct BaiBuilder {
+  struct Ref {
     std::map<uint32_t, std::vector<std::pair<uint64_t, uint64_t>>> bins;
-    std::vector<uint64_t> lin;
+    std::vector<uint64_t> lin;  // first record start per 16 kb window, UINT64_MAX = none yet
     uint64_t off_beg = 0, off_end = 0, n_map = 0, n_unmap = 0;
     bool any = false;
     int last_bin = -1;
-    while (i < recs.size() && recs[i].tid == t) {
-      const OutRec &r = recs[i];
-      const uint64_t v0 = voff(r.u0), v1 = voff(r.u1);
-      const int b = reg2bin(r.beg, r.end);
-      auto &ch = bins[(uint32_t)b];
-      if (b == last_bin && !ch.empty() && ch.back().second == v0)
-        ch.back().second = v1;  // consecutive records of one bin form one chunk
-      else
-        ch.emplace_back(v0, v1);
-      last_bin = b;
-      const size_t w0 = (size_t)(r.beg >> 14), w1 = (size_t)((r.end - 1) >> 14);
-      if (lin.size() <= w1) lin.resize(w1 + 1, 0);
-      for (size_t w = w0; w <= w1; ++w)
-        if (lin[w] == 0) lin[w] = v0;
-      if (!any) off_beg = v0;
-      off_end = v1;
-      any = true;
-      (r.mapped ? n_map : n_unmap)++;
-      ++i;
+  };
+  std::vector<Ref> refs;
+  int32_t prev_tid = -1, prev_beg = -1;
+  bool sorted = true;
+
+  explicit BaiBuilder(int n_ref) : refs((size_t)n_ref) {}
+
+  void add(int32_t tid, int32_t beg, int32_t end, uint64_t u0, uint64_t u1, bool mapped) {
+    if (tid < prev_tid || (tid == prev_tid && beg < prev_beg)) sorted = false;
+    prev_tid = tid;
+    prev_beg = beg;
+    if (tid < 0 || (size_t)tid >= refs.size()) {
+      sorted = false;
+      return;
     }
-    for (size_t w = 1; w < lin.size(); ++w)
-      if (lin[w] == 0) lin[w] = lin[w - 1];
-    put32(bai, (uint32_t)(bins.size() + (any ? 1 : 0)));
-    for (auto &kv : bins) {
-      put32(bai, kv.first);
-      put32(bai, (uint32_t)kv.second.size());
-      for (auto &c : kv.second) {
-        put64(bai, c.first);
-        put64(bai, c.second);
+    Ref &r = refs[(size_t)tid];
+    const int b = reg2bin(beg, end);
+    auto &ch = r.bins[(uint32_t)b];
+    if (b == r.last_bin && !ch.empty() && ch.back().second == u0)
+      ch.back().second = u1;  // consecutive records of one bin form one chunk
+    else
+      ch.emplace_back(u0, u1);
+    r.last_bin = b;
+    const size_t w0 = (size_t)(beg >> 14), w1 = (size_t)((end - 1) >> 14);
+    if (r.lin.size() <= w1) r.lin.resize(w1 + 1, UINT64_MAX);
+    for (size_t w = w0; w <= w1; ++w)
+      if (r.lin[w] == UINT64_MAX) r.lin[w] = u0;
+    if (!r.any) r.off_beg = u0;
+    r.off_end = u1;
+    r.any = true;
+    (mapped ? r.n_map : r.n_unmap)++;
+  }
+
+  template <typename VOFF>
+  void finish(VOFF voff, std::vector<uint8_t> &bai) const {
+    bai.clear();
+    bai.insert(bai.end(), {'B', 'A', 'I', 1});
+    put32(bai, (uint32_t)refs.size());
+    for (const Ref &r : refs) {
+      put32(bai, (uint32_t)(r.bins.size() + (r.any ? 1 : 0)));
+      for (const auto &kv : r.bins) {
+        put32(bai, kv.first);
+        put32(bai, (uint32_t)kv.second.size());
+        for (const auto &c : kv.second) {
+          put64(bai, voff(c.first));
+          put64(bai, voff(c.second));
+        }
+      }
+      if (r.any) {
+        put32(bai, 37450u);
+        put32(bai, 2u);
+        put64(bai, voff(r.off_beg));
+        put64(bai, voff(r.off_end));
+        put64(bai, r.n_map);
+        put64(bai, r.n_unmap);
+      }
+      put32(bai, (uint32_t)r.lin.size());
+      uint64_t prev = 0;
+      for (uint64_t u : r.lin) {  // windows no record starts in inherit the previous offset, as samtools does
+        if (u != UINT64_MAX) prev = voff(u);
+        put64(bai, prev);
       }
     }
-    if (any) {
-      put32(bai, 37450u);
-      put32(bai, 2u);
-      put64(bai, off_beg);
-      put64(bai, off_end);
-      put64(bai, n_map);
-      put64(bai, n_unmap);
-    }
-    put32(bai, (uint32_t)lin.size());
-    for (uint64_t v : lin) put64(bai, v);
+    put64(bai, 0);  // records without coordinates: none are written
   }
-  put64(bai, 0);  // records without coordinates: none are written
-  return true;
-}
+};
 
-static bool write_file(const std::string &path, const std::vector<uint8_t> &a, const uint8_t *tail, size_t ntail, std::string &err) {
+// One output BAM: pending uncompressed bytes, the file, the compressed offset of every member written so far.
+struct OutStream {
+  std::string path;
+  FILE *f = nullptr;
+  std::vector<uint8_t> pending;
+  uint64_t flushed = 0;         // uncompressed bytes already deflated (always a multiple of kBlockPayload)
+  uint64_t c_total = 0;         // compressed bytes written
+  std::vector<uint64_t> coff;   // file offset of member i
+  BaiBuilder bai;
+
+  OutStream(const std::string &p, int n_ref) : path(p), bai(n_ref) {}
+
+  uint64_t tell() const { return flushed + pending.size(); }
+
+  bool flush(bool final, int threads, int level, std::string &err) {
+    const size_t nbytes = final ? pending.size() : (pending.size() / kBlockPayload) * kBlockPayload;
+    if (nbytes) {
+      std::vector<uint8_t> comp;
+      std::vector<uint64_t> rel;
+      if (!deflate_stream(pending.data(), nbytes, threads, level, comp, rel, err)) return false;
+      for (size_t i = 0; i + 1 < rel.size(); ++i) coff.push_back(c_total + rel[i]);
+      if (fwrite(comp.data(), 1, comp.size(), f) != comp.size()) {
+        err = "short write to " + path;
+        return false;
+      }
+      c_total += comp.size();
+      flushed += nbytes;
+      pending.erase(pending.begin(), pending.begin() + (ptrdiff_t)nbytes);
+    }
+    if (final) coff.push_back(c_total);  // virtual offset of the end of the stream = start of the EOF member
+    return true;
+  }
+
+  uint64_t voff(uint64_t u) const { return (coff[u / kBlockPayload] << 16) | (u % kBlockPayload); }
+};
+
+static bool write_whole(const std::string &path, const std::vector<uint8_t> &a, std::string &err) {
   FILE *f = fopen(path.c_str(), "wb");
   if (!f) {
     err = "cannot create " + path;
     return false;
   }
   bool ok = a.empty() || fwrite(a.data(), 1, a.size(), f) == a.size();
-  if (ok && ntail) ok = fwrite(tail, 1, ntail, f) == ntail;
   ok = (fclose(f) == 0) && ok;
   if (!ok) err = "short write to " + path;
   return ok;
 }
+
+// Sequential reader of a BGZF file: each round() appends the inflated payload of the next ~kReadChunk compressed
+// bytes to `out` (members inflated in parallel) and returns false at end of file or on error (err set).
+struct BgzfChunkReader {
+  FILE *f = nullptr;
+  std::vector<uint8_t> cbuf;
+  size_t have = 0;
+  bool eof = false;
+  int threads = 1;
+  size_t kReadChunk = kReadChunkDefault;
+
+  bool round(std::vector<uint8_t> &out, std::string &err) {
+    if (!eof) {
+      cbuf.resize(have + kReadChunk);
+      const size_t got = fread(cbuf.data() + have, 1, kReadChunk, f);
+      have += got;
+      if (got < kReadChunk) eof = true;
+    }
+    struct M {
+      size_t coff, uoff;
+      uint32_t csize, usize;
+    };
+    std::vector<M> ms;
+    size_t off = 0, uo = out.size();
+    while (off + 18 <= have) {
+      const uint8_t *p = cbuf.data() + off;
+      if (p[0] != 0x1f || p[1] != 0x8b || !(p[3] & 4)) {
+        err = "not a BGZF file (bad gzip member header)";
+        return false;
+      }
+      const uint32_t xlen = rd16(p + 10);
+      if (off + 12 + xlen > have) break;
+      uint32_t bsize = 0;
+      const uint8_t *x = p + 12, *xe = p + 12 + xlen;
+      while (x + 4 <= xe) {
+        const uint32_t slen = rd16(x + 2);
+        if (x[0] == 'B' && x[1] == 'C' && slen == 2) bsize = (uint32_t)rd16(x + 4) + 1;
+        x += 4 + slen;
+      }
+      if (bsize == 0) {
+        err = "corrupt BGZF block";
+        return false;
+      }
+      if (off + bsize > have) break;
+      M m;
+      m.coff = off;
+      m.csize = bsize;
+      m.usize = rd32(p + bsize - 4);
+      m.uoff = uo;
+      ms.push_back(m);
+      uo += m.usize;
+      off += bsize;
+    }
+    if (ms.empty()) {
+      if (eof && have == off) return false;  // clean end
+      if (eof) {
+        err = "truncated BGZF file";
+        return false;
+      }
+      return true;  // a member larger than what is buffered cannot happen (<= 64 KiB); read more
+    }
+    out.resize(uo);
+    std::atomic<size_t> next(0);
+    std::atomic<int> bad(0);
+    auto worker = [&]() {
+      for (;;) {
+        const size_t i = next.fetch_add(16);
+        if (i >= ms.size()) break;
+        for (size_t j = i; j < i + 16 && j < ms.size(); ++j)
+          if (ms[j].usize && !inflate_member(cbuf.data() + ms[j].coff, ms[j].csize, out.data() + ms[j].uoff, ms[j].usize)) bad = 1;
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < (threads < 1 ? 1 : threads); ++t) th.emplace_back(worker);
+    for (auto &t : th) t.join();
+    if (bad) {
+      err = "inflate failed";
+      return false;
+    }
+    memmove(cbuf.data(), cbuf.data() + off, have - off);
+    have -= off;
+    return true;
+  }
+};
 
 }  // namespace
 
@@ -205,139 +339,184 @@ int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths,
                  const uint32_t *bc_off, const int32_t *bc_type, int64_t n_bc, int min_mapq, int max_nm, int max_nh,
                  int n_trim, int threads, int level, int64_t *counters, int64_t *first_seen, char *err, int errlen) {
   std::string e;
+  std::vector<OutStream> outs;
+  BgzfChunkReader rd;
   auto fail = [&](const std::string &m) {
     snprintf(err, (size_t)errlen, "%s", m.c_str());
+    for (auto &o : outs)
+      if (o.f) fclose(o.f);
+    if (rd.f) fclose(rd.f);
     return -1;
   };
   for (int k = 0; k < 36; ++k) counters[k] = 0;
   for (int k = 0; k < 32; ++k) first_seen[k] = 0;
-  std::vector<uint8_t> raw;
-  if (!inflate_file(in_path, threads, raw, e)) return fail(e);
-  const uint8_t *p = raw.data(), *end = raw.data() + raw.size();
-  if (raw.size() < 12 || memcmp(p, "BAM\1", 4) != 0) return fail("bad BAM magic");
-  const uint32_t l_text = rd32(p + 4);
-  if ((uint64_t)12 + l_text > raw.size()) return fail("truncated BAM header");
-  p += 8 + l_text;
-  const uint32_t n_ref = rd32(p);
-  p += 4;
-  for (uint32_t i = 0; i < n_ref; ++i) {
-    if (p + 8 > end) return fail("truncated BAM header");
-    p += 8 + rd32(p);
-  }
-  if (p > end) return fail("truncated BAM header");
-  const size_t header_len = (size_t)(p - raw.data());
+  rd.f = fopen(in_path, "rb");
+  if (!rd.f) return fail(std::string("cannot open ") + in_path);
+  rd.threads = threads;
+  rd.kReadChunk = env_size("LS_SPLIT_READ_CHUNK", kReadChunkDefault);
+  const size_t kFlushBytes = env_size("LS_SPLIT_FLUSH_BYTES", kFlushBytesDefault);
 
   std::unordered_map<std::string, int32_t> table;
   table.reserve((size_t)n_bc * 2 + 1);
   for (int64_t i = 0; i < n_bc; ++i)
     table[std::string(bc_blob + bc_off[i], bc_off[i + 1] - bc_off[i])] = bc_type[i];  // later rows win, like dict()
 
-  std::vector<std::vector<uint8_t>> streams((size_t)n_types);
-  std::vector<std::vector<OutRec>> recs((size_t)n_types);
-  for (auto &s : streams) s.assign(raw.data(), raw.data() + header_len);
-
+  std::vector<uint8_t> ubuf;  // [carry of the previous round | newly inflated bytes]
+  bool header_done = false;
+  uint32_t n_ref = 0;
   int64_t visited = 0;
   std::string key;
-  while (p + 4 <= end) {
-    const uint32_t bs = rd32(p);
-    const uint8_t *r = p + 4;
-    if (bs < 32 || r + bs > end) return fail("truncated BAM record");
-    p = r + bs;
-    const int32_t tid = (int32_t)rd32(r);
-    if (tid < 0) continue;  // fetch() without a region does not visit reads without a reference
-    ++visited;
-    ++counters[0];
-    const int32_t pos = (int32_t)rd32(r + 4);
-    const uint32_t l_name = r[8], mapq = r[9];
-    const uint32_t n_cig = rd16(r + 12), flag = rd16(r + 14), l_seq = rd32(r + 16);
-    const uint8_t *cig = r + 32 + l_name;
-    const uint8_t *seq = cig + 4 * (size_t)n_cig;
-    const uint8_t *qual = seq + (l_seq + 1) / 2;
-    const uint8_t *aux = qual + l_seq;
-    if (aux > r + bs) return fail("corrupt BAM record");
-    const AuxHit cb = find_aux(aux, r + bs, 'C', 'B');
-    if (!cb.found) {
-      ++counters[2];
-      continue;
-    }
-    if (!cb.is_text) return fail("CB tag is not a string (the reference fails on barcode.split here)");
-    const char *dash = strchr(cb.text, '-');
-    key.assign(cb.text, dash ? (size_t)(dash - cb.text) : strlen(cb.text));
-    auto it = table.find(key);
-    if (it == table.end()) {
-      ++counters[3];
-      continue;
-    }
-    int mask = 0;
-    if (max_nm >= 0) {
-      const AuxHit h = find_aux(aux, r + bs, 'n', 'M');
-      if (!h.found)
-        mask |= LS_SPLIT_NM_MISSING;
-      else if (!(h.is_int || h.is_float))
-        return fail("nM tag is not numeric");
-      else if ((h.is_int ? (double)h.ival : h.fval) > (double)max_nm)
-        mask |= LS_SPLIT_NM;
-    }
-    if (max_nh >= 0) {
-      const AuxHit h = find_aux(aux, r + bs, 'N', 'H');
-      if (!h.found)
-        mask |= LS_SPLIT_NH_MISSING;
-      else if (!(h.is_int || h.is_float))
-        return fail("NH tag is not numeric");
-      else if ((h.is_int ? (double)h.ival : h.fval) > (double)max_nh)
-        mask |= LS_SPLIT_NH;
-    }
-    if (min_mapq > 0 && (int)mapq < min_mapq) mask |= LS_SPLIT_MAPQ;
-    if (mask) {
-      ++counters[4 + mask];
-      if (!first_seen[mask]) first_seen[mask] = visited;
-      continue;
-    }
-    ++counters[1];
-    std::vector<uint8_t> &s = streams[(size_t)it->second];
-    const uint64_t u0 = s.size();
-    s.insert(s.end(), r - 4, r + bs);
-    if (n_trim > 0) {
-      uint32_t trim_start = (uint32_t)n_trim, trim_end = (uint32_t)n_trim;
-      if (n_cig > 1) {
-        const uint32_t c0 = rd32(cig), c1 = rd32(cig + 4 * (size_t)(n_cig - 1));
-        if ((c0 & 15u) == 4u) trim_start = (((c0 >> 4) >= 20 && (c0 >> 4) < 30) ? 30u : (c0 >> 4)) + (uint32_t)n_trim;
-        if ((c1 & 15u) == 4u) trim_end = (((c1 >> 4) >= 20 && (c1 >> 4) < 30) ? 30u : (c1 >> 4)) + (uint32_t)n_trim;
+  for (;;) {
+    const size_t before = ubuf.size();
+    const bool more = rd.round(ubuf, e);
+    if (!e.empty()) return fail(e);
+    const uint8_t *p = ubuf.data(), *end = ubuf.data() + ubuf.size();
+    if (!header_done) {
+      // magic, l_text, text, n_ref, then per reference l_name, name, l_ref: wait until all of it is buffered
+      bool complete = false;
+      size_t hl = 0;
+      if (ubuf.size() >= 12) {
+        if (memcmp(p, "BAM\1", 4) != 0) return fail("bad BAM magic");
+        const uint64_t l_text = rd32(p + 4);
+        if (ubuf.size() >= 12 + l_text) {
+          n_ref = rd32(p + 8 + l_text);
+          size_t q = 12 + (size_t)l_text;
+          uint32_t i = 0;
+          for (; i < n_ref; ++i) {
+            if (q + 4 > ubuf.size()) break;
+            const uint64_t l_name = rd32(p + q);
+            if (q + 8 + l_name > ubuf.size()) break;
+            q += 8 + (size_t)l_name;
+          }
+          if (i == n_ref) {
+            complete = true;
+            hl = q;
+          }
+        }
       }
-      if (l_seq == 0 || qual[0] == 0xff) return fail("read without base qualities cannot be trimmed (TypeError in the reference)");
-      if (trim_start > l_seq || trim_end > l_seq)
-        return fail("IndexError: read shorter than the trimmed ends (the reference fails here as well)");
-      uint8_t *q = s.data() + u0 + 4 + (size_t)(qual - r);
-      memset(q, 0, trim_start);
-      memset(q + l_seq - trim_end, 0, trim_end);
+      if (!complete) {
+        if (!more) return fail(ubuf.empty() ? "empty file" : "truncated BAM header");
+        continue;
+      }
+      outs.reserve((size_t)n_types);
+      for (int t = 0; t < n_types; ++t) {
+        outs.emplace_back(out_paths[t], (int)n_ref);
+        outs.back().f = fopen(out_paths[t], "wb");
+        if (!outs.back().f) return fail(std::string("cannot create ") + out_paths[t]);
+        outs.back().pending.assign(p, p + hl);
+      }
+      header_done = true;
+      p += hl;
     }
-    // reference span for the index: M/D/N/=/X lengths (bam_endpos; 1 for records without one)
-    int64_t span = 0;
-    for (uint32_t k = 0; k < n_cig; ++k) {
-      const uint32_t c = rd32(cig + 4 * (size_t)k), op = c & 15u;
-      if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4;
+    while (p + 4 <= end) {
+      const uint32_t bs = rd32(p);
+      if (bs < 32) return fail("corrupt BAM record");
+      if (p + 4 + (size_t)bs > end) break;  // the rest of this record comes with the next round
+      const uint8_t *r = p + 4;
+      p = r + bs;
+      const int32_t tid = (int32_t)rd32(r);
+      if (tid < 0) continue;  // fetch() without a region does not visit reads without a reference
+      ++visited;
+      ++counters[0];
+      const int32_t pos = (int32_t)rd32(r + 4);
+      const uint32_t l_name = r[8], mapq = r[9];
+      const uint32_t n_cig = rd16(r + 12), flag = rd16(r + 14), l_seq = rd32(r + 16);
+      const uint8_t *cig = r + 32 + l_name;
+      const uint8_t *seq = cig + 4 * (size_t)n_cig;
+      const uint8_t *qual = seq + (l_seq + 1) / 2;
+      const uint8_t *aux = qual + l_seq;
+      if (aux > r + bs) return fail("corrupt BAM record");
+      const AuxHit cb = find_aux(aux, r + bs, 'C', 'B');
+      if (!cb.found) {
+        ++counters[2];
+        continue;
+      }
+      if (!cb.is_text) return fail("CB tag is not a string (the reference fails on barcode.split here)");
+      const char *dash = strchr(cb.text, '-');
+      key.assign(cb.text, dash ? (size_t)(dash - cb.text) : strlen(cb.text));
+      auto it = table.find(key);
+      if (it == table.end()) {
+        ++counters[3];
+        continue;
+      }
+      int mask = 0;
+      if (max_nm >= 0) {
+        const AuxHit h = find_aux(aux, r + bs, 'n', 'M');
+        if (!h.found)
+          mask |= LS_SPLIT_NM_MISSING;
+        else if (!(h.is_int || h.is_float))
+          return fail("nM tag is not numeric");
+        else if ((h.is_int ? (double)h.ival : h.fval) > (double)max_nm)
+          mask |= LS_SPLIT_NM;
+      }
+      if (max_nh >= 0) {
+        const AuxHit h = find_aux(aux, r + bs, 'N', 'H');
+        if (!h.found)
+          mask |= LS_SPLIT_NH_MISSING;
+        else if (!(h.is_int || h.is_float))
+          return fail("NH tag is not numeric");
+        else if ((h.is_int ? (double)h.ival : h.fval) > (double)max_nh)
+          mask |= LS_SPLIT_NH;
+      }
+      if (min_mapq > 0 && (int)mapq < min_mapq) mask |= LS_SPLIT_MAPQ;
+      if (mask) {
+        ++counters[4 + mask];
+        if (!first_seen[mask]) first_seen[mask] = visited;
+        continue;
+      }
+      ++counters[1];
+      OutStream &o = outs[(size_t)it->second];
+      const uint64_t u0 = o.tell();
+      const size_t at = o.pending.size();
+      o.pending.insert(o.pending.end(), r - 4, r + bs);
+      if (n_trim > 0) {
+        uint32_t trim_start = (uint32_t)n_trim, trim_end = (uint32_t)n_trim;
+        if (n_cig > 1) {
+          const uint32_t c0 = rd32(cig), c1 = rd32(cig + 4 * (size_t)(n_cig - 1));
+          if ((c0 & 15u) == 4u) trim_start = (((c0 >> 4) >= 20 && (c0 >> 4) < 30) ? 30u : (c0 >> 4)) + (uint32_t)n_trim;
+          if ((c1 & 15u) == 4u) trim_end = (((c1 >> 4) >= 20 && (c1 >> 4) < 30) ? 30u : (c1 >> 4)) + (uint32_t)n_trim;
+        }
+        if (l_seq == 0 || qual[0] == 0xff) return fail("read without base qualities cannot be trimmed (TypeError in the reference)");
+        if (trim_start > l_seq || trim_end > l_seq)
+          return fail("IndexError: read shorter than the trimmed ends (the reference fails here as well)");
+        uint8_t *q = o.pending.data() + at + 4 + (size_t)(qual - r);
+        memset(q, 0, trim_start);
+        memset(q + l_seq - trim_end, 0, trim_end);
+      }
+      // reference span for the index: M/D/N/=/X lengths (bam_endpos; 1 for records without one)
+      int64_t span = 0;
+      for (uint32_t k = 0; k < n_cig; ++k) {
+        const uint32_t c = rd32(cig + 4 * (size_t)k), op = c & 15u;
+        if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) span += c >> 4;
+      }
+      const bool mapped = !(flag & 4u);
+      o.bai.add(tid, pos, (int32_t)(pos + ((mapped && span > 0) ? span : 1)), u0, o.tell(), mapped);
+      if (o.pending.size() >= kFlushBytes && !o.flush(false, threads, level, e)) return fail(e);
     }
-    const bool mapped = !(flag & 4u);
-    OutRec o;
-    o.tid = tid;
-    o.beg = pos;
-    o.end = (int32_t)(pos + ((mapped && span > 0) ? span : 1));
-    o.u0 = u0;
-    o.u1 = s.size();
-    o.mapped = mapped;
-    recs[(size_t)it->second].push_back(o);
+    // keep the incomplete tail for the next round
+    const size_t left = (size_t)(end - p);
+    if (left) memmove(ubuf.data(), p, left);
+    ubuf.resize(left);
+    if (!more) {
+      if (left) return fail("truncated BAM record");
+      break;
+    }
+    (void)before;
   }
-  raw.clear();
-  raw.shrink_to_fit();
+  if (!header_done) return fail("truncated BAM header");
+  fclose(rd.f);
+  rd.f = nullptr;
 
-  for (int t = 0; t < n_types; ++t) {
-    std::vector<uint8_t> comp, bai;
-    std::vector<uint64_t> coff;
-    if (!deflate_stream(streams[(size_t)t].data(), streams[(size_t)t].size(), threads, level, comp, coff, e)) return fail(e);
-    if (!write_file(out_paths[t], comp, kEofBlock, sizeof kEofBlock, e)) return fail(e);
-    if (!build_bai(recs[(size_t)t], (int)n_ref, coff, bai, e)) return fail(e + " (" + out_paths[t] + ")");
-    if (!write_file(std::string(out_paths[t]) + ".bai", bai, nullptr, 0, e)) return fail(e);
-    std::vector<uint8_t>().swap(streams[(size_t)t]);
+  for (auto &o : outs) {
+    if (!o.flush(true, threads, level, e)) return fail(e);
+    bool ok = fwrite(kEofBlock, 1, sizeof kEofBlock, o.f) == sizeof kEofBlock;
+    ok = (fclose(o.f) == 0) && ok;
+    o.f = nullptr;
+    if (!ok) return fail("short write to " + o.path);
+    if (!o.bai.sorted) return fail("records are not sorted by coordinate: cannot index (" + o.path + ")");
+    std::vector<uint8_t> bai;
+    o.bai.finish([&](uint64_t u) { return o.voff(u); }, bai);
+    if (!write_whole(o.path + ".bai", bai, e)) return fail(e);
   }
   return 0;
 }

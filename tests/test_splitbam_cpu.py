@@ -117,3 +117,32 @@ def test_split_fails_loudly_like_the_reference(tmp_path, built):
         splitbam.main(["--bam", bam, "--meta", meta, "--id", "s", "--outdir", str(tmp_path), "--min_MQ", "0", "--n_trim", "500"])
     with pytest.raises(RuntimeError, match="cannot open"):
         splitbam.main(["--bam", bam + ".missing", "--meta", meta, "--id", "s", "--outdir", str(tmp_path)])
+
+
+def test_split_streaming_rounds_and_flushes_do_not_change_the_output(tmp_path, built, monkeypatch):
+    """The splitter streams: input in chunks of compressed bytes, outputs deflated whenever enough records are
+    pending.  Tiny chunk sizes force hundreds of rounds, records that straddle rounds and mid-stream flushes; BAMs
+    (record dumps), reports and region queries must not change."""
+    import bai_query
+    import pipeline_inputs as pi
+    from longsom_b200.cli import splitbam
+    bam, meta = pi.write_split_input("g1", str(tmp_path))
+    dumps = {}
+    for tag, env in (("big", {}), ("small", {"LS_SPLIT_READ_CHUNK": "70001", "LS_SPLIT_FLUSH_BYTES": "90000"}),
+                     ("tiny", {"LS_SPLIT_READ_CHUNK": "4096", "LS_SPLIT_FLUSH_BYTES": "4096"})):
+        out = os.path.join(str(tmp_path), tag)
+        os.makedirs(out)
+        for k in ("LS_SPLIT_READ_CHUNK", "LS_SPLIT_FLUSH_BYTES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        splitbam.main(["--bam", bam, "--meta", meta, "--id", "s", "--outdir", out, "--min_MQ", "60", "--n_trim", "5"])
+        dumps[tag] = {fn: pi.dump_bam_records(os.path.join(out, fn)) for fn in sorted(os.listdir(out)) if fn.endswith(".bam")}
+        if tag != "big":
+            assert dumps[tag] == dumps["big"]
+            fn = sorted(dumps[tag])[0]
+            recs = [l.split("\t") for l in dumps[tag][fn][1:]]
+            tid, pos = int(recs[len(recs) // 2][2]), int(recs[len(recs) // 2][3])
+            assert bai_query.query(os.path.join(out, fn), tid, pos, pos + 2000) == \
+                bai_query.query(os.path.join(str(tmp_path), "big", fn), tid, pos, pos + 2000)
+    assert gold("g1", "split.s.Cancer.records.txt") == dumps["big"]["s.Cancer.bam"]
