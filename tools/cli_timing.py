@@ -25,3 +25,10 @@ write_counter_tsv(tmp + "/out.tsv", "x", sites, bd.contig_names); t4 = time.time
 print("decode BAM %.2f s | windows+ref %.2f s | GPU upload+run+fetch %.2f s (device %.1f ms) | TSV %d sites %.2f s | total %.2f s" % (
     t1 - t0, t2 - t1, t3 - t2, stats[0]["ms_total"], sites.n_sites, t4 - t3, t4 - t0))
 print("end-to-end %.3g aligned bases/s from BAM on disk to TSV on disk" % (b.aligned_bases() / (t4 - t0)))
+# the same GPU section again (CUDA context and library already warm), one call and pipelined window shards
+for shards in ("1", "8"):
+    os.environ["LONGSOM_SHARDS_PER_GPU"] = shards
+    ta = time.time()
+    s2 = count_sites(batch, iv, seqs, CountParams(min_bq=20, min_mq=60), [0], [])
+    print("warm GPU section, LONGSOM_SHARDS_PER_GPU=%s: %.2f s (%d sites)" % (shards, time.time() - ta, s2.n_sites))
+    assert s2.n_sites == sites.n_sites and np.array_equal(s2.counts, sites.counts)
