@@ -15,10 +15,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -42,9 +44,13 @@ struct Bam {
   std::vector<int32_t> tid, pos, cb, lq;
   std::vector<uint16_t> flag;
   std::vector<uint8_t> mapq;
-  std::vector<uint32_t> cigar_off, cigar;
+  std::vector<uint32_t> cigar_off;
+  // large payload arrays: allocated uninitialised and first touched by the parallel fill (a value-initialised
+  // std::vector would zero ~3 GB per million long reads on one thread before the copy even starts)
+  std::unique_ptr<uint32_t[]> cigar;
+  std::unique_ptr<uint8_t[]> seq4, qual;
+  size_t n_cigar = 0, n_qual = 0;
   std::vector<uint64_t> base_off;
-  std::vector<uint8_t> seq4, qual;
   std::vector<std::string> barcodes;
   int64_t n_reads = 0;
 };
@@ -52,21 +58,20 @@ struct Bam {
 static inline uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
 
-static bool inflate_block(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
+// zs: a raw-deflate stream the calling thread initialised once (inflateInit2(-15)); reset per member, which
+// saves the ~40 KB state allocation that inflateInit2 / inflateEnd would do for every 64 KB member
+static bool inflate_block(z_stream &zs, const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
   // gzip member: 10-byte header + XLEN extra, deflate stream, CRC32, ISIZE
   if (csize < 18) return false;
   uint32_t xlen = rd16(src + 10);
   const uint8_t *def = src + 12 + xlen;
   uint32_t dlen = csize - 12 - xlen - 8;
-  z_stream zs;
-  memset(&zs, 0, sizeof zs);
-  if (inflateInit2(&zs, -15) != Z_OK) return false;
+  if (inflateReset(&zs) != Z_OK) return false;
   zs.next_in = const_cast<Bytef *>(def);
   zs.avail_in = dlen;
   zs.next_out = dst;
   zs.avail_out = usize;
   int rc = inflate(&zs, Z_FINISH);
-  inflateEnd(&zs);
   return rc == Z_STREAM_END && zs.total_out == usize;
 }
 
@@ -107,8 +112,22 @@ static const char *find_cb(const uint8_t *p, const uint8_t *end) {
 
 extern "C" {
 
+static double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
 void *ls_bam_read(const char *path, int threads) {
   Bam *b = new Bam();
+  const bool timing = getenv("LS_BAM_TIMING") != nullptr;
+  double t_prev = now_s();
+  auto lap = [&](const char *what) {
+    if (!timing) return;
+    const double t = now_s();
+    fprintf(stderr, "[ls_bam_read] %-28s %.3f s\n", what, t - t_prev);
+    t_prev = t;
+  };
   FILE *f = fopen(path, "rb");
   if (!f) {
     b->err = std::string("cannot open ") + path;
@@ -117,18 +136,19 @@ void *ls_bam_read(const char *path, int threads) {
   fseek(f, 0, SEEK_END);
   const uint64_t fsize = (uint64_t)ftell(f);
   fseek(f, 0, SEEK_SET);
-  std::vector<uint8_t> comp(fsize);
-  if (fsize && fread(comp.data(), 1, fsize, f) != fsize) {
+  std::unique_ptr<uint8_t[]> comp(new uint8_t[fsize ? fsize : 1]);
+  if (fsize && fread(comp.get(), 1, fsize, f) != fsize) {
     fclose(f);
     b->err = "short read";
     return b;
   }
   fclose(f);
+  lap("read file");
   // pass 1: BGZF block table
   std::vector<Block> blocks;
   uint64_t off = 0, uoff = 0;
   while (off + 18 <= fsize) {
-    const uint8_t *p = comp.data() + off;
+    const uint8_t *p = comp.get() + off;
     if (p[0] != 0x1f || p[1] != 0x8b || !(p[3] & 4)) {
       b->err = "not a BGZF file (bad gzip member header)";
       return b;
@@ -154,35 +174,44 @@ void *ls_bam_read(const char *path, int threads) {
     uoff += bl.usize;
     off += bsize;
   }
+  lap("member table");
   // pass 2: inflate in parallel
-  std::vector<uint8_t> raw(uoff);
+  std::unique_ptr<uint8_t[]> raw(new uint8_t[uoff ? uoff : 1]);
+  const size_t raw_size = (size_t)uoff;
   if (threads < 1) threads = 1;
   std::atomic<size_t> next(0);
   std::atomic<int> bad(0);
   auto worker = [&]() {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) {
+      bad = 1;
+      return;
+    }
     for (;;) {
       size_t i = next.fetch_add(16);
       if (i >= blocks.size()) break;
       for (size_t j = i; j < i + 16 && j < blocks.size(); ++j) {
         const Block &bl = blocks[j];
-        if (bl.usize && !inflate_block(comp.data() + bl.coff, bl.csize, raw.data() + bl.uoff, bl.usize)) bad = 1;
+        if (bl.usize && !inflate_block(zs, comp.get() + bl.coff, bl.csize, raw.get() + bl.uoff, bl.usize)) bad = 1;
       }
     }
+    inflateEnd(&zs);
   };
   {
     std::vector<std::thread> th;
     for (int t = 0; t < threads; ++t) th.emplace_back(worker);
     for (auto &t : th) t.join();
   }
-  comp.clear();
-  comp.shrink_to_fit();
+  lap("alloc + inflate");
+  comp.reset();
   if (bad) {
     b->err = "inflate failed";
     return b;
   }
   // header
-  const uint8_t *p = raw.data(), *end = raw.data() + raw.size();
-  if (raw.size() < 12 || memcmp(p, "BAM\1", 4) != 0) {
+  const uint8_t *p = raw.get(), *end = raw.get() + raw_size;
+  if (raw_size < 12 || memcmp(p, "BAM\1", 4) != 0) {
     b->err = "bad BAM magic";
     return b;
   }
@@ -208,6 +237,7 @@ void *ls_bam_read(const char *path, int threads) {
     recs.push_back(p + 4);
     p += 4 + bs;
   }
+  lap("record offsets");
   const int64_t n = (int64_t)recs.size();
   b->n_reads = n;
   b->tid.resize(n);
@@ -253,11 +283,15 @@ void *ls_bam_read(const char *path, int threads) {
       }
     }
   }
+  lap("fixed fields + barcodes");
   b->cigar_off[n] = co;
   b->base_off[n] = bo;
-  b->cigar.resize(co);
-  b->seq4.assign(bo / 2, 0);
-  b->qual.assign(bo, 0);
+  b->n_cigar = co;
+  b->n_qual = (size_t)bo;
+  b->cigar.reset(new uint32_t[co ? co : 1]);
+  b->seq4.reset(new uint8_t[bo / 2 ? bo / 2 : 1]);
+  b->qual.reset(new uint8_t[bo ? bo : 1]);
+  lap("alloc seq/qual");
   // pass 5: fill cigar / seq / qual in parallel
   std::atomic<int64_t> nx(0);
   auto filler = [&]() {
@@ -270,10 +304,14 @@ void *ls_bam_read(const char *path, int threads) {
         const uint32_t n_cig = rd16(r + 12);
         const uint32_t l_seq = rd32(r + 16);
         const uint8_t *cg = r + 32 + l_name;
-        memcpy(b->cigar.data() + b->cigar_off[i], cg, 4 * (size_t)n_cig);
+        memcpy(b->cigar.get() + b->cigar_off[i], cg, 4 * (size_t)n_cig);
         const uint8_t *sq = cg + 4 * n_cig;
-        memcpy(b->seq4.data() + b->base_off[i] / 2, sq, (l_seq + 1) / 2);
-        memcpy(b->qual.data() + b->base_off[i], sq + (l_seq + 1) / 2, l_seq);
+        const uint64_t bo_i = b->base_off[i], pad = b->base_off[i + 1] - bo_i;  // padded to a multiple of 16 bases
+        const uint32_t sb = (l_seq + 1) / 2;
+        memcpy(b->seq4.get() + bo_i / 2, sq, sb);
+        memset(b->seq4.get() + bo_i / 2 + sb, 0, (size_t)(pad / 2 - sb));
+        memcpy(b->qual.get() + bo_i, sq + sb, l_seq);
+        memset(b->qual.get() + bo_i + l_seq, 0, (size_t)(pad - l_seq));
       }
     }
   };
@@ -282,14 +320,15 @@ void *ls_bam_read(const char *path, int threads) {
     for (int t = 0; t < threads; ++t) th.emplace_back(filler);
     for (auto &t : th) t.join();
   }
+  lap("fill cigar/seq/qual");
   return b;
 }
 
 const char *ls_bam_error(void *h) { Bam *b = (Bam *)h; return b->err.empty() ? nullptr : b->err.c_str(); }
 void ls_bam_free(void *h) { delete (Bam *)h; }
 int64_t ls_bam_n_reads(void *h) { return ((Bam *)h)->n_reads; }
-int64_t ls_bam_n_cigar(void *h) { return (int64_t)((Bam *)h)->cigar.size(); }
-int64_t ls_bam_n_bases(void *h) { return (int64_t)((Bam *)h)->qual.size(); }
+int64_t ls_bam_n_cigar(void *h) { return (int64_t)((Bam *)h)->n_cigar; }
+int64_t ls_bam_n_bases(void *h) { return (int64_t)((Bam *)h)->n_qual; }
 int32_t ls_bam_n_contigs(void *h) { return (int32_t)((Bam *)h)->contig_names.size(); }
 const char *ls_bam_contig_name(void *h, int i) { return ((Bam *)h)->contig_names[i].c_str(); }
 int32_t ls_bam_contig_len(void *h, int i) { return ((Bam *)h)->contig_lens[i]; }
@@ -306,11 +345,11 @@ const void *ls_bam_array(void *h, int which) {
     case 3: return b->mapq.data();
     case 4: return b->cb.data();
     case 5: return b->cigar_off.data();
-    case 6: return b->cigar.data();
+    case 6: return b->cigar.get();
     case 7: return b->base_off.data();
     case 8: return b->lq.data();
-    case 9: return b->seq4.data();
-    case 10: return b->qual.data();
+    case 9: return b->seq4.get();
+    case 10: return b->qual.get();
   }
   return nullptr;
 }
