@@ -100,3 +100,26 @@ def test_host_sf_matches_scipy(cephes):
         ref = betabinom.sf(k - 0.1, n, a, b)
         assert np.max(np.abs(p - ref)) < 1e-14
         assert np.array_equal(np.round(p, 4), np.round(ref, 4))
+
+
+def test_decoded_arrays_outlive_the_bam_object(built, tmp_path):
+    """read_bam returns views into the native decoder's buffers: they must stay valid (and writable) after the
+    BamData object is gone, and round-trip what write_bam wrote."""
+    import gc
+    import numpy as np
+    from longsom_b200 import bamio, synth
+    d = synth.generate(seed=3, contig_lens=[60000], n_genes=4, n_reads=400, n_cells=10)
+    path = os.path.join(str(tmp_path), "x.bam")
+    bamio.write_bam(path, d.contig_names, d.contig_lens, d.batch, lambda i: None if d.batch.cell[i] < 0 else "BC%d-1" % d.batch.cell[i])
+    bd = bamio.read_bam(path, threads=3)
+    b = bd.batch
+    del bd
+    gc.collect()
+    for f in ("tid", "pos", "flag", "mapq", "cigar_off", "cigar", "l_qseq"):
+        assert np.array_equal(getattr(b, f), getattr(d.batch, f)), f
+    lq, bo, bo0 = b.l_qseq.astype(np.int64), b.base_off.astype(np.int64), d.batch.base_off.astype(np.int64)
+    for i in (0, 1, b.n_reads // 2, b.n_reads - 1):
+        assert np.array_equal(b.qual[bo[i]:bo[i] + lq[i]], d.batch.qual[bo0[i]:bo0[i] + lq[i]])
+        assert not b.qual[bo[i] + lq[i]:bo[i + 1]].any()          # padding to 16 bases is zeroed
+    b.qual[0] = 7   # writable view
+    assert b.qual[0] == 7
