@@ -39,6 +39,41 @@ def devices_from_env():
     return list(range(n)) if n > 0 else [0]
 
 
+# ---- CUDA context pre-warm ---------------------------------------------------------------------------------
+# Creating a CUDA context on a 180 GB device takes about a second or more; the CLIs start it in a background
+# thread before they decode the BAM (the native decoder releases the GIL), so the two overlap.
+_WARM = {}
+_WARM_LOCK = threading.Lock()
+
+
+def prewarm(devices):
+    """Start creating one Engine (CUDA context + stream) per device in the background."""
+    def make(dev, box):
+        try:
+            box["engine"] = Engine(dev)
+        except Exception as e:  # surfaced by take_engine
+            box["error"] = e
+    for dev in devices:
+        box = {}
+        t = threading.Thread(target=make, args=(dev, box), daemon=True)
+        with _WARM_LOCK:
+            _WARM.setdefault(dev, []).append((t, box))
+        t.start()
+
+
+def take_engine(dev):
+    """An Engine for dev: the pre-warmed one if prewarm() was called, else a new one.  The caller closes it."""
+    with _WARM_LOCK:
+        entry = _WARM[dev].pop() if _WARM.get(dev) else None
+    if entry is None:
+        return Engine(dev)
+    t, box = entry
+    t.join()
+    if "error" in box:
+        raise box["error"]
+    return box["engine"]
+
+
 def read_ends(batch: ReadBatch):
     """Exclusive reference end of every read (pos + M/D/N/=/X lengths)."""
     if batch.n_reads == 0:
@@ -127,7 +162,7 @@ def count_sites(batch, windows_iv, contig_seq, params: CountParams, devices=None
             else:
                 sub = batch
             win = Windows.from_intervals(sub_iv, contig_seq)
-            with Engine(dev) as eng:
+            with take_engine(dev) as eng:
                 results[k] = eng.pileup_count(sub, win, params)
                 if stats_out is not None:
                     stats_out.append(dict(device=dev, **eng.last_stats))
@@ -176,7 +211,7 @@ def count_shards_pipelined(shards, params: CountParams, outs, device=0, lanes=2,
     outs[i] (preallocated, e.g. pinned) receives shard i's sites and the per-shard site counts are returned; with
     outs=None each shard's SiteCounts is allocated after its run and the list of SiteCounts is returned."""
     own = engines is None
-    engines = engines or [Engine(device) for _ in range(max(1, lanes))]
+    engines = engines or [take_engine(device) for _ in range(max(1, lanes))]
     n_sites = [0] * len(shards)
     errors = []
 

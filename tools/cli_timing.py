@@ -12,10 +12,10 @@ bamio.write_fasta(tmp + "/ref.fa", d.contig_names, [d.contig_seq(i) for i in ran
 names = [synth.barcode_of(c) + "-1" for c in range(d.n_cells + d.n_extra_cells)]
 bamio.write_bam(tmp + "/x.bam", d.contig_names, d.contig_lens, b, lambda i: None if b.cell[i] < 0 else names[b.cell[i]])
 print("reads %d, aligned bases %d, BAM %.1f MB (written in %.1f s)" % (b.n_reads, b.aligned_bases(), os.path.getsize(tmp + "/x.bam") / 1e6, time.time() - t))
-from longsom_b200.pipeline import load_bam_for_counting, prune_and_sort_windows, read_ends, count_sites, write_counter_tsv
+from longsom_b200.pipeline import load_bam_for_counting, prune_and_sort_windows, read_ends, count_sites, write_counter_tsv, prewarm
 from longsom_b200.windows import make_windows
 from longsom_b200.engine import CountParams
-t0 = time.time(); fa = bamio.Fasta(tmp + "/ref.fa"); bd, batch, _ = load_bam_for_counting(tmp + "/x.bam"); t1 = time.time()
+t0 = time.time(); prewarm([0]); fa = bamio.Fasta(tmp + "/ref.fa"); bd, batch, _ = load_bam_for_counting(tmp + "/x.bam"); t1 = time.time()
 named = make_windows(fa.references, fa.lengths, "all", 50000)
 iv = prune_and_sort_windows(named, bd.contig_names, batch, read_ends(batch))
 seqs = {t_: fa.contig(bd.contig_names[t_]) for t_ in sorted({w[0] for w in iv})}; t2 = time.time()
