@@ -14,6 +14,7 @@ import math
 import os
 import re
 import sys
+import threading
 import timeit
 
 import numpy as np
@@ -72,6 +73,16 @@ def genotype(args, hccv):
     bins = build_dict_variants(args.infile, args.bin)
 
     # ---- candidate sites of every bin -------------------------------------------------------------
+    # the CUDA context comes up in the background while the BAM is decoded (the native decoder releases the GIL)
+    warm = {}
+
+    def _make_engine():
+        try:
+            warm["engine"] = Engine(devices_from_env()[0])
+        except Exception as e:
+            warm["error"] = e
+    warm_thread = threading.Thread(target=_make_engine, daemon=True)
+    warm_thread.start()
     bam = bamio.read_bam(args.bam)
     tid_of = {n: i for i, n in enumerate(bam.contig_names)}
     bin_info = []  # (chrom, Target_sites dict in file order)
@@ -100,7 +111,10 @@ def genotype(args, hccv):
         raw_to_cell = np.array([bc_index.get(b.split("-")[0], -1) for b in bam.barcodes], np.int32)
     batch = bam.with_cells(raw_to_cell) if len(bam.barcodes) else bam.batch
     n_cells = len(barcodes)
-    with Engine(devices_from_env()[0]) as eng:
+    warm_thread.join()
+    if "error" in warm:
+        raise warm["error"]
+    with warm["engine"] as eng:
         eng.upload(batch, None)
         dp, alt = eng.genotype_count(site_tid, site_pos, alt_cls, n_cells, min_bq=args.min_bq, min_mq=args.min_mq,
                                      max_depth=200000, alt_only=(args.alt_flag != 'All'), bin_size=args.bin)
