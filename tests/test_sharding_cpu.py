@@ -115,3 +115,29 @@ def test_window_shards_are_slices_and_reproduce_the_whole(built):
     assert np.array_equal(np.concatenate([x.pos for x in parts]), full.pos)
     assert np.array_equal(np.concatenate([x.counts for x in parts]), full.counts)
     assert window_shards(d.batch, w, 1)[0][0] is d.batch
+
+
+def test_prewarm_hands_out_background_engines(monkeypatch):
+    """pipeline.prewarm / take_engine: engines are built in background threads, handed out once, errors surface."""
+    import threading
+    import time
+    from longsom_b200 import pipeline
+    made = []
+
+    class FakeEngine:
+        def __init__(self, dev):
+            time.sleep(0.05)
+            if dev == 7:
+                raise RuntimeError("no such device")
+            self.dev, self.thread = dev, threading.current_thread().name
+            made.append(self)
+    monkeypatch.setattr(pipeline, "Engine", FakeEngine)
+    pipeline.prewarm([0, 1])
+    a, b = pipeline.take_engine(0), pipeline.take_engine(1)
+    assert (a.dev, b.dev) == (0, 1) and a.thread != threading.current_thread().name
+    c = pipeline.take_engine(0)          # pool empty: built on demand, in the caller's thread
+    assert c is not a and c.thread == threading.current_thread().name
+    pipeline.prewarm([7])
+    with pytest.raises(RuntimeError, match="no such device"):
+        pipeline.take_engine(7)
+    assert len(made) == 3
