@@ -28,6 +28,9 @@ CASES = [
     dict(seed=4, contig_lens=[100000], n_genes=5, n_reads=300, n_cells=20),
     # indel every ~25 bases: dozens of CIGAR pieces per (read, tile) segment (piece-queue overflow path)
     dict(seed=7, contig_lens=[100000], n_genes=5, n_reads=3000, n_cells=30, p_ins=0.02, p_del=0.02),
+    # ~6 kb reads: > 5 (read, tile) segments per read, so the segment builder's first-run size estimate is too
+    # small and the exact-size relaunch path runs
+    dict(seed=8, contig_lens=[500000], n_genes=8, n_reads=2500, n_cells=40, mean_len=6000.0),
 ]
 
 
