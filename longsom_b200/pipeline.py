@@ -121,62 +121,32 @@ def prune_and_sort_windows(named_windows, bam_names, batch, ends):
 
 
 def count_sites(batch, windows_iv, contig_seq, params: CountParams, devices=None, stats_out=None):
-    """Pileup counts for windows_iv = [(tid, start, end)] (sorted, disjoint).  One Engine per device,
-    windows sharded by aligned-base weight; results concatenated in window order."""
+    """Pileup counts for windows_iv = [(tid, start, end)] (sorted, disjoint).  The windows are cut into
+    coverage-balanced shards (array slices of the batch, no copies): one per device, or
+    LONGSOM_SHARDS_PER_GPU per device, in which case each device runs two CUDA contexts so that uploads, kernels
+    and result copies of its shards overlap.  Results are concatenated in window order."""
     devices = devices or [0]
     if not windows_iv:
         return SiteCounts.empty(0)
-    per_gpu = int(os.environ.get("LONGSOM_SHARDS_PER_GPU", "1") or 1)
-    if len(devices) == 1 and per_gpu > 1:
-        # one GPU, large input: window shards on two CUDA contexts so that uploads, kernels and result copies overlap
-        win = Windows.from_intervals(windows_iv, contig_seq)
-        res = count_shards_pipelined(window_shards(batch, win, per_gpu), params, None, device=devices[0], lanes=2)
-        return SiteCounts(np.concatenate([r.tid for r in res]), np.concatenate([r.pos for r in res]),
-                          np.concatenate([r.ref for r in res]), np.concatenate([r.counts for r in res], axis=0))
-    ends = read_ends(batch)
-    if len(devices) == 1:
-        shards = [(0, len(windows_iv))]
-    else:
-        wk_hi = np.array([(t << 32) | e for t, s, e in windows_iv], np.int64)
-        rk = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
-        idx = np.minimum(np.searchsorted(wk_hi, rk, side="right"), len(windows_iv) - 1)
-        w = np.zeros(len(windows_iv))
-        np.add.at(w, idx, batch.l_qseq.astype(np.float64))
-        shards = balanced_window_shards(w, len(devices))
-    results = [None] * len(shards)
-    errors = []
-
-    def work(k, dev, lo, hi):
-        try:
-            if hi <= lo:
-                results[k] = SiteCounts.empty(0)
-                return
-            sub_iv = windows_iv[lo:hi]
-            if len(shards) > 1:
-                lo_key = (sub_iv[0][0] << 32) | sub_iv[0][1]
-                hi_key = (sub_iv[-1][0] << 32) | sub_iv[-1][2]
-                rk_lo = (batch.tid.astype(np.int64) << 32) | batch.pos.astype(np.int64)
-                rk_hi = (batch.tid.astype(np.int64) << 32) | np.maximum(ends, batch.pos.astype(np.int64) + 1)
-                sel = np.nonzero((rk_lo < hi_key) & (rk_hi > lo_key))[0]
-                sub = batch.select(sel)
-            else:
-                sub = batch
-            win = Windows.from_intervals(sub_iv, contig_seq)
-            with take_engine(dev) as eng:
-                results[k] = eng.pileup_count(sub, win, params)
-                if stats_out is not None:
-                    stats_out.append(dict(device=dev, **eng.last_stats))
-        except Exception as e:  # surfaced below: the reference silently drops failed windows, we do not
-            errors.append(e)
-    threads = [threading.Thread(target=work, args=(k, devices[k], lo, hi)) for k, (lo, hi) in enumerate(shards)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
-    if errors:
-        raise errors[0]
-    return SiteCounts(np.concatenate([r.tid for r in results]), np.concatenate([r.pos for r in results]),
-                      np.concatenate([r.ref for r in results]), np.concatenate([r.counts for r in results], axis=0))
+    per_gpu = max(1, int(os.environ.get("LONGSOM_SHARDS_PER_GPU", "1") or 1))
+    win = Windows.from_intervals(windows_iv, contig_seq)
+    if len(devices) == 1 and per_gpu == 1:
+        with take_engine(devices[0]) as eng:
+            res = eng.pileup_count(batch, win, params)
+            if stats_out is not None:
+                stats_out.append(dict(device=devices[0], **eng.last_stats))
+        return res
+    lanes = 2 if per_gpu > 1 else 1
+    engines = [take_engine(dev) for dev in devices for _ in range(lanes)]
+    try:
+        res = count_shards_pipelined(window_shards(batch, win, len(devices) * per_gpu), params, None, engines=engines)
+        if stats_out is not None:
+            stats_out.extend(dict(device=e.device, **(e.last_stats or {})) for e in engines)
+    finally:
+        for e in engines:
+            e.close()
+    return SiteCounts(np.concatenate([r.tid for r in res]), np.concatenate([r.pos for r in res]),
+                      np.concatenate([r.ref for r in res]), np.concatenate([r.counts for r in res], axis=0))
 
 
 def window_shards(batch: ReadBatch, windows: Windows, n_shards):
@@ -205,9 +175,11 @@ def window_shards(batch: ReadBatch, windows: Windows, n_shards):
 
 
 def count_shards_pipelined(shards, params: CountParams, outs, device=0, lanes=2, engines=None):
-    """Runs ls_pileup_count() on every (batch, windows) shard with `lanes` CUDA contexts on ONE device, each in
-    its own host thread: while one lane computes or copies results back, another uploads its next shard, so the
-    PCIe transfers of a job overlap with each other (H2D / D2H are separate engines) and with the kernels.
+    """Runs ls_pileup_count() on every (batch, windows) shard, shard i on engine i mod len(engines), each engine
+    (CUDA context; by default `lanes` of them on ONE device) in its own host thread: while one computes or copies
+    results back, another uploads its next shard, so the PCIe transfers of a job overlap with each other (H2D /
+    D2H are separate engines) and with the kernels.  With engines on several devices the same loop is the
+    multi-GPU path.
     outs[i] (preallocated, e.g. pinned) receives shard i's sites and the per-shard site counts are returned; with
     outs=None each shard's SiteCounts is allocated after its run and the list of SiteCounts is returned."""
     own = engines is None
