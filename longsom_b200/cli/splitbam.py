@@ -7,8 +7,8 @@ module mirrors the reference's CLI, its barcode-table handling (meta_to_dict, :1
 
 Output BAMs hold the same records, byte for byte (qualities of trimmed ends zeroed), in the same
 order as the reference's; the compressed bytes differ because members are deflated in parallel
-(zlib level 6 like htslib's default; LONGSOM_BAM_LEVEL=1 trades ~30 % larger files for about a third less time:
-1 M long reads / 394 MB in 12.9 s at level 6, 8.5 s at level 1 on 8 cores)."""
+(zlib level 6 like htslib's default; LONGSOM_BAM_LEVEL=1 trades ~30 % larger files for less CPU time:
+1 M long reads / 394 MB in about 11 s at level 6 on 8 cores, deflate-bound)."""
 import argparse
 import ctypes as C
 import os

@@ -13,9 +13,10 @@
 //   * the record is appended, otherwise byte for byte, to the BAM of its cell type; outputs get the
 //     input's header, a BGZF EOF marker and a .bai index.
 // Streaming: the input is read in ~64 MB compressed chunks whose BGZF members are inflated in parallel;
-// each output keeps at most a few MB of pending records, deflates full 0xff00-byte members in parallel
-// and appends them to its file; the .bai is accumulated on uncompressed offsets and translated to
-// virtual offsets at the end.  Memory is bounded by the chunk sizes, not by the BAM.
+// each output keeps at most a few MB of pending records and hands full 0xff00-byte members to a background
+// stage that deflates them in parallel and appends them to its file while the next input chunk is inflated
+// and routed; the .bai is accumulated on uncompressed offsets and translated to virtual offsets at the end.
+// Memory is bounded by the chunk sizes, not by the BAM.
 // Differences by construction: members are deflated in parallel (so the compressed bytes differ from
 // htslib's, the records do not).
 #include <stdint.h>
@@ -23,7 +24,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -206,26 +210,93 @@ struct OutStream {
 
   uint64_t tell() const { return flushed + pending.size(); }
 
-  bool flush(bool final, int threads, int level, std::string &err) {
+  // Router side: cut the deflatable prefix off `pending` (everything when final) and account for it; the bytes
+  // are handed to the background writer, which is the only thread that touches f / c_total / coff.
+  bool take(bool final, std::vector<uint8_t> &chunk) {
     const size_t nbytes = final ? pending.size() : (pending.size() / kBlockPayload) * kBlockPayload;
-    if (nbytes) {
+    chunk.assign(pending.begin(), pending.begin() + (ptrdiff_t)nbytes);
+    flushed += nbytes;
+    pending.erase(pending.begin(), pending.begin() + (ptrdiff_t)nbytes);
+    return nbytes != 0 || final;
+  }
+
+  // Writer side.
+  bool write_chunk(const std::vector<uint8_t> &chunk, bool final, int threads, int level, std::string &err) {
+    if (!chunk.empty()) {
       std::vector<uint8_t> comp;
       std::vector<uint64_t> rel;
-      if (!deflate_stream(pending.data(), nbytes, threads, level, comp, rel, err)) return false;
+      if (!deflate_stream(chunk.data(), chunk.size(), threads, level, comp, rel, err)) return false;
       for (size_t i = 0; i + 1 < rel.size(); ++i) coff.push_back(c_total + rel[i]);
       if (fwrite(comp.data(), 1, comp.size(), f) != comp.size()) {
         err = "short write to " + path;
         return false;
       }
       c_total += comp.size();
-      flushed += nbytes;
-      pending.erase(pending.begin(), pending.begin() + (ptrdiff_t)nbytes);
     }
     if (final) coff.push_back(c_total);  // virtual offset of the end of the stream = start of the EOF member
     return true;
   }
 
   uint64_t voff(uint64_t u) const { return (coff[u / kBlockPayload] << 16) | (u % kBlockPayload); }
+};
+
+// Background stage: deflates and appends the chunks the router hands over, in order, while the router goes on
+// inflating and routing the next input.  Bounded queue (a few chunks) keeps memory bounded.
+struct WriterStage {
+  struct Job {
+    int out;
+    bool final;
+    std::vector<uint8_t> data;
+  };
+  std::vector<OutStream> *outs = nullptr;
+  int threads = 1, level = 6;
+  std::deque<Job> q;
+  std::mutex mu;
+  std::condition_variable cv_push, cv_pop;
+  bool stop = false;
+  std::string err;
+  std::thread th;
+  static constexpr size_t kMaxJobs = 4;
+
+  void start() {
+    th = std::thread([this]() {
+      for (;;) {
+        Job j;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv_pop.wait(lk, [this]() { return stop || !q.empty(); });
+          if (q.empty()) return;
+          j = std::move(q.front());
+          q.pop_front();
+        }
+        cv_push.notify_one();
+        std::string e;
+        if (err.empty() && !(*outs)[(size_t)j.out].write_chunk(j.data, j.final, threads, level, e)) {
+          std::lock_guard<std::mutex> lk(mu);
+          err = e;
+        }
+      }
+    });
+  }
+  // false when the writer has already failed (message in err)
+  bool push(int out, bool final, std::vector<uint8_t> &&data) {
+    std::unique_lock<std::mutex> lk(mu);
+    cv_push.wait(lk, [this]() { return q.size() < kMaxJobs; });
+    if (!err.empty()) return false;
+    q.push_back(Job{out, final, std::move(data)});
+    lk.unlock();
+    cv_pop.notify_one();
+    return true;
+  }
+  void finish() {
+    if (!th.joinable()) return;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv_pop.notify_one();
+    th.join();
+  }
 };
 
 static bool write_whole(const std::string &path, const std::vector<uint8_t> &a, std::string &err) {
@@ -341,7 +412,9 @@ int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths,
   std::string e;
   std::vector<OutStream> outs;
   BgzfChunkReader rd;
+  WriterStage writer;
   auto fail = [&](const std::string &m) {
+    writer.finish();
     snprintf(err, (size_t)errlen, "%s", m.c_str());
     for (auto &o : outs)
       if (o.f) fclose(o.f);
@@ -405,6 +478,10 @@ int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths,
         if (!outs.back().f) return fail(std::string("cannot create ") + out_paths[t]);
         outs.back().pending.assign(p, p + hl);
       }
+      writer.outs = &outs;
+      writer.threads = threads;
+      writer.level = level;
+      writer.start();
       header_done = true;
       p += hl;
     }
@@ -491,7 +568,10 @@ int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths,
       }
       const bool mapped = !(flag & 4u);
       o.bai.add(tid, pos, (int32_t)(pos + ((mapped && span > 0) ? span : 1)), u0, o.tell(), mapped);
-      if (o.pending.size() >= kFlushBytes && !o.flush(false, threads, level, e)) return fail(e);
+      if (o.pending.size() >= kFlushBytes) {
+        std::vector<uint8_t> chunk;
+        if (o.take(false, chunk) && !writer.push(it->second, false, std::move(chunk))) return fail(writer.err);
+      }
     }
     // keep the incomplete tail for the next round
     const size_t left = (size_t)(end - p);
@@ -507,8 +587,14 @@ int ls_bam_split(const char *in_path, int n_types, const char *const *out_paths,
   fclose(rd.f);
   rd.f = nullptr;
 
+  for (size_t t = 0; t < outs.size(); ++t) {
+    std::vector<uint8_t> chunk;
+    outs[t].take(true, chunk);
+    if (!writer.push((int)t, true, std::move(chunk))) return fail(writer.err);
+  }
+  writer.finish();
+  if (!writer.err.empty()) return fail(writer.err);
   for (auto &o : outs) {
-    if (!o.flush(true, threads, level, e)) return fail(e);
     bool ok = fwrite(kEofBlock, 1, sizeof kEofBlock, o.f) == sizeof kEofBlock;
     ok = (fclose(o.f) == 0) && ok;
     o.f = nullptr;
