@@ -5,8 +5,11 @@ betabinom.sf 2-12 times (~100 us each, :196,201,329-330).  Here the table is par
 (k, n) query of the run is gathered into two arrays (read counts with alpha1/beta1, cell counts
 with alpha2/beta2), the tails are computed in two GPU launches (K2, ls_betabinom_sf), and the
 label cascade is applied on the rounded p-values exactly as the
-reference does.  Output bytes are identical, including its quirks (Q5-Q8)."""
+reference does.  Output bytes are identical, including its quirks (Q5-Q8).  The per-row Python of the two passes
+is what this step costs, so tables above 8 MB are cut into byte ranges handled by forked worker processes
+(LONGSOM_PROCS, default min(16, cores)); the GPU calls stay in the parent."""
 import argparse
+import os
 import sys
 import timeit
 
@@ -72,28 +75,22 @@ def _fisher_p(cand, bcf, REF):
     return "|".join(str(round(stats.fisher_exact([[Fw[x], Fw[x]], [Fw[REF], Fw[REF]]])[1], 4)) for x in cand)
 
 
-def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, min_ac_cells, min_ac_reads, min_cells,
-                          min_reads, min_cell_types, max_cell_types, fisher_cutoff, engine):
-    fa = bamio.Fasta(fasta) if fasta is not None else None
-    out_lines = []          # header lines written verbatim
-    rows = []               # per data row: dict with parsed pieces
-    q1k, q1n, q2k, q2n = [], [], [], []  # K2 queries: (bc, DP | alpha1,beta1) and (cc, NC | alpha2,beta2)
-    cell_types_idx = None
-    seen_header = False
-    with open(infile) as f:
-        for line in f:
-            if line.startswith('##'):
-                out_lines.append(line)
-                continue
-            if line.startswith('#CHROM') and not seen_header:
-                seen_header = True
-                elements = line.rstrip('\n').split('\t')
-                cell_types_idx = {x: elements[x] for x in range(len(elements)) if x > 4}
-                for _, text in INFO_HEADER:
-                    out_lines.append(text + '\n')
-                elements.insert(4, "\t".join(k for k, _ in INFO_HEADER))
-                out_lines.append('\t'.join(elements) + '\n')
-                continue
+class _Params:
+    """The thresholds both passes need (picklable: the worker processes receive one)."""
+
+    def __init__(self, min_ac_cells, min_ac_reads, min_cells, min_reads, min_cell_types, max_cell_types, fisher_cutoff):
+        self.min_ac_cells, self.min_ac_reads, self.min_cells, self.min_reads = min_ac_cells, min_ac_reads, min_cells, min_reads
+        self.min_cell_types, self.max_cell_types, self.fisher_cutoff = min_cell_types, max_cell_types, fisher_cutoff
+
+
+def _parse_rows(lines, cell_types_idx, fa, P):
+    """Pass 1 over data lines: per row the parsed pieces, plus the beta-binomial queries of the rows
+    (q1: read counts with alpha1/beta1, q2: cell counts with alpha2/beta2); row indices into the query arrays are
+    relative to this call."""
+    min_reads, min_cells = P.min_reads, P.min_cells
+    rows = []
+    q1k, q1n, q2k, q2n = [], [], [], []
+    for line in lines:
             elements = line.rstrip('\n').split('\t')
             CHROM, POS, REF = str(elements[0]), int(elements[1]), elements[3]
             up_context = down_context = '.'
@@ -153,98 +150,243 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
                 q2k.append(Sum_alts_cc)
                 q2n.append(Sum_nc)
             rows.append(row)
+    return rows, (np.array(q1k, np.int32), np.array(q1n, np.int32), np.array(q2k, np.int32), np.array(q2n, np.int32))
 
-    # ---- all beta-binomial tails of the run: two GPU launches ----------------------------------
-    p1 = engine.betabinom_sf(np.array(q1k, np.int32), np.array(q1n, np.int32), alpha1, beta1)
-    p2 = engine.betabinom_sf(np.array(q2k, np.int32), np.array(q2n, np.int32), alpha2, beta2)
-    r1 = np.round(p1, 4)  # == round(np.float64, 4) of the reference, element-wise
-    r2 = np.round(p2, 4)
 
+def _format_rows(rows, r1, r2, P):
+    """Pass 2: the label cascade on the rounded p-values (r1 / r2 hold the tails of THESE rows' queries) and the
+    output lines."""
+    min_ac_cells, min_ac_reads, min_cell_types = P.min_ac_cells, P.min_ac_reads, P.min_cell_types
+    max_cell_types, fisher_cutoff = P.max_cell_types, P.fisher_cutoff
+    lines = []
+    for row in rows:
+        elements, calls = row["elements"], row["calls"]
+        Sum_alts_bc, Sum_alts_cc, Sum_dp, Sum_nc = row["sums"]
+        if row["rest"] is not None:
+            BC_noise_p, CC_noise_p = r1[row["rest"][0]], r2[row["rest"][1]]
+        else:
+            BC_noise_p, CC_noise_p = 1, 1  # plain ints, printed as '1' (:334-335)
+        rest_BC = ";".join([str(Sum_alts_bc), str(Sum_dp), str(BC_noise_p)])
+        rest_CC = ";".join([str(Sum_alts_cc), str(Sum_nc), str(CC_noise_p)])
+        n_qual = str(row["n_qual"])
+        if calls:
+            Alts, Cell_types, DPs, NCs, BCs, CCs, BCp, CCp, VAF, MCF, Filter, Fisher_p = ([] for _ in range(12))
+            for t in calls:
+                cand = t.cand
+                Alts.append("|".join(cand))
+                Cell_types.append(t.cell_type)
+                DPs.append(str(t.DP))
+                NCs.append(str(t.NC))
+                P_BC = [r1[i] for i in t.q_bc.values()]
+                P_CC = [r2[i] for i in t.q_cc.values()]
+                fisher_p = None
+                if fisher_cutoff != 1:
+                    fisher_p = _fisher_p(cand, t.bcf, t.REF)
+                    Fisher_p.append(fisher_p)
+                b = "|".join(str(t.bc[x]) for x in cand)
+                c = "|".join(str(t.cc[x]) for x in cand)
+                BCs.append(b)
+                CCs.append(c)
+                BCp.append("|".join(str(r1[t.q_bc[x]]) for x in cand))
+                CCp.append("|".join(str(r2[t.q_cc[x]]) for x in cand))
+                VAF.append("|".join(str(round(t.bc[x] / float(t.DP), 4)) for x in cand))
+                MCF.append("|".join(str(round(t.cc[x] / float(t.NC), 4)) for x in cand))
+                mb, mc = min(P_BC), min(P_CC)
+                if mb >= 0.05 or mc >= 0.05:
+                    Filter.append('Non-Significant')
+                elif 0.001 < mb < 0.05 or 0.001 < mc < 0.05:
+                    Filter.append('Low-Significance')
+                elif len(cand) > 1:
+                    Filter.append('Multi-allelic')
+                elif int(c) < min_ac_cells:
+                    Filter.append('Low_cells')
+                elif int(b) < min_ac_reads:
+                    Filter.append('Low_reads')
+                elif fisher_cutoff != 1:
+                    if float(fisher_p) < fisher_cutoff:  # may append nothing (Q8)
+                        Filter.append('Fisher')
+                else:
+                    Filter.append('PASS')
+            FILTER = []
+            n_pass = sum(1 for x in Filter if x == 'PASS')
+            n_nonsig = sum(1 for x in Filter if x == 'Non-Significant')
+            if n_pass > max_cell_types:
+                FILTER.append('Multiple_cell_types')
+            LEN_Alts = len(set(Alts))
+            if LEN_Alts > 1 or 'Multi-allelic' in Filter:
+                FILTER.append('Multi-allelic')
+            if row["n_qual"] < min_cell_types:
+                FILTER.append('Min_cell_types')
+            if len(Filter) - n_pass - n_nonsig > 0:
+                FILTER.append('Cell_type_noise')
+            if BC_noise_p < 0.05 or CC_noise_p < 0.05:
+                FILTER.append('Noisy_site')
+            if homopolymer(row["up"], Alts, True) == 1:
+                FILTER.append("LC_Upstream")
+            if homopolymer(row["down"], Alts, False) == 1:
+                FILTER.append("LC_Downstream")
+            if len(FILTER) == 0:
+                FILTER = 'PASS' if 'PASS' in Filter else ",".join(Filter)
+            else:
+                FILTER = ",".join(FILTER)
+            INFO = [",".join(Alts), FILTER, ",".join(Cell_types), row["up"], row["down"], str(LEN_Alts), ",".join(DPs),
+                    ",".join(NCs), ",".join(BCs), ",".join(CCs), ",".join(VAF), ",".join(MCF), ",".join(BCp),
+                    ",".join(CCp), n_qual, n_qual, rest_BC, rest_CC,
+                    ",".join(Fisher_p) if fisher_cutoff != 1 else '.', ",".join(Filter)]
+        else:
+            FILTER = 'Noisy_site' if (BC_noise_p < 0.001 or CC_noise_p < 0.001) else '.'
+            INFO = [".", FILTER, ".", row["up"], row["down"], ".", ".", ".", ".", ".", ".", ".", ".", ".", n_qual, n_qual,
+                    rest_BC, rest_CC, '.', '.']
+        elements.insert(4, "\t".join(INFO))
+        lines.append('\t'.join(elements) + '\n')
+    return lines
+
+
+# ---- worker processes: the per-row Python of both passes is the cost of this step (tens of microseconds per row, the
+# GPU tails are milliseconds), so large tables are cut into byte ranges handled by forked workers; each parses its
+# range, sends its queries, receives its tails, formats its lines.  The order of the output is the order of the ranges.
+def _worker(conn, infile, lo, hi, cell_types_idx, fasta, P):
+    try:
+        fa = bamio.Fasta(fasta) if fasta is not None else None
+        with open(infile, 'rb') as f:
+            f.seek(lo)
+            lines = f.read(hi - lo).decode().splitlines(True)
+        rows, q = _parse_rows(lines, cell_types_idx, fa, P)
+        conn.send(("queries", q))
+        r1, r2 = conn.recv()
+        conn.send(("lines", "".join(_format_rows(rows, r1, r2, P)), len(rows)))
+    except BaseException as e:  # surfaced in the parent
+        import traceback
+        conn.send(("error", "%r\n%s" % (e, traceback.format_exc())))
+    finally:
+        conn.close()
+
+
+def _line_aligned_ranges(path, start, n):
+    """n byte ranges [lo, hi) covering [start, EOF), each ending at a line break."""
+    size = os.path.getsize(path)
+    cuts = [start]
+    with open(path, 'rb') as f:
+        for k in range(1, n):
+            f.seek(max(start, start + (size - start) * k // n))
+            f.readline()
+            cuts.append(min(max(f.tell(), cuts[-1]), size))
+    cuts.append(size)
+    return [(cuts[i], cuts[i + 1]) for i in range(n) if cuts[i + 1] > cuts[i]]
+
+
+def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, min_ac_cells, min_ac_reads, min_cells,
+                          min_reads, min_cell_types, max_cell_types, fisher_cutoff, engine, procs=None):
+    P = _Params(min_ac_cells, min_ac_reads, min_cells, min_reads, min_cell_types, max_cell_types, fisher_cutoff)
+    out_lines = []          # header lines written verbatim
+    cell_types_idx = None
+    body_start = 0
+    with open(infile, 'rb') as f:   # header: '##' lines and the first '#CHROM' line
+        while True:
+            pos = f.tell()
+            raw = f.readline()
+            if not raw:
+                body_start = pos
+                break
+            line = raw.decode()
+            if line.startswith('##'):
+                out_lines.append(line)
+                continue
+            if line.startswith('#CHROM') and cell_types_idx is None:
+                elements = line.rstrip('\n').split('\t')
+                cell_types_idx = {x: elements[x] for x in range(len(elements)) if x > 4}
+                for _, text in INFO_HEADER:
+                    out_lines.append(text + '\n')
+                elements.insert(4, "\t".join(k for k, _ in INFO_HEADER))
+                out_lines.append('\t'.join(elements) + '\n')
+                continue
+            body_start = pos
+            break
+    body_bytes = os.path.getsize(infile) - body_start
+    if procs is None:
+        procs = int(os.environ.get("LONGSOM_PROCS", "0") or 0)   # an explicit setting is honoured as is
+        if procs <= 0:
+            procs = 1 if body_bytes < (8 << 20) else min(16, os.cpu_count() or 1)   # small tables: not worth forking
+
+    warm = {}
+
+    def get_engine():
+        # `engine` may be a factory: the CUDA context is then created after the workers have been forked (a forked
+        # child must never inherit a live context) and, in the multi-process path, while they parse
+        if "thread" in warm:
+            warm.pop("thread").join()
+            if "error" in warm:
+                raise warm["error"]
+        if "engine" not in warm:
+            warm["engine"] = engine() if callable(engine) else engine
+        return warm["engine"]
+
+    def tails(q):
+        eng = get_engine()
+        p1 = eng.betabinom_sf(q[0], q[1], alpha1, beta1)
+        p2 = eng.betabinom_sf(q[2], q[3], alpha2, beta2)
+        # == round(np.float64, 4) of the reference, element-wise
+        return np.round(p1, 4), np.round(p2, 4)
+
+    if procs <= 1:
+        fa = bamio.Fasta(fasta) if fasta is not None else None
+        with open(infile, 'rb') as f:
+            f.seek(body_start)
+            data_lines = f.read().decode().splitlines(True)
+        if cell_types_idx is None and data_lines:
+            raise TypeError("'NoneType' object is not iterable")  # data before any #CHROM line: the reference fails here too
+        rows, q = _parse_rows(data_lines, cell_types_idx, fa, P)
+        r1, r2 = tails(q)
+        with open(outfile, 'w') as out:
+            out.writelines(out_lines)
+            out.writelines(_format_rows(rows, r1, r2, P))
+        if fa is not None:
+            fa.close()
+        return len(rows), len(q[0]) + len(q[2])
+
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    workers = []
+    for lo, hi in _line_aligned_ranges(infile, body_start, procs):
+        parent, child = ctx.Pipe()
+        pr = ctx.Process(target=_worker, args=(child, infile, lo, hi, cell_types_idx, fasta, P), daemon=True)
+        pr.start()
+        child.close()
+        workers.append((pr, parent))
+
+    if callable(engine):
+        import threading
+
+        def make():
+            try:
+                warm["engine"] = engine()
+            except Exception as e:
+                warm["error"] = e
+        warm["thread"] = threading.Thread(target=make, daemon=True)
+        warm["thread"].start()
+
+    def receive(conn, kind):
+        msg = conn.recv()
+        if msg[0] == "error":
+            raise RuntimeError("step1 worker failed: " + msg[1])
+        assert msg[0] == kind
+        return msg[1:]
+    queries = [receive(conn, "queries")[0] for _, conn in workers]
+    r1, r2 = tails(tuple(np.concatenate([q[j] for q in queries]) for j in range(4)))
+    o1 = o2 = 0
+    for (_, conn), q in zip(workers, queries):
+        conn.send((r1[o1:o1 + len(q[0])], r2[o2:o2 + len(q[2])]))
+        o1 += len(q[0])
+        o2 += len(q[2])
+    n_rows = 0
     with open(outfile, 'w') as out:
         out.writelines(out_lines)
-        for row in rows:
-            elements, calls = row["elements"], row["calls"]
-            Sum_alts_bc, Sum_alts_cc, Sum_dp, Sum_nc = row["sums"]
-            if row["rest"] is not None:
-                BC_noise_p, CC_noise_p = r1[row["rest"][0]], r2[row["rest"][1]]
-            else:
-                BC_noise_p, CC_noise_p = 1, 1  # plain ints, printed as '1' (:334-335)
-            rest_BC = ";".join([str(Sum_alts_bc), str(Sum_dp), str(BC_noise_p)])
-            rest_CC = ";".join([str(Sum_alts_cc), str(Sum_nc), str(CC_noise_p)])
-            n_qual = str(row["n_qual"])
-            if calls:
-                Alts, Cell_types, DPs, NCs, BCs, CCs, BCp, CCp, VAF, MCF, Filter, Fisher_p = ([] for _ in range(12))
-                for t in calls:
-                    cand = t.cand
-                    Alts.append("|".join(cand))
-                    Cell_types.append(t.cell_type)
-                    DPs.append(str(t.DP))
-                    NCs.append(str(t.NC))
-                    P_BC = [r1[i] for i in t.q_bc.values()]
-                    P_CC = [r2[i] for i in t.q_cc.values()]
-                    fisher_p = None
-                    if fisher_cutoff != 1:
-                        fisher_p = _fisher_p(cand, t.bcf, t.REF)
-                        Fisher_p.append(fisher_p)
-                    b = "|".join(str(t.bc[x]) for x in cand)
-                    c = "|".join(str(t.cc[x]) for x in cand)
-                    BCs.append(b)
-                    CCs.append(c)
-                    BCp.append("|".join(str(r1[t.q_bc[x]]) for x in cand))
-                    CCp.append("|".join(str(r2[t.q_cc[x]]) for x in cand))
-                    VAF.append("|".join(str(round(t.bc[x] / float(t.DP), 4)) for x in cand))
-                    MCF.append("|".join(str(round(t.cc[x] / float(t.NC), 4)) for x in cand))
-                    mb, mc = min(P_BC), min(P_CC)
-                    if mb >= 0.05 or mc >= 0.05:
-                        Filter.append('Non-Significant')
-                    elif 0.001 < mb < 0.05 or 0.001 < mc < 0.05:
-                        Filter.append('Low-Significance')
-                    elif len(cand) > 1:
-                        Filter.append('Multi-allelic')
-                    elif int(c) < min_ac_cells:
-                        Filter.append('Low_cells')
-                    elif int(b) < min_ac_reads:
-                        Filter.append('Low_reads')
-                    elif fisher_cutoff != 1:
-                        if float(fisher_p) < fisher_cutoff:  # may append nothing (Q8)
-                            Filter.append('Fisher')
-                    else:
-                        Filter.append('PASS')
-                FILTER = []
-                n_pass = sum(1 for x in Filter if x == 'PASS')
-                n_nonsig = sum(1 for x in Filter if x == 'Non-Significant')
-                if n_pass > max_cell_types:
-                    FILTER.append('Multiple_cell_types')
-                LEN_Alts = len(set(Alts))
-                if LEN_Alts > 1 or 'Multi-allelic' in Filter:
-                    FILTER.append('Multi-allelic')
-                if row["n_qual"] < min_cell_types:
-                    FILTER.append('Min_cell_types')
-                if len(Filter) - n_pass - n_nonsig > 0:
-                    FILTER.append('Cell_type_noise')
-                if BC_noise_p < 0.05 or CC_noise_p < 0.05:
-                    FILTER.append('Noisy_site')
-                if homopolymer(row["up"], Alts, True) == 1:
-                    FILTER.append("LC_Upstream")
-                if homopolymer(row["down"], Alts, False) == 1:
-                    FILTER.append("LC_Downstream")
-                if len(FILTER) == 0:
-                    FILTER = 'PASS' if 'PASS' in Filter else ",".join(Filter)
-                else:
-                    FILTER = ",".join(FILTER)
-                INFO = [",".join(Alts), FILTER, ",".join(Cell_types), row["up"], row["down"], str(LEN_Alts), ",".join(DPs),
-                        ",".join(NCs), ",".join(BCs), ",".join(CCs), ",".join(VAF), ",".join(MCF), ",".join(BCp),
-                        ",".join(CCp), n_qual, n_qual, rest_BC, rest_CC,
-                        ",".join(Fisher_p) if fisher_cutoff != 1 else '.', ",".join(Filter)]
-            else:
-                FILTER = 'Noisy_site' if (BC_noise_p < 0.001 or CC_noise_p < 0.001) else '.'
-                INFO = [".", FILTER, ".", row["up"], row["down"], ".", ".", ".", ".", ".", ".", ".", ".", ".", n_qual, n_qual,
-                        rest_BC, rest_CC, '.', '.']
-            elements.insert(4, "\t".join(INFO))
-            out.write('\t'.join(elements) + '\n')
-    if fa is not None:
-        fa.close()
-    return len(rows), len(q1k) + len(q2k)
+        for pr, conn in workers:
+            text, n = receive(conn, "lines")
+            out.write(text)
+            n_rows += n
+            pr.join()
+    return n_rows, len(r1) + len(r2)
 
 
 def initialize_parser():
@@ -278,11 +420,19 @@ def main(argv=None):
     print('------------------------------\n')
     print('- Variant calling step 1\n')
     outfile1 = args.outfile + ".calling.step1.tsv"
-    with Engine(devices_from_env()[0]) as eng:
+    made = []
+
+    def make_engine():  # created lazily: after the worker processes have been forked, while they parse
+        made.append(Engine(devices_from_env()[0]))
+        return made[-1]
+    try:
         n_rows, n_q = variant_calling_step1(args.infile, outfile1, args.ref, args.alpha1, args.beta1, args.alpha2,
                                             args.beta2, args.min_ac_cells, args.min_ac_reads, args.min_cells,
                                             args.min_cov, args.min_cell_types, args.max_cell_types, args.fisher_cutoff,
-                                            eng)
+                                            make_engine)
+    finally:
+        for eng in made:
+            eng.close()
     print('Step 1 variant calling: %d positions processed, %d beta-binomial tails on the GPU' % (n_rows, n_q))
     print('\nTotal computing time: ' + str(round(timeit.default_timer() - start, 2)) + ' seconds')
 

@@ -312,3 +312,17 @@ def test_filters_fail_like_reference_on_empty_selection(tmp_path):
         hccv_variants.main(["--SNVs", src, "--outfile", os.path.join(str(tmp_path), "e"), "--min_dp", "20", "--deltaVAF", "0.1",
                             "--deltaMCF", "0.3"])
     assert os.path.exists(os.path.join(str(tmp_path), "e.calling.step3.tsv"))
+
+
+def test_step1_worker_processes_do_not_change_the_output(work):
+    """step1 cuts large tables into byte ranges handled by forked workers (queries gathered in the parent, tails
+    sent back, lines concatenated in range order): forced here on the golden table, 1..5 workers."""
+    import pipeline_inputs as pi
+    from longsom_b200.cli.step1 import variant_calling_step1
+    case, d, p, data = work
+    for procs in (2, 3, 5):
+        out = os.path.join(d, "step1_mp%d.tsv" % procs)
+        n_rows, n_q = variant_calling_step1(os.path.join(d, "merged.tsv"), out, p["ref"], pi.ALPHA1, pi.BETA1, pi.ALPHA2, pi.BETA2,
+                                            2, 3, 5, 5, 2, 1, 1, OracleEngine(), procs=procs)
+        assert_same(file_lines(out), gold_lines(case, "step1.tsv"), "BaseCellCalling.step1 with %d workers" % procs)
+        assert n_rows == len([l for l in gold_lines(case, "step1.tsv") if not l.startswith("#")])
