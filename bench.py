@@ -83,7 +83,8 @@ def build_workload(scale, rank, world, sample_bases=None):
     we = np.array([i[2] for i in iv], np.int32)
     weights = window_weights(wt, ws, we, tid, pos, tlen)
     if sample_bases is not None:
-        # densest run of consecutive windows holding ~sample_bases aligned bases
+        # the first run of consecutive covered windows holding ~sample_bases aligned bases (genes are laid out
+        # left to right with i.i.d. expression weights, so a prefix of the genome is a fair sample of the batch)
         cum = np.concatenate([[0.0], np.cumsum(weights)])
         start = int(np.argmax(weights > 0))
         end = int(np.searchsorted(cum, cum[start] + sample_bases, side="left"))
@@ -204,7 +205,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import __graft_entry__ as g
-    g.build()
+    g.build_checker()  # generator + oracle only: this arm never loads liblongsom_b200.so
     cores = os.cpu_count() or 1
     scale = args.scale
     # size the per-step sample so that (steps + warmup) steps take ~2 minutes: probe first

@@ -45,7 +45,7 @@ extern "C" int ls_ctx_destroy(ls_ctx *ctx) {
                   &ctx->rs_hist,   &ctx->scan_tmp,  &ctx->counters,  &ctx->tile_flag,  &ctx->tile_rank, &ctx->slot_tile,
                   &ctx->slot_lo,   &ctx->slot_out,  &ctx->slot_mask, &ctx->slot_npass, &ctx->slot_off, &ctx->drop_keys,
                   &ctx->out_tid,   &ctx->out_pos,   &ctx->out_ref,   &ctx->out_counts, &ctx->l2_scratch, &ctx->g_a,
-                  &ctx->g_b,       &ctx->g_c,       &ctx->g_d,       &ctx->g_e,        &ctx->rend,     &ctx->wcount,   &ctx->part_slot, &ctx->part_k, &ctx->slot_nparts, &ctx->slot_done, &ctx->acbuf};
+                  &ctx->g_b,       &ctx->g_c,       &ctx->g_d,       &ctx->g_e,        &ctx->rend,     &ctx->wcount,   &ctx->part_slot, &ctx->part_k, &ctx->slot_nparts, &ctx->slot_done, &ctx->acbuf, &ctx->offs_s, &ctx->offs_m, &ctx->offs_u, &ctx->units};
   for (DBuf *b : bufs) b->release();
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -91,6 +91,20 @@ extern "C" int ls_flush_l2(ls_ctx *ctx) {
   return LS_OK;
 }
 
+// BAM packs base 2b in the HIGH nibble of byte b; the kernels want it in the low nibble (see ls_ctx::seq4_d)
+__global__ void __launch_bounds__(256) nibble_swap_kernel(uint4 *p, size_t n16) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n16; i += stride) {
+    uint4 v = p[i];
+    v.x = ((v.x & 0x0f0f0f0fu) << 4) | ((v.x >> 4) & 0x0f0f0f0fu);
+    v.y = ((v.y & 0x0f0f0f0fu) << 4) | ((v.y >> 4) & 0x0f0f0f0fu);
+    v.z = ((v.z & 0x0f0f0f0fu) << 4) | ((v.z >> 4) & 0x0f0f0f0fu);
+    v.w = ((v.w & 0x0f0f0f0fu) << 4) | ((v.w >> 4) & 0x0f0f0f0fu);
+    p[i] = v;
+  }
+}
+
 #define UP(buf, src, bytes)                                                                   \
   do {                                                                                        \
     LS_CK(ctx->buf.ensure((bytes) ? (bytes) : 16));                                           \
@@ -105,6 +119,7 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
   const int64_t n = b->n_reads;
   if (n < 0 || b->n_cigar < 0 || b->n_bases < 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: negative size");
   if (n >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_pileup_upload: more than 2^32-1 reads per batch");
+  if (b->n_bases >= ((int64_t)1 << 36)) LS_FAIL(LS_E_ARG, "ls_pileup_upload: more than 2^36 query bases per batch");
   if (n > 0 && (!b->tid || !b->pos || !b->flag || !b->mapq || !b->cell || !b->cigar_off || !b->base_off || !b->l_qseq))
     LS_FAIL(LS_E_ARG, "ls_pileup_upload: null per-read array");
   if (b->n_cigar > 0 && !b->cigar) LS_FAIL(LS_E_ARG, "ls_pileup_upload: null cigar");
@@ -151,8 +166,23 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
   UP(cigar, b->cigar, (size_t)b->n_cigar * 4);
   UP(base_off, b->base_off, (size_t)(n + 1) * 8);
   UP(lq, b->l_qseq, (size_t)n * 4);
-  UP(seq4, b->seq4, (size_t)(b->n_bases + 1) / 2);
-  UP(qual, b->qual, (size_t)b->n_bases);
+  {
+    // qual / seq4 sit LS_QPAD bytes into zero-initialised allocations with as much slack behind them
+    const size_t nq = (size_t)b->n_bases, ns = (size_t)(b->n_bases + 1) / 2;
+    const size_t ns16 = (ns + 15) / 16 * 16;
+    LS_CK(ctx->qual.ensure(nq + 2 * LS_QPAD));
+    LS_CK(ctx->seq4.ensure(ns16 + 2 * LS_QPAD));
+    LS_CK(cudaMemsetAsync(ctx->qual.p, 0, LS_QPAD, st));
+    LS_CK(cudaMemsetAsync((uint8_t *)ctx->qual.p + LS_QPAD + nq, 0, LS_QPAD, st));
+    LS_CK(cudaMemsetAsync(ctx->seq4.p, 0, LS_QPAD, st));
+    LS_CK(cudaMemsetAsync((uint8_t *)ctx->seq4.p + LS_QPAD + ns, 0, ns16 - ns + LS_QPAD, st));
+    if (nq) LS_CK(cudaMemcpyAsync((uint8_t *)ctx->qual.p + LS_QPAD, b->qual, nq, cudaMemcpyHostToDevice, st));
+    if (ns) {
+      LS_CK(cudaMemcpyAsync((uint8_t *)ctx->seq4.p + LS_QPAD, b->seq4, ns, cudaMemcpyHostToDevice, st));
+      nibble_swap_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(reinterpret_cast<uint4 *>((uint8_t *)ctx->seq4.p + LS_QPAD), ns16 / 16);
+      LS_CK(cudaGetLastError());
+    }
+  }
   UP(wtid, w ? w->tid : nullptr, (size_t)nw * 4);
   UP(wstart, w ? w->start : nullptr, (size_t)nw * 4);
   UP(wend, w ? w->end : nullptr, (size_t)nw * 4);

@@ -49,31 +49,39 @@ struct DBuf {
   }
 };
 
-// one (read, tile) work item of the pileup-count kernel
+// one (read, tile) work item of the pileup-count kernel (16 B, self-contained: the count kernel never touches the
+// per-read arrays)
 struct __align__(16) Segment {
-  uint32_t read;   // read index in the batch
-  uint32_t p0;     // first piece of the segment in pieces[]
-  uint32_t np;     // bits 0-15: number of pieces (consecutive: a read's CIGAR visits a tile once);
-                   // bits 16-31: query bases spanned by the pieces (saturating), for prefetching
-  uint32_t y0;     // query index of the first piece
+  uint32_t p0;      // first piece of the segment in pieces[] (consecutive: a read's CIGAR visits a tile once)
+  uint32_t np_nu;   // bits 0-15: number of pieces; bits 16-31: number of 32-base units the pieces expand to
+  uint32_t boff16;  // base_off[read] / 16: where the read's qualities / bases start
+  uint32_t flags;   // bit 0: reverse strand
 };
-__host__ __device__ __forceinline__ uint32_t segment_np_word(uint32_t np, uint32_t y0, uint32_t y1) {
-  const uint32_t q = y1 > y0 ? y1 - y0 : 0u;
-  return np | ((q > 65535u ? 65535u : q) << 16);
-}
 
 // One CIGAR op clipped to one tile, produced by the segment builder so that the count kernel does not walk
 // CIGARs: a match piece covers query bases [ya, ya + n) at tile columns [col, col + n); a deletion piece covers
 // n columns that all carry the quality of query base ya (htslib: qpos of a deletion = the next query base).
 // `ind` marks a piece whose last column is the op's last column and is followed by an insertion (1) or a
 // deletion (2): that column's class becomes I / D.  A ref-skip followed by an indel is a 1-column deletion piece.
+// `virt` marks query positions past the stored sequence (malformed record): quality 0, base 'N'.
 struct __align__(8) Piece {
   uint32_t ya;
-  uint32_t meta;  // col: bits 0-8, n (1..512): bits 9-18, deletion-like: bit 19, ind: bits 20-21
+  uint32_t meta;  // col: bits 0-8, n (1..512): bits 9-18, deletion-like: bit 19, ind: bits 20-21, virt: bit 22
 };
-__host__ __device__ __forceinline__ uint32_t piece_meta(uint32_t col, uint32_t n, uint32_t del, uint32_t ind) {
-  return col | (n << 9) | (del << 19) | (ind << 20);
+__host__ __device__ __forceinline__ uint32_t piece_meta(uint32_t col, uint32_t n, uint32_t del, uint32_t ind,
+                                                        uint32_t virt) {
+  return col | (n << 9) | (del << 19) | (ind << 20) | (virt << 22);
 }
+// Units of a piece: the piece cut at the 32-column windows of its tile (a unit never crosses a window, so the
+// count kernel can keep one window's per-site state in registers and the padded accumulator rows need no carry).
+__host__ __device__ __forceinline__ uint32_t piece_units(uint32_t meta) {
+  const uint32_t col = meta & 511u, n = (meta >> 9) & 1023u;
+  return ((col + n - 1u) >> 5) - (col >> 5) + 1u;
+}
+
+// Device copies of qual[] / seq4[] start LS_QPAD bytes into their allocations (and end with as much slack): a unit
+// loads the aligned 40-byte / 24-byte blocks around its bases, which may reach a few bytes past either end.
+#define LS_QPAD 64
 
 struct ls_ctx {
   int device = 0;
@@ -88,6 +96,11 @@ struct ls_ctx {
   int32_t max_cell = -1;
   DBuf tid, pos, flag, mapq, cell, cigar_off, cigar, base_off, lq, seq4, qual;
   DBuf wtid, wstart, wend, wref_off, ref, wtile_base;
+  // seq4 on the device is nibble-swapped at upload (even base in the LOW nibble): base n of the batch then sits at
+  // bits 4n .. 4n+3 of the little-endian byte stream, so aligning a unit to its window is one funnel shift
+  const uint8_t *qual_d() const { return as_u8(qual) + LS_QPAD; }
+  const uint8_t *seq4_d() const { return as_u8(seq4) + LS_QPAD; }
+  static const uint8_t *as_u8(const DBuf &b) { return reinterpret_cast<const uint8_t *>(b.p); }
   std::vector<int32_t> h_wtid, h_wstart, h_wend;
   std::vector<int64_t> h_wtile_base;  // [n_windows+1]
   int64_t n_tiles_total = 0;
@@ -98,6 +111,7 @@ struct ls_ctx {
   DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;
   DBuf drop_keys, rend, wcount, part_slot, part_k, slot_nparts, slot_done, acbuf;
+  DBuf offs_s, offs_m, offs_u, units;
   int64_t n_drop = 0;
   bool k1_attr_set = false;
   int64_t n_segments = 0, n_pieces = 0, n_slots = 0, n_sites = 0;

@@ -1,52 +1,65 @@
-// K1 pileup-count kernel (third generation) + part bookkeeping.  Included by ls_pileup.cu.
+// K1 pileup-count kernel (one LANE per 32-column unit) + the unit expansion and part bookkeeping around it.
+// Included by ls_pileup.cu.
 //
-// Unit of work: a PART = up to K1_PART_SEGS consecutive (tile, cell)-sorted segments of one
-// tile.  Most tiles are one part; deep tiles (chrM, hotspot genes: >1e5 reads per locus) are
-// split so that no CTA owns more than ~4e5 pileup entries.  Same-cell runs never straddle
-// parts (a run belongs to the part / chunk that holds its first segment), so NC / CC stay
-// exact and every output word is additive across parts; multi-part tiles add into their HBM
-// slot and the last part to finish applies the reference's gates.
+// After the (tile, cell) sort, `classify_kernel` + scans + `expand_kernel` turn the sorted segments into UNIT STREAMS
+// in HBM.  A unit is one piece (CIGAR op clipped to the tile) clipped to one of the tile's sixteen 32-column windows:
+// where its query bases start in qual[] / seq4[], the window, the columns [lo, hi) it covers, strand, and whether it
+// is a run of deletion columns (which all carry one quality).  Three streams, each in sorted-segment order:
+//   S = segments whose (tile, cell) key occurs once,
+//   M = same-cell runs (>= 2 segments of one cell in one tile); inside a run the units are ordered WINDOW-MAJOR, so
+//       that all entries one cell has at one reference position are consecutive units of the stream,
+//   U = visible-but-uncounted reads (only with --min_ac > 0).
 //
-// Inside a part (CTA of 8 warps, tile accumulators in shared memory):
-//   * a warp grabs a chunk of <= 32 segments; lane j loads segment j's record and read
-//     metadata (one global-latency for the whole chunk instead of one per segment);
-//     and L2-prefetches the query bytes / first piece line that segment will touch;
-//   * per segment the lanes fetch its pieces (CIGAR ops clipped to the tile, precomputed by the segment
-//     builder in ls_segments.cuh) 32 at a time and go through them warp-uniformly -- no CIGAR walk here;
-//   * a match piece is consumed 128 query bases per step: lane L loads one aligned 32-bit word of
-//     qualities and one 16-bit word of 4-bit bases (vectorised, coalesced), classifies its 4
-//     bases and issues ONE packed shared atomic per visible base (count<<20 | quality).
-// (A two-phase variant that flattens op pieces into a per-warp unit queue was measured 1.8x
-//  slower on C2 -- register spills and the per-word unit search cost more than the idle lanes.)
-// Distinct-cell counts: NC/CC = reads minus same-cell duplicates.  Runs of >1 same-cell
-// segments mark (site, class) bits with atomicOr in a per-warp seen[] array, so the order in
-// which a run's bases are visited does not matter; single-segment runs skip this entirely.
-// The accumulator column of site s is [s mod 4][s / 4]: the 4-bases-per-lane pattern then
-// hits 32 distinct banks on each of its 4 atomics.
+// Unit of work of a count CTA: a PART = up to K1_PART_SEGS consecutive sorted segments of one tile.  Most tiles are
+// one part; deep tiles (chrM, hotspot genes: >1e5 reads per locus) are split so that no CTA owns more than ~4e5
+// pileup entries.  Same-cell runs never straddle parts (a run belongs to the part that holds its first segment), so
+// NC / CC stay exact and every output word is additive across parts; multi-part tiles add into their HBM slot and
+// the last part to finish applies the reference's gates.
+//
+// Inside a part (CTA of K1_WARPS warps, tile accumulators in shared memory) every lane owns whole units:
+//   * the lane loads the aligned 40-byte block of qualities and 24-byte block of 4-bit bases around its unit and
+//     shifts them so that byte / nibble j is the base at column j of the window (seq4 is nibble-swapped at upload so
+//     that this is one funnel shift);
+//   * 32 fully unrolled columns: byte permute -> packed (count<<20 | quality) word, nibble -> row offset through a
+//     16-entry shared-memory table, one `red.shared.add` per column (a zero add for columns that must not count:
+//     ptxas never predicates a shared atomic, it branches around it).  Rows are padded by one word per window, so
+//     the lanes of a warp -- which work on different windows and strands -- hit different banks;
+//   * all 32 lanes work on different reads, so lane occupancy does not depend on piece lengths (the previous
+//     generation gave a whole warp to one piece: 2.5 warp-instructions per pileup entry at 21 of 32 lanes).
+// Distinct-cell counts: NC/CC = reads minus same-cell duplicates.  In the M stream the units of one (cell, window)
+// group are consecutive and handled by ONE lane, which keeps the class bits the cell has shown at each of the 32
+// columns in eight registers: a column whose bit / byte is already set is a (cell, class) / (cell) duplicate.  No
+// shared-memory state, no atomics and no warp-level serialisation per run.
 #pragma once
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_WARPS = 8;
+constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr int K1_PART_SEGS = 2048;       // nominal segments per part
 constexpr int K1_MAX_RUN_PACKED = 2039;  // packed counters (12-bit) need: part segs + run extension <= 4095
-constexpr int K1_ROWS = 18;               // 9 row pairs: 8 classes + the dump pair
-constexpr uint32_t K1_CLASS_STRIDE = 2u * LS_TILE * 4u;  // bytes between the row pairs of consecutive classes
-constexpr uint32_t K1_DUMP_OFF = 8u * K1_CLASS_STRIDE;
+constexpr int K1_CROWS = 18;             // 16 (class, strand) rows + a dump row pair for ignored base codes
+constexpr int K1_ROWW = 16 * 33;         // words per row: 16 windows of 32 columns + 1 pad word each
+constexpr uint32_t K1_ROW_BYTES = 4u * K1_ROWW;
+constexpr uint32_t K1_DUMP_OFF = 16u * K1_ROW_BYTES;
 constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
 
-static_assert(LS_TILE % 128 == 0 && LS_TILE % K1_THREADS == 0 && LS_TILE <= 65536, "tile / block shape");
+static_assert(LS_TILE % K1_THREADS == 0 && LS_TILE == 512, "tile / block shape");
 
-__host__ __device__ __forceinline__ int swz(int s) { return ((s & 3) * (LS_TILE / 4)) | (s >> 2); }
+// unit.x: low 32 bits of q = index in qual[] of the base at column lo (deletion-like: of the one quality byte)
+// unit.y: q >> 32: bits 0-3 | window: 4-7 | lo: 8-12 | hi: 13-18 | strand: 19 | deletion-like: 20 | ind: 21-22 |
+//         virt: 23 | first unit of its (run, window) group: 24
+constexpr uint32_t UM_STRAND = 1u << 19;
+constexpr uint32_t UM_DEL = 1u << 20;
+constexpr uint32_t UM_VIRT = 1u << 23;
+constexpr uint32_t UM_GSTART = 1u << 24;
+
+__host__ __device__ __forceinline__ int k1_col(int s) { return s + (s >> 5); }  // column -> word of a padded row
 
 struct CountArgs {
-  const uint16_t *flag;
-  const Piece *pieces;
-  const uint64_t *base_off;
-  const int32_t *lq;
-  const uint8_t *seq4, *qual;
-  const Segment *segs;
+  const uint8_t *seq4, *qual;                // device copies (padded, seq4 nibble-swapped; see ls_ctx)
+  const uint2 *units;                        // S stream, then M, then U
+  const uint32_t *offs_s, *offs_m, *offs_u;  // [nseg + 1] first unit of sorted segment i in its stream (offs_u may be null)
+  const uint64_t *tot_s, *tot_m;             // stream sizes (M starts at *tot_s, U at *tot_s + *tot_m)
   const uint64_t *keys;
-  const uint32_t *vals;
   const int64_t *slot_tile;
   const uint32_t *slot_lo;
   const uint32_t *part_slot, *part_k, *slot_nparts;
@@ -65,21 +78,21 @@ struct CountArgs {
   int cell_bits;
   uint32_t uncounted_key;
   int min_bq, min_dp, min_cc, min_ac;
-  int prefetch;
+  uint32_t cnt1;  // 1 << K1_CNT_SHIFT for the packed kernel, 0 for the unpacked one (a run-time value on purpose:
+                  // as a compile-time constant it takes PRMT's immediate slot and the byte selectors need a MOV each)
 };
 
 template <bool PACKED>
 struct TileSmemT {
-  // rows [cls*2+strand], cls 0..7 real classes, cls 8 = "dump" rows that absorb invisible / ignored bases so that
-  // the 4-base step needs no branches.  PACKED: cnt<<20|bq; else rows [0..17] counts, [18..35] quality sums.
-  uint32_t hist[PACKED ? K1_ROWS : 2 * K1_ROWS][LS_TILE];
-  uint32_t dupcc[3][LS_TILE];                // (cell, class) already seen at the site: class c in half-word c/3 of row c%3
-  uint32_t lut2[16];                         // BAM nibble code -> byte offset of the class row pair (dump rows if ignored)
-  uint32_t dupnc[LS_TILE];                   // entries whose cell was already seen at the site (any class)
-  uint32_t acx[LS_TILE];                     // alt entries of visible-but-uncounted reads (--min_ac > 0)
-  uint32_t seen[K1_WARPS][LS_TILE / 4];      // per warp: class bits (1 byte per site) of the current same-cell run
+  // rows [cls*2+strand] for cls 0..7, rows 16-17 = "dump" (ignored base codes).  PACKED: cnt<<20|bq; else rows
+  // [0..17] counts, [18..35] quality sums.  Column s of a row is word k1_col(s).
+  uint32_t hist[PACKED ? K1_CROWS : 2 * K1_CROWS][K1_ROWW];
+  uint32_t dup[8][K1_ROWW];               // per class: (cell, class) duplicates | (cell) duplicates << 16
+  uint32_t acx[K1_ROWW];                  // alt entries of visible-but-uncounted reads (--min_ac > 0)
+  alignas(64) uint32_t lut[16];           // BAM nibble code -> byte offset of the class's row pair (dump rows if ignored)
+  uint32_t lut2[2][16];                   // [deletion-like][code] -> class bit | byte offset of the class's dup row << 8
   uint8_t ref[LS_TILE];
-  uint32_t next, npass, ticket;
+  uint32_t next1, next2, next3, npass, ticket;
 };
 
 __device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t tile) {
@@ -94,221 +107,360 @@ __device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t ti
   return lo;
 }
 
-// shared-memory reduction on a 32-bit shared-window address (no generic->shared conversion per base)
+// shared-memory accesses on 32-bit shared-window addresses (no generic->shared conversion per base)
 __device__ __forceinline__ void red_shared_add(uint32_t addr, uint32_t v) {
   // no "memory" clobber: nothing reads the accumulators before the CTA barrier, so loads may move across
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v));
 }
-
-// hs = shared address of hist[strand][0]: the (class, strand) row of class c starts 2*LS_TILE words further per class
-template <bool PACKED>
-__device__ __forceinline__ void note_seen(TileSmemT<PACKED> &sm, uint32_t *seen, int s, int cls) {
-  const int sidx = swz(s);
-  const int sh = 8 * (s & 3);
-  const uint32_t old = (atomicOr(&seen[s >> 2], (1u << cls) << sh) >> sh) & 255u;
-  if (((old >> cls) & 1u) && cls < 6) atomicAdd(&sm.dupcc[cls % 3][sidx], 1u << (16 * (cls / 3)));
-  if (old) atomicAdd(&sm.dupnc[sidx], 1u);
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));  // tables are written once, before the first barrier
+  return v;
+}
+template <uint32_t SEL>
+__device__ __forceinline__ uint32_t prmt_sel(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "n"(SEL));
+  return d;
+}
+__device__ __forceinline__ uint32_t prmt_var(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ uint2 ldg_v2(const void *p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
 }
 
-template <bool PACKED, bool SEEN>
-__device__ __forceinline__ void add_entry(TileSmemT<PACKED> &sm, uint32_t *seen, int s, int cls, uint32_t q,
-                                          uint32_t hs) {
-  const uint32_t addr = hs + (uint32_t)cls * K1_CLASS_STRIDE + (uint32_t)swz(s) * 4u;
-  if (PACKED) {
-    red_shared_add(addr, (1u << K1_CNT_SHIFT) | q);
-  } else {
-    red_shared_add(addr, 1u);
-    red_shared_add(addr + (uint32_t)K1_ROWS * LS_TILE * 4u, q);
-  }
-  if (SEEN) note_seen<PACKED>(sm, seen, s, cls);
-}
-
-template <bool PACKED>
-__device__ __forceinline__ void add_uncounted(TileSmemT<PACKED> &sm, int s, int cls) {
-  // AC pre-gate of BaseCellCounter.py:165-174,221 for reads the counts ignore (no CB / supplementary)
-  const bool alt = (cls == LS_CLASS_D || cls == LS_CLASS_I) || (cls != LS_CLASS_O && class_letter(cls) != sm.ref[s]);
-  if (alt) atomicAdd(&sm.acx[swz(s)], 1u);
-}
-
-// nibble code -> class id, 4 bits per entry: 1->A(0) 2->C(1) 4->G(3) 8->T(2) 15->N(6), else NA(8)
-#define K1_CLASS_LUT 0x6888888288838108ull
-
-struct SegMeta {
-  uint32_t p0, np, lq;
-  uint32_t y0, qlen;  // query extent of the segment (prefetch only; not shuffled)
-  uint64_t boff;
-  int strand;
+struct UData {
+  uint32_t qw[8];  // byte j = quality of the base at column j of the window
+  uint32_t hw[4];  // nibble j (bits 4j .. 4j+3) = its BAM base code
+  uint32_t qlast;  // quality of the base at column hi - 1 (the one that carries a following indel)
 };
 
-__device__ __forceinline__ SegMeta load_meta(const CountArgs &a, uint32_t i) {
-  const Segment sg = a.segs[a.vals[i]];
-  SegMeta m;
-  m.p0 = sg.p0;
-  m.np = sg.np & 0xffffu;
-  m.y0 = sg.y0;
-  m.qlen = sg.np >> 16;
-  m.boff = a.base_off[sg.read];
-  m.lq = (uint32_t)a.lq[sg.read];
-  m.strand = (a.flag[sg.read] & LS_FLAG_REVERSE) ? 1 : 0;
-  return m;
+__device__ __forceinline__ UData load_unit(const CountArgs &a, uint2 u) {
+  UData d;
+  const uint32_t meta = u.y;
+  const uint32_t lo = (meta >> 8) & 31u, hi = (meta >> 13) & 63u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d.qw[i] = 0u;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) d.hw[i] = ~0u;  // 'N': what deletion-like and virtual units run as
+  d.qlast = 0u;
+  if (hi == 0u) return d;  // empty lane
+  const int64_t q = (int64_t)(((uint64_t)(meta & 15u) << 32) | u.x);
+  if (meta & UM_VIRT) {
+    // query positions past the stored sequence: quality 0, base 'N'
+  } else if (meta & UM_DEL) {
+    const uint32_t qv = a.qual[q];
+    const uint32_t q4 = qv * 0x01010101u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d.qw[i] = q4;
+    d.qlast = qv;
+  } else {
+    const int64_t q0 = q - (int64_t)lo;  // where column 0 of the window would be (possibly before the read)
+    {
+      const uint8_t *p = a.qual + (q0 & ~(int64_t)7);
+      const uint32_t sh = (uint32_t)q0 & 7u;
+      uint32_t w[10];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const uint2 t = ldg_v2(p + 8 * i);
+        w[2 * i] = t.x;
+        w[2 * i + 1] = t.y;
+      }
+      const bool o = (sh & 4u) != 0u;
+      uint32_t x[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) x[i] = o ? w[i + 1] : w[i];
+      const uint32_t sel = 0x3210u + 0x1111u * (sh & 3u);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) d.qw[i] = prmt_var(x[i], x[i + 1], sel);
+    }
+    {
+      const int64_t b0 = q0 >> 1;  // byte of nibble q0 (arithmetic shift: q0 may be slightly negative)
+      const uint8_t *p = a.seq4 + (b0 & ~(int64_t)7);
+      const uint32_t shift = 4u * ((uint32_t)q0 & 15u);
+      uint32_t h[6];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const uint2 t = ldg_v2(p + 8 * i);
+        h[2 * i] = t.x;
+        h[2 * i + 1] = t.y;
+      }
+      const bool o = (shift & 32u) != 0u;
+      uint32_t y[5];
+#pragma unroll
+      for (int i = 0; i < 5; ++i) y[i] = o ? h[i + 1] : h[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d.hw[i] = __funnelshift_r(y[i], y[i + 1], shift & 31u);
+    }
+    if ((meta >> 21) & 3u) d.qlast = a.qual[q + (int64_t)(hi - 1u - lo)];
+  }
+  return d;
 }
 
-__device__ __forceinline__ SegMeta shfl_meta(const SegMeta &m, int j) {
-  SegMeta r;
-  r.p0 = __shfl_sync(0xffffffffu, m.p0, j);
-  r.np = __shfl_sync(0xffffffffu, m.np, j);
-  r.lq = __shfl_sync(0xffffffffu, m.lq, j);
-  r.boff = __shfl_sync(0xffffffffu, m.boff, j);
-  r.strand = __shfl_sync(0xffffffffu, m.strand, j);
-  return r;
-}
+struct WarpCtx {
+  uint32_t hist_s, lut_s, dup_s;  // shared-window addresses
+  uint32_t thr;                   // PACKED: (1 << 20) | min_bq, else min_bq (clamped to [0, 256])
+  uint32_t cnt1;                  // PACKED: 1 << 20, else 0
+};
 
-// ---- one segment, warp-cooperative: its pieces (CIGAR ops clipped to the tile, precomputed by the segment
-// builder) are fetched 32 at a time; a match piece is consumed 128 query bases per step (4 per lane, one 32-bit
-// quality word + one 16-bit base word) ----------------------------------------------------------------------
-template <bool PACKED, bool SEEN, bool COUNTED>
-__device__ __forceinline__ void process_segment_fast(const CountArgs &a, TileSmemT<PACKED> &sm, uint32_t *seen,
-                                                     const SegMeta m, int lane, uint32_t hist_s) {
-  const uint8_t *__restrict__ qual = a.qual + m.boff;
-  const uint8_t *__restrict__ seq4 = a.seq4 + (m.boff >> 1);
-  const uint32_t strand = hist_s + (uint32_t)m.strand * (LS_TILE * 4u);  // shared address of hist[strand][0]
-  const uint32_t lq = m.lq;
-  for (uint32_t pb = 0; pb < m.np; pb += 32u) {
-    Piece pc;
-    pc.ya = 0u;
-    pc.meta = 0u;
-    if (pb + (uint32_t)lane < m.np) pc = a.pieces[m.p0 + pb + (uint32_t)lane];
-    const int nloc = (int)((m.np - pb) < 32u ? (m.np - pb) : 32u);
-    for (int t = 0; t < nloc; ++t) {
-      const uint32_t y0 = __shfl_sync(0xffffffffu, pc.ya, t);
-      const uint32_t meta = __shfl_sync(0xffffffffu, pc.meta, t);
-      const int sbase = (int)(meta & 511u);
-      const uint32_t n = (meta >> 9) & 1023u;
-      const uint32_t ind = (meta >> 20) & 3u;
-      const int indcls = ind == 2u ? LS_CLASS_D : LS_CLASS_I;
-      {
-        if ((meta >> 19) & 1u) {  // deletion / ref-skip columns: every column carries the quality of the next query base
-          const uint32_t q = y0 < lq ? qual[y0] : 0u;
-          if ((int)q >= a.min_bq) {
-            for (uint32_t p = (uint32_t)lane; p < n; p += 32u) {
-              const int cls = (p == n - 1u && ind != 0u) ? indcls : LS_CLASS_O;
-              if (COUNTED)
-                add_entry<PACKED, SEEN>(sm, seen, sbase + (int)p, cls, q, strand);
-              else
-                add_uncounted<PACKED>(sm, sbase + (int)p, cls);
-            }
-          }
-        } else {
-          const uint32_t ya = y0, yb = y0 + n;                                       // query range inside the tile
-          const uint32_t ybl = yb < lq ? yb : lq;                                    // bases that exist
-          const uint32_t ylast = (ind != 0) ? (yb - 1u) : 0xffffffffu;
-          // the base that carries a following indel is handled on its own (below); the word loop stops before it
-          const uint32_t yw = (ind != 0 && ylast < ybl) ? ylast : ybl;
-          if (COUNTED && a.min_bq >= 0 && a.min_bq <= 128) {
-            // Branch-free 4-base step.  Class decode = one shared lookup per base byte (2 bases); bases that must
-            // not count (quality below min_bq, ignored code, outside [ya, yw)) are steered to the dump rows instead
-            // of being branched around.  (site & 3) of byte j is identical for all lanes and steps, so the
-            // swizzled column of byte j is colb[j] + 4 * (site_of_byte0 >> 2) with colb[] warp-uniform.
-            const int a4 = (sbase - (int)(ya & 3u)) & 3;
-            uint32_t colb[4];
+// One column of a unit.  A column that must not count -- outside [lo, hi), below the quality threshold -- adds ZERO to
+// the word it would have hit, and an ignored base code adds to a dump row through the nibble table: the 32 unrolled
+// columns are straight-line code.  SEEN adds the same-cell bookkeeping on the lane's per-window state `seen` (one
+// byte of class bits per column): a class bit that was already set is a (cell, class) duplicate, any bit already set
+// a (cell) duplicate; both go to the class's dup word with one more (possibly zero) add.
+template <bool PACKED, bool SEEN, int J>
+struct BaseLoop {
+  static __device__ __forceinline__ void run(const WarpCtx &c, const UData &d, uint32_t hs, uint32_t vm, uint32_t ds,
+                                             uint32_t lut2p, uint32_t (&seen)[8]) {
+    constexpr uint32_t QOFF = (uint32_t)K1_CROWS * K1_ROW_BYTES;
+    const uint32_t v = prmt_sel<0x4640u | (uint32_t)(J & 3)>(d.qw[J >> 2], c.cnt1);
+    constexpr int pos = 4 * (J & 7);  // bit position of column J's nibble in its word
+    const uint32_t idx = pos >= 2 ? ((d.hw[J >> 3] >> (pos >= 2 ? pos - 2 : 0)) & 0x3cu) : ((d.hw[J >> 3] << 2) & 0x3cu);
+    const uint32_t off = lds_u32(idx | c.lut_s);  // the table is 64-byte aligned
+    uint32_t vz, okm;  // vz = v, okm = 0xff if column J is inside [lo, hi) and v >= thr; else 0
+    asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %3, %4;\n setp.ne.u32 p, t, 0;\n setp.ge.and.u32 p, %2, %5, p;\n"
+        " selp.u32 %0, %2, 0, p;\n selp.u32 %1, 255, 0, p;\n}"
+        : "=r"(vz), "=r"(okm)
+        : "r"(v), "r"(vm), "n"(1u << J), "r"(c.thr));
+    const uint32_t addr = hs + off + 4u * J;
+    if (PACKED) {
+      red_shared_add(addr, vz);
+    } else {
+      red_shared_add(addr, okm & 1u);
+      red_shared_add(addr + QOFF, vz);
+    }
+    if (SEEN) {
+      const uint32_t w2 = lds_u32(idx | lut2p);  // class bit | dup row offset << 8
+      constexpr int sh = 8 * (J & 3);
+      const uint32_t bsh = (w2 & okm) << sh;
+      const uint32_t sw = seen[J >> 2];
+      const uint32_t dv = ((sw & bsh) ? 1u : 0u) + ((bsh && (sw & (0xffu << sh))) ? 65536u : 0u);
+      seen[J >> 2] = sw | bsh;
+      red_shared_add(ds + (w2 >> 8) + 4u * J, dv);
+    }
+    BaseLoop<PACKED, SEEN, J + 1>::run(c, d, hs, vm, ds, lut2p, seen);
+  }
+};
+template <bool PACKED, bool SEEN>
+struct BaseLoop<PACKED, SEEN, 32> {
+  static __device__ __forceinline__ void run(const WarpCtx &, const UData &, uint32_t, uint32_t, uint32_t, uint32_t,
+                                             uint32_t (&)[8]) {}
+};
+
+// One unit per lane: 32 unrolled columns.  The strand selects the row inside the class's row pair through the base
+// address; a deletion-like unit runs as 32 'N' bases with the base address one class (row pair) up, which turns N
+// into O -- so one 16-entry nibble table serves every lane.
+template <bool PACKED, bool SEEN>
+__device__ __forceinline__ void count_unit(const WarpCtx &c, uint32_t meta, const UData &d, int lane, uint32_t (&seen)[8]) {
+  const uint32_t lo = (meta >> 8) & 31u, hi = (meta >> 13) & 63u;
+  const uint32_t ind = (meta >> 21) & 3u;
+  // an empty lane (hi == 0) still issues its 32 zero adds: give it a window / strand of its own in the dump rows
+  const uint32_t w = hi ? ((meta >> 4) & 15u) : ((uint32_t)lane & 15u);
+  const uint32_t strand = hi ? ((meta >> 19) & 1u) : ((uint32_t)lane >> 4);
+  const uint32_t del = (meta >> 20) & 1u;
+  uint32_t vm = hi ? ((0xffffffffu >> (32u - hi)) & (0xffffffffu << lo)) : 0u;
+  if (ind) vm &= ~(1u << (hi - 1u));
+  const uint32_t sb = w * 132u;
+  const uint32_t hs = c.hist_s + sb + strand * K1_ROW_BYTES + del * (2u * K1_ROW_BYTES);
+  const uint32_t ds = c.dup_s + sb;
+  BaseLoop<PACKED, SEEN, 0>::run(c, d, hs, vm, ds, c.lut_s + 64u + del * 64u, seen);
+  if (ind) {  // last base of the op, followed by an insertion / deletion: class I / D instead of its letter
+    const uint32_t v = PACKED ? ((1u << K1_CNT_SHIFT) | d.qlast) : d.qlast;
+    if (v >= c.thr) {
+      const uint32_t cls = ind == 2u ? (uint32_t)LS_CLASS_D : (uint32_t)LS_CLASS_I;
+      const uint32_t jl = hi - 1u;
+      const uint32_t addr = c.hist_s + (cls * 2u + strand) * K1_ROW_BYTES + sb + 4u * jl;
+      if (PACKED) {
+        red_shared_add(addr, v);
+      } else {
+        red_shared_add(addr, 1u);
+        red_shared_add(addr + (uint32_t)K1_CROWS * K1_ROW_BYTES, v);
+      }
+      if (SEEN) {
+        const uint32_t r = jl >> 2, sh = 8u * (jl & 3u);
+        uint32_t sw = 0u;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) colb[j] = (uint32_t)((((a4 + j) & 3) * (LS_TILE / 4)) + ((a4 + j) >> 2)) * 4u;
-            const uint32_t mq4 = (uint32_t)a.min_bq * 0x01010101u;
-            for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < yw; g += 128u) {
-              const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
-              const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
-              const int d0 = (int)(g - ya);  // index inside the piece of this word's byte 0 (< 0 in the head word)
-              // bit 8j+7 <=> quality of byte j >= min_bq   ((q|0x80) >= 128 >= min_bq: no borrow between bytes)
-              uint32_t okm = (((w | 0x80808080u) - mq4) | w) & 0x80808080u;
-              const int hi = (int)(yw - g);
-              if (d0 < 0 || hi < 4) {  // head / tail word
-                uint32_t m = 0xffffffffu;
-                if (d0 < 0) m <<= 8 * (-d0);
-                if (hi < 4) m &= 0xffffffffu >> (8 * (4 - hi));
-                okm &= m;
-              }
-              const int c4 = (sbase + d0) >> 2;  // site of byte 0, divided by 4 (arithmetic shift: -1 in the head word)
-              const uint32_t rowb = strand + (uint32_t)c4 * 4u;
+        for (int i = 0; i < 8; ++i) sw = (uint32_t)i == r ? seen[i] : sw;
+        const uint32_t bsh = (1u << cls) << sh;
+        const uint32_t dv = ((sw & bsh) ? 1u : 0u) + ((sw & (0xffu << sh)) ? 65536u : 0u);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                // 16-entry table: every lane pair reads the same word (broadcast) or different banks -> conflict-free
-                uint32_t off = sm.lut2[(h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u];
-                if (!((okm >> (8 * j + 7)) & 1u)) off = K1_DUMP_OFF;
-                const uint32_t q = (w >> (8 * j)) & 255u;
-                const uint32_t addr = rowb + colb[j] + off;
-                if (PACKED) {
-                  red_shared_add(addr, (1u << K1_CNT_SHIFT) | q);
-                } else {
-                  red_shared_add(addr, 1u);
-                  red_shared_add(addr + (uint32_t)K1_ROWS * LS_TILE * 4u, q);
-                }
-                if (SEEN) {
-                  if (off != K1_DUMP_OFF) {  // same-cell duplicate marks; (site & 3) and the column are warp-uniform per j
-                    const int tj = a4 + j;
-                    const int sh = 8 * (tj & 3);
-                    const uint32_t cls = off / K1_CLASS_STRIDE;
-                    const uint32_t bit = (1u << cls) << sh;
-                    const uint32_t old = atomicOr(&seen[c4 + (tj >> 2)], bit);
-                    const uint32_t dcol = (uint32_t)(c4 + (int)(colb[j] >> 2));
-                    if ((old & bit) && cls < 6u) atomicAdd(&sm.dupcc[0][0] + (cls % 3u) * LS_TILE + dcol, 1u << (16u * (cls / 3u)));
-                    if ((old >> sh) & 255u) atomicAdd(&sm.dupnc[dcol], 1u);
-                  }
-                }
-              }
-            }
-          } else {
-            for (uint32_t g = (ya & ~3u) + 4u * (uint32_t)lane; g < yw; g += 128u) {
-              const uint32_t w = *reinterpret_cast<const uint32_t *>(qual + g);
-              const uint32_t h = *reinterpret_cast<const uint16_t *>(seq4 + (g >> 1));
-              const int sg = sbase + (int)(g - ya);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t q = (w >> (8 * j)) & 255u;
-                const bool ok = (int)q >= a.min_bq && (g + (uint32_t)j >= ya) && (g + (uint32_t)j < yw);
-                const uint32_t code = (h >> (8 * (j >> 1) + ((j & 1) ? 0 : 4))) & 15u;
-                const int cls = class_of_code(code);
-                if (ok && cls != LS_CLASS_NA) {
-                  if (COUNTED)
-                    add_entry<PACKED, SEEN>(sm, seen, sg + j, cls, q, strand);
-                  else
-                    add_uncounted<PACKED>(sm, sg + j, cls);
-                }
-              }
-            }
-          }
-          if (ind != 0 && ylast < ybl && lane == 0) {  // last base of the op, followed by an insertion / deletion
-            const uint32_t q = qual[ylast];
-            if ((int)q >= a.min_bq) {
-              if (COUNTED)
-                add_entry<PACKED, SEEN>(sm, seen, sbase + (int)(ylast - ya), indcls, q, strand);
-              else
-                add_uncounted<PACKED>(sm, sbase + (int)(ylast - ya), indcls);
-            }
-          }
-          // query positions past the stored sequence (malformed record): base 'N', quality 0
-          if (yb > lq && a.min_bq <= 0) {
-            for (uint32_t qp = (ya > lq ? ya : lq) + (uint32_t)lane; qp < yb; qp += 32u) {
-              const int cls = (qp == ylast) ? indcls : LS_CLASS_N;
-              if (COUNTED)
-                add_entry<PACKED, SEEN>(sm, seen, sbase + (int)(qp - ya), cls, 0u, strand);
-              else
-                add_uncounted<PACKED>(sm, sbase + (int)(qp - ya), cls);
-            }
-          }
-        }
+        for (int i = 0; i < 8; ++i) seen[i] = (uint32_t)i == r ? (sw | bsh) : seen[i];
+        if (dv) red_shared_add(ds + cls * K1_ROW_BYTES + 4u * jl, dv);
       }
     }
   }
 }
 
+// A unit of a visible-but-uncounted read (no CB tag / supplementary): only the AC pre-gate of
+// BaseCellCounter.py:165-174,221 sees it.  Rare (--min_ac > 0 only): plain loop, bytes straight from memory.
 template <bool PACKED>
-__global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a) {
+__device__ __noinline__ void count_unit_uncounted(const uint8_t *__restrict__ qual, const uint8_t *__restrict__ seq4,
+                                                  int min_bq, TileSmemT<PACKED> &sm, uint2 u) {
+  const uint32_t meta = u.y;
+  const uint32_t w = (meta >> 4) & 15u, lo = (meta >> 8) & 31u, hi = (meta >> 13) & 63u;
+  const uint32_t ind = (meta >> 21) & 3u;
+  const bool virt = (meta & UM_VIRT) != 0, del = (meta & UM_DEL) != 0;
+  const int64_t q = (int64_t)(((uint64_t)(meta & 15u) << 32) | u.x);
+  for (uint32_t j = lo; j < hi; ++j) {
+    const int64_t qi = del ? q : q + (int64_t)(j - lo);
+    const uint32_t qv = virt ? 0u : qual[qi];
+    if ((int)qv < min_bq) continue;
+    int cls;
+    if (ind && j == hi - 1u)
+      cls = ind == 2u ? LS_CLASS_D : LS_CLASS_I;
+    else if (del)
+      cls = LS_CLASS_O;
+    else if (virt)
+      cls = LS_CLASS_N;
+    else
+      cls = class_of_code((qi & 1) ? (uint32_t)(seq4[qi >> 1] >> 4) : (seq4[qi >> 1] & 15u));  // nibble-swapped copy
+    if (cls == LS_CLASS_NA) continue;
+    const int s = (int)(w * 32u + j);
+    const bool alt = (cls == LS_CLASS_D || cls == LS_CLASS_I) || (cls != LS_CLASS_O && class_letter(cls) != sm.ref[s]);
+    if (alt) atomicAdd(&sm.acx[k1_col(s)], 1u);
+  }
+}
+
+// ---- sorted segments -> unit streams ---------------------------------------------------------------------------
+// Class of sorted segment i: 2 = visible-but-uncounted read, 1 = member of a same-(tile, cell) run, 0 = single.
+__device__ __forceinline__ int segment_class(const uint64_t *__restrict__ keys, int64_t i, int64_t n, uint64_t cmask,
+                                             uint64_t unc) {
+  const uint64_t k = keys[i];
+  if ((k & cmask) == unc) return 2;
+  if ((i > 0 && keys[i - 1] == k) || (i + 1 < n && keys[i + 1] == k)) return 1;
+  return 0;
+}
+
+__global__ void __launch_bounds__(256) classify_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                       const Segment *__restrict__ segs, int64_t n, uint64_t cmask,
+                                                       uint64_t unc, uint32_t *__restrict__ nu_s,
+                                                       uint32_t *__restrict__ nu_m, uint32_t *__restrict__ nu_u) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) {  // the arrays have n + 1 entries: after the exclusive scans entry n holds the stream size
+    nu_s[n] = 0u;
+    nu_m[n] = 0u;
+    if (nu_u) nu_u[n] = 0u;
+    return;
+  }
+  const int cls = segment_class(keys, i, n, cmask, unc);
+  const uint32_t nu = segs[vals[i]].np_nu >> 16;
+  nu_s[i] = cls == 0 ? nu : 0u;
+  nu_m[i] = cls == 1 ? nu : 0u;
+  if (nu_u) nu_u[i] = cls == 2 ? nu : 0u;
+}
+
+struct ExpandArgs {
+  const uint64_t *keys;
+  const uint32_t *vals;
+  const Segment *segs;
+  const Piece *pieces;
+  int64_t n;
+  uint64_t cmask, unc;
+  const uint32_t *offs_s, *offs_m, *offs_u;
+  const uint64_t *tot_s, *tot_m;
+  uint2 *units;
+};
+
+// The units of one segment, piece by piece, window by window.  f(window, unit) places them.
+template <typename F>
+__device__ __forceinline__ void segment_units(const ExpandArgs &a, int64_t i, F &&f) {
+  const uint4 r = *reinterpret_cast<const uint4 *>(a.segs + a.vals[i]);
+  const uint32_t p0 = r.x, np = r.y & 0xffffu;
+  const uint64_t boff = (uint64_t)r.z << 4;
+  const uint32_t strand = r.w & 1u;
+  const uint2 *pp = reinterpret_cast<const uint2 *>(a.pieces) + p0;
+  uint2 pc = np ? __ldg(pp) : make_uint2(0u, 0u);
+  for (uint32_t k = 0; k < np; ++k) {
+    const uint2 cur = pc;
+    if (k + 1u < np) pc = __ldg(pp + k + 1u);
+    const uint32_t meta = cur.y;
+    const uint32_t col = meta & 511u, len = (meta >> 9) & 1023u, ind = (meta >> 20) & 3u;
+    const uint32_t del = (meta >> 19) & 1u, virt = (meta >> 22) & 1u;
+    const uint64_t g0 = boff + cur.x;
+    const uint32_t wa = col >> 5, wb = (col + len - 1u) >> 5;
+    const uint32_t common = (strand << 19) | (del << 20) | (virt << 23);
+    for (uint32_t w = wa; w <= wb; ++w) {
+      const uint32_t lo_s = col > 32u * w ? col : 32u * w;
+      const uint32_t hi_s = (col + len) < 32u * w + 32u ? (col + len) : 32u * w + 32u;
+      const uint64_t q = del ? g0 : g0 + (lo_s - col);
+      uint32_t um = common | (uint32_t)(q >> 32) | (w << 4) | ((lo_s - 32u * w) << 8) | ((hi_s - 32u * w) << 13);
+      if (w == wb) um |= ind << 21;
+      f(w, make_uint2((uint32_t)q, um));
+    }
+  }
+}
+
+// One thread per run start (a single segment is a run of one): the run's units go to its place in its stream; the
+// units of a same-cell run are written window-major (all units of window 0, then window 1, ...), the first unit of
+// each window group flagged, so that the count kernel can give a whole (cell, window) group to one lane.
+__global__ void __launch_bounds__(256) expand_kernel(ExpandArgs a) {
+  __shared__ uint32_t cnt[16][256];  // per thread: units per window of its run, then the write cursors
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const uint64_t key = a.keys[i];
+  const bool isunc = (key & a.cmask) == a.unc;
+  if (isunc && !a.offs_u) return;
+  if (!isunc && i > 0 && a.keys[i - 1] == key) return;  // not the first segment of its run
+  int64_t klen = 1;
+  if (!isunc)
+    while (i + klen < a.n && a.keys[i + klen] == key) ++klen;
+  if (klen == 1) {
+    uint2 *q = a.units + (isunc ? *a.tot_s + *a.tot_m + a.offs_u[i] : (uint64_t)a.offs_s[i]);
+    segment_units(a, i, [&](uint32_t, uint2 u) {
+      u.y |= UM_GSTART;
+      *q++ = u;
+    });
+    return;
+  }
+  uint2 *q = a.units + *a.tot_s + a.offs_m[i];
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) cnt[w][t] = 0u;
+  for (int64_t j = i; j < i + klen; ++j) segment_units(a, j, [&](uint32_t w, uint2) { ++cnt[w][t]; });
+  uint32_t run = 0;
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    const uint32_t c = cnt[w][t];
+    cnt[w][t] = run | (c ? 0x80000000u : 0u);  // cursor; top bit = the next unit written opens the window group
+    run += c;
+  }
+  for (int64_t j = i; j < i + klen; ++j)
+    segment_units(a, j, [&](uint32_t w, uint2 u) {
+      const uint32_t c = cnt[w][t];
+      if (c & 0x80000000u) u.y |= UM_GSTART;
+      q[c & 0x7fffffffu] = u;
+      cnt[w][t] = (c & 0x7fffffffu) + 1u;
+    });
+}
+
+// first sorted segment at or after i (inside the slot) that starts a run; warp-uniform
+__device__ __forceinline__ uint32_t run_start_at_or_after(const uint64_t *__restrict__ keys, uint32_t i, uint32_t slot_lo,
+                                                          uint32_t slot_hi, int lane) {
+  if (i <= slot_lo) return slot_lo;
+  for (;;) {
+    if (i >= slot_hi) return slot_hi;
+    const uint32_t idx = i + (uint32_t)lane;
+    const bool st = idx >= slot_hi || keys[idx] != keys[idx - 1];
+    const uint32_t m = __ballot_sync(0xffffffffu, st);
+    if (m) return i + (uint32_t)(__ffs(m) - 1);
+    i += 32u;
+  }
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
   const uint32_t part = blockIdx.x;
   const uint32_t pslot = a.part_slot[part];
   if (pslot == 0xffffffffu) return;  // unused entry between the heavy (front) and light (back) parts
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int64_t slot = pslot;
   const uint32_t pk = a.part_k[part];
   const uint32_t nparts = a.slot_nparts[slot];
@@ -321,102 +473,141 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
   const int32_t tile_end = (tile_start + LS_TILE) < a.wend[w] ? (tile_start + LS_TILE) : a.wend[w];
   const uint64_t ref_base = a.wref_off[w] + (uint64_t)(tile_start - a.wstart[w]);
 
-  {  // zero the accumulators, stage the reference bases
-    uint32_t *z = reinterpret_cast<uint32_t *>(&sm);
-    constexpr int NZ = ((PACKED ? K1_ROWS : 2 * K1_ROWS) + 3) * LS_TILE;  // hist + dupcc (dupnc / acx zeroed below)
-    for (int i = threadIdx.x; i < NZ; i += K1_THREADS) z[i] = 0u;
-    for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS) {
+  {  // zero the accumulators, stage the reference bases, build the nibble tables
+    uint4 *z = reinterpret_cast<uint4 *>(&sm);
+    constexpr int NZ = ((PACKED ? K1_CROWS : 2 * K1_CROWS) + 8 + 1) * K1_ROWW / 4;  // hist + dup + acx
+    for (int i = threadIdx.x; i < NZ; i += K1_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS)
       sm.ref[i] = (tile_start + i < tile_end) ? upper_ascii(a.ref[ref_base + i]) : (uint8_t)'N';
-      sm.dupnc[i] = 0u;
-      sm.acx[i] = 0u;
+    if (threadIdx.x < 16) {
+      const int cls = class_of_code((uint32_t)threadIdx.x);
+      sm.lut[threadIdx.x] = cls == LS_CLASS_NA ? K1_DUMP_OFF : (uint32_t)cls * 2u * K1_ROW_BYTES;
+      // deletion-like units run as 'N' one class up (N -> O): their table carries O's bit and dup row
+      const int c0 = cls == LS_CLASS_NA ? -1 : cls, c1 = cls == LS_CLASS_N ? LS_CLASS_O : -1;
+      sm.lut2[0][threadIdx.x] = c0 < 0 ? 0u : ((1u << c0) | (((uint32_t)c0 * K1_ROW_BYTES) << 8));
+      sm.lut2[1][threadIdx.x] = c1 < 0 ? 0u : ((1u << c1) | (((uint32_t)c1 * K1_ROW_BYTES) << 8));
     }
-    if (threadIdx.x < 16)  // BAM nibble code -> byte offset of the class row pair; ignored codes -> dump rows (class 8)
-      sm.lut2[threadIdx.x] = (uint32_t)class_of_code((uint32_t)threadIdx.x) * K1_CLASS_STRIDE;
     if (threadIdx.x == 0) {
-      sm.next = 0;
+      sm.next1 = 0;
+      sm.next2 = 0;
+      sm.next3 = 0;
       sm.npass = 0;
       sm.ticket = 0;
     }
   }
   __syncthreads();
 
-  const uint64_t cmask = (1ull << a.cell_bits) - 1ull;
-  const uint64_t unc = (uint64_t)a.uncounted_key;
-  uint32_t *seen = sm.seen[warp];
-  const uint32_t hist_s = (uint32_t)__cvta_generic_to_shared(&sm.hist[0][0]);
-  const uint32_t nmine = my_hi - my_lo;
-  for (;;) {
-    // guided self-scheduling: grab ~1/(2*warps) of what is left (<= 32 segments, >= 2), so that the
-    // last grabs are small and the warps of the CTA reach the barrier together
-    uint32_t g = 0, chunk = 0;
-    if (lane == 0) {
-      const uint32_t seen_next = *(volatile uint32_t *)&sm.next;
-      const uint32_t left = seen_next < nmine ? nmine - seen_next : 0u;
-      chunk = left / (2u * K1_WARPS);
-      chunk = chunk < 2u ? 2u : (chunk > 32u ? 32u : chunk);
-      g = atomicAdd(&sm.next, chunk);
-    }
-    g = __shfl_sync(0xffffffffu, g, 0);
-    chunk = __shfl_sync(0xffffffffu, chunk, 0);
-    if (g >= nmine) break;
-    const uint32_t ca = my_lo + g;
-    const uint32_t cb = (ca + chunk) < my_hi ? (ca + chunk) : my_hi;
-    const int n = (int)(cb - ca);
-    // lane j < n owns segment ca + j: key, "starts a run" flag, record + read metadata
-    uint64_t ck = ~0ull;
-    bool start = false;
-    SegMeta mm = {};
-    if (lane < n) {
-      const uint32_t i = ca + (uint32_t)lane;
-      ck = a.keys[i] & cmask;
-      start = (i == slot_lo) || ck == unc || (a.keys[i - 1] & cmask) != ck;
-      mm = load_meta(a, i);
-      // lane-parallel warm-up for the 32 segments of the chunk: the first piece, and the first lines of the
-      // qualities / bases it points at, are pulled towards the SM while earlier segments are being processed
-      if (a.prefetch) {
-        const uint64_t qb = mm.boff + (uint64_t)mm.y0;
-        const uint8_t *q = a.qual + qb;
-        const uint8_t *sq = a.seq4 + (qb >> 1);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(sq));
-        if (a.prefetch & 16) asm volatile("prefetch.global.L1 [%0];" ::"l"(a.pieces + mm.p0));
-        if (a.prefetch & 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.pieces + mm.p0));
-        if ((a.prefetch & 15) >= 2) {
-          // the remaining lines of the segment's query bytes (typically ~200 qualities, ~100 base bytes)
-          const uint32_t qe = ((uint32_t)(qb & 127u) + mm.qlen) >> 7;          // extra quality lines
-          const uint32_t se = ((uint32_t)((qb >> 1) & 127u) + (mm.qlen >> 1)) >> 7;  // extra base lines
-          for (uint32_t l = 1; l <= qe && l <= (uint32_t)(a.prefetch & 15); ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + 128u * l));
-          for (uint32_t l = 1; l <= se && l <= (uint32_t)(a.prefetch & 15); ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(sq + 128u * l));
+  WarpCtx c;
+  c.hist_s = (uint32_t)__cvta_generic_to_shared(&sm.hist[0][0]);
+  c.lut_s = (uint32_t)__cvta_generic_to_shared(&sm.lut[0]);
+  c.dup_s = (uint32_t)__cvta_generic_to_shared(&sm.dup[0][0]);
+  {
+    const int mq = a.min_bq < 0 ? 0 : (a.min_bq > 256 ? 256 : a.min_bq);
+    c.thr = PACKED ? ((1u << K1_CNT_SHIFT) + (uint32_t)mq) : (uint32_t)mq;
+    c.cnt1 = a.cnt1;
+  }
+  uint32_t seen[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) seen[i] = 0u;
+
+  // ---- phase 1: the part's single-segment units, one unit per lane and step ------------------------------------
+  {
+    const uint32_t u_lo = a.offs_s[my_lo];
+    const uint32_t nun = a.offs_s[my_hi] - u_lo;
+    const uint2 *us = a.units + u_lo;
+    for (;;) {
+      // guided self-scheduling: a grab is G batches of 32 units, G shrinking towards the end of the stream so that
+      // the warps of the CTA finish together
+      uint32_t g = 0, G = 0;
+      if (lane == 0) {
+        const uint32_t seen_next = *(volatile uint32_t *)&sm.next1;
+        const uint32_t left = seen_next < nun ? nun - seen_next : 0u;
+        G = left / (64u * K1_WARPS);
+        G = G < 1u ? 1u : (G > 8u ? 8u : G);
+        g = atomicAdd(&sm.next1, 32u * G);
+      }
+      g = __shfl_sync(0xffffffffu, g, 0);
+      G = __shfl_sync(0xffffffffu, G, 0);
+      if (g >= nun) break;
+      uint32_t k = g + (uint32_t)lane;
+      uint2 u0 = k < nun ? __ldg(us + k) : make_uint2(0u, 0u);
+      UData d0 = load_unit(a, u0);
+      for (uint32_t b = 0; b < G; ++b) {
+        uint2 u1 = make_uint2(0u, 0u);
+        UData d1 = d0;
+        if (b + 1u < G) {
+          if (k + 32u < nun) u1 = __ldg(us + k + 32u);
+          d1 = load_unit(a, u1);
         }
+        count_unit<PACKED, false>(c, u0.y, d0, lane, seen);
+        u0 = u1;
+        d0 = d1;
+        k += 32u;
       }
     }
-    const uint32_t startmask = __ballot_sync(0xffffffffu, start);
-    uint32_t rem = startmask;
-    while (rem) {
-      const int j0 = __ffs(rem) - 1;
-      rem &= rem - 1;
-      const int j1 = rem ? (__ffs(rem) - 1) : n;
-      const uint64_t rk = __shfl_sync(0xffffffffu, ck, j0);
-      const bool counted = rk != unc;
-      // a run that reaches the end of the chunk continues into the following segments of the tile
-      uint32_t ext = 0;
-      if (j1 == n && counted) {
-        while (cb + ext < slot_hi && (a.keys[cb + ext] & cmask) == rk) ++ext;
+  }
+
+  // ---- phase 2: the same-cell runs that start in the part.  A lane takes the (cell, window) groups that start
+  // inside its K consecutive units and follows the last one to its end ---------------------------------------
+  {
+    uint32_t r_lo = my_lo, r_hi = my_hi;
+    if (nparts > 1) {
+      r_lo = run_start_at_or_after(a.keys, my_lo, slot_lo, slot_hi, lane);
+      r_hi = run_start_at_or_after(a.keys, my_hi, slot_lo, slot_hi, lane);
+    }
+    const uint32_t m_lo = a.offs_m[r_lo];
+    const uint32_t nM = a.offs_m[r_hi] - m_lo;
+    const uint2 *um = a.units + *a.tot_s + m_lo;
+    for (;;) {
+      uint32_t g = 0, K = 0;
+      if (lane == 0) {
+        const uint32_t seen_next = *(volatile uint32_t *)&sm.next2;
+        const uint32_t left = seen_next < nM ? nM - seen_next : 0u;
+        K = left / (64u * K1_WARPS);
+        K = K < 4u ? 4u : (K > 32u ? 32u : K);
+        g = atomicAdd(&sm.next2, 32u * K);
       }
-      const uint32_t runlen = (uint32_t)(j1 - j0) + ext;
-      if (runlen == 1) {
-        if (counted)
-          process_segment_fast<PACKED, false, true>(a, sm, seen, shfl_meta(mm, j0), lane, hist_s);
-        else
-          process_segment_fast<PACKED, false, false>(a, sm, seen, shfl_meta(mm, j0), lane, hist_s);
-      } else {
-        for (int q = lane; q < LS_TILE / 4; q += 32) seen[q] = 0u;
-        __syncwarp();
-        for (int j = j0; j < j1; ++j)
-          process_segment_fast<PACKED, true, true>(a, sm, seen, shfl_meta(mm, j), lane, hist_s);
-        for (uint32_t e = 0; e < ext; ++e)
-          process_segment_fast<PACKED, true, true>(a, sm, seen, load_meta(a, cb + e), lane, hist_s);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      K = __shfl_sync(0xffffffffu, K, 0);
+      if (g >= nM) break;
+      uint32_t p = g + (uint32_t)lane * K;          // next unit to look at
+      const uint32_t pend = p + K;                  // groups that start at or after pend belong to someone else
+      bool done = p >= nM, started = false;
+      uint2 u0 = done ? make_uint2(0u, 0u) : __ldg(um + p);
+      UData d0 = load_unit(a, u0);
+      while (__any_sync(0xffffffffu, !done)) {
+        uint2 u1 = make_uint2(0u, 0u);
+        if (!done && p + 1u < nM) u1 = __ldg(um + p + 1u);
+        UData d1 = load_unit(a, u1);
+        const bool gs = (u0.y & UM_GSTART) != 0u;
+        if (!done && gs && p >= pend) done = true;
+        if (!done && gs) {
+          started = true;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) seen[i] = 0u;
+        }
+        count_unit<PACKED, true>(c, (!done && started) ? u0.y : 0u, d0, lane, seen);
+        if (!done) {
+          ++p;
+          if (p >= nM) done = true;
+        }
+        u0 = u1;
+        d0 = d1;
       }
+    }
+  }
+
+  // ---- phase 3: visible-but-uncounted reads (only emitted when --min_ac > 0) ---------------------------------
+  if (a.offs_u) {
+    const uint32_t u_lo = a.offs_u[my_lo], u_hi = a.offs_u[my_hi];
+    const uint2 *uu = a.units + *a.tot_s + *a.tot_m + u_lo;
+    const uint32_t nun = u_hi - u_lo;
+    for (;;) {
+      uint32_t g = 0;
+      if (lane == 0) g = atomicAdd(&sm.next3, 32u);
+      g = __shfl_sync(0xffffffffu, g, 0);
+      if (g >= nun) break;
+      if (g + (uint32_t)lane < nun) count_unit_uncounted<PACKED>(a.qual, a.seq4, a.min_bq, sm, __ldg(uu + g + lane));
     }
   }
   __syncthreads();
@@ -439,31 +630,36 @@ __global__ void __launch_bounds__(K1_THREADS, 4) pileup_count_kernel(CountArgs a
       __threadfence();
     }
     for (int s = threadIdx.x; s < LS_TILE; s += K1_THREADS) {
-      const int sidx = swz(s);
       const uint8_t rb = sm.ref[s];
+      const int sc = k1_col(s);
       uint32_t dp = 0, nc = 0, ac = 0;
       uint32_t f[8], r[8], bq[6], cc[6];
       if (pass_no == 0) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           if (PACKED) {
-            const uint32_t hf = sm.hist[k * 2][sidx], hr = sm.hist[k * 2 + 1][sidx];
+            const uint32_t hf = sm.hist[k * 2][sc], hr = sm.hist[k * 2 + 1][sc];
             f[k] = hf >> K1_CNT_SHIFT;
             r[k] = hr >> K1_CNT_SHIFT;
             if (k < 6) bq[k] = (hf & ((1u << K1_CNT_SHIFT) - 1u)) + (hr & ((1u << K1_CNT_SHIFT) - 1u));
           } else {
-            f[k] = sm.hist[k * 2][sidx];
-            r[k] = sm.hist[k * 2 + 1][sidx];
-            if (k < 6) bq[k] = sm.hist[K1_ROWS + k * 2][sidx] + sm.hist[K1_ROWS + k * 2 + 1][sidx];
+            f[k] = sm.hist[k * 2][sc];
+            r[k] = sm.hist[k * 2 + 1][sc];
+            if (k < 6) bq[k] = sm.hist[K1_CROWS + k * 2][sc] + sm.hist[K1_CROWS + k * 2 + 1][sc];
           }
           dp += f[k] + r[k];
         }
         nev += dp;
-        nc = dp - sm.dupnc[sidx];
+        uint32_t dnc = 0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cc[k] = f[k] + r[k] - ((sm.dupcc[k % 3][sidx] >> (16 * (k / 3))) & 0xffffu);
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t dw = sm.dup[k][sc];
+          dnc += dw >> 16;
+          if (k < 6) cc[k] = f[k] + r[k] - (dw & 0xffffu);
+        }
+        nc = dp - dnc;
         if (a.min_ac > 0) {
-          ac = sm.acx[sidx] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
+          ac = sm.acx[sc] + f[LS_CLASS_I] + r[LS_CLASS_I] + f[LS_CLASS_D] + r[LS_CLASS_D];
           const int base_cls[5] = {LS_CLASS_A, LS_CLASS_C, LS_CLASS_T, LS_CLASS_G, LS_CLASS_N};
 #pragma unroll
           for (int j = 0; j < 5; ++j)

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
                 uint32_t code = 15u;
                 if (qpos < lq) {
                   uint32_t bb = a.seq4[(boff + qpos) >> 1];
-                  code = (qpos & 1u) ? (bb & 15u) : (bb >> 4);
+                  code = (qpos & 1u) ? (bb >> 4) : (bb & 15u);  // device copy is nibble-swapped (ls_ctx::seq4_d)
                 }
                 cls = class_of_code(code);
               } else
@@ -324,8 +324,8 @@ extern "C" int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int
   a.cigar_off = ctx->cigar_off.as<uint32_t>();
   a.cigar = ctx->cigar.as<uint32_t>();
   a.base_off = ctx->base_off.as<uint64_t>();
-  a.seq4 = ctx->seq4.as<uint8_t>();
-  a.qual = ctx->qual.as<uint8_t>();
+  a.seq4 = ctx->seq4_d();
+  a.qual = ctx->qual_d();
   a.site_key = ctx->g_a.as<uint64_t>();
   a.alt_class = ctx->g_b.as<uint8_t>();
   a.site_bin = ctx->g_e.as<uint32_t>();

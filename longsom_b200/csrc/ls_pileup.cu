@@ -130,6 +130,8 @@ static SegArgs make_seg_args(ls_ctx *ctx, const ls_count_params &p, bool emit_un
   a.mapq = ctx->mapq.as<uint8_t>();
   a.cigar_off = ctx->cigar_off.as<uint32_t>();
   a.cigar = ctx->cigar.as<uint32_t>();
+  a.base_off = ctx->base_off.as<uint64_t>();
+  a.lq = ctx->lq.as<int32_t>();
   a.n_windows = ctx->n_windows;
   a.wtid = ctx->wtid.as<int32_t>();
   a.wstart = ctx->wstart.as<int32_t>();
@@ -178,8 +180,11 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
 
   LS_CK(cudaEventRecord(ctx->ev[0], st));
   uint64_t h_tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  uint64_t h_seg[2] = {0, 0};
-  uint64_t *d_seg_totals = reinterpret_cast<uint64_t *>(d_aligned + 8);  // [0] segments, [1] pieces
+  uint64_t h_seg[3] = {0, 0, 0};
+  uint64_t *d_seg_totals = reinterpret_cast<uint64_t *>(d_aligned + 8);  // [0] segments, [1] pieces, [2] units
+  uint64_t *d_tot_s = reinterpret_cast<uint64_t *>(d_aligned + 11);      // sizes of the S / M / U unit streams
+  uint64_t *d_tot_m = reinterpret_cast<uint64_t *>(d_aligned + 12);
+  uint64_t *d_tot_u = reinterpret_cast<uint64_t *>(d_aligned + 13);
   if (n > 0 && ctx->n_windows > 0) {
     ctx->n_drop = 0;
     sa.n_drop = 0;
@@ -210,7 +215,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       ++launches;
       LS_CK(cudaGetLastError());
       LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
-      LS_CK(cudaMemcpyAsync(h_seg, d_seg_totals, 16, cudaMemcpyDeviceToHost, st));
+      LS_CK(cudaMemcpyAsync(h_seg, d_seg_totals, 24, cudaMemcpyDeviceToHost, st));
       LS_CK(cudaStreamSynchronize(st));
       bool again = false;
       if (want_wcount) {
@@ -235,12 +240,12 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       if (!again) break;
       if (attempt >= 3) LS_FAIL(LS_E_STATE, "ls_pileup_run: segment builder did not converge");
       LS_CK(cudaMemsetAsync(d_aligned, 0, 8, st));
-      LS_CK(cudaMemsetAsync(d_seg_totals, 0, 16, st));
+      LS_CK(cudaMemsetAsync(d_seg_totals, 0, 24, st));
     }
   }
   const int64_t nseg = (int64_t)h_seg[0];
-  if (nseg >= (int64_t)0xffffffffll || h_seg[1] >= 0xffffffffull)
-    LS_FAIL(LS_E_ARG, "ls_pileup_run: more than 2^32 segments or pieces in one batch");
+  if (nseg >= (int64_t)0xffffffffll || h_seg[1] >= 0xffffffffull || h_seg[2] >= 0xffffffffull)
+    LS_FAIL(LS_E_ARG, "ls_pileup_run: more than 2^32 segments, pieces or units in one batch");
   S.n_aligned = (int64_t)h_tot[0];
   S.n_segments = nseg;
   ctx->n_segments = nseg;
@@ -276,6 +281,45 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
         ctx->sorted_keys, nseg, ctx->cell_bits, ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), n_slots,
         ctx->slot_tile.as<int64_t>(), ctx->slot_lo.as<uint32_t>());
     ++launches;
+    {
+      // sorted segments -> unit streams (S: single segments, M: same-cell runs, U: uncounted reads)
+      const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
+      const uint64_t unc = (uint64_t)(uint32_t)(ctx->max_cell + 1);
+      const bool with_u = params->min_ac > 0;
+      LS_CK(ctx->offs_s.ensure((size_t)(nseg + 1) * 4));
+      LS_CK(ctx->offs_m.ensure((size_t)(nseg + 1) * 4));
+      if (with_u) LS_CK(ctx->offs_u.ensure((size_t)(nseg + 1) * 4));
+      LS_CK(ctx->units.ensure((size_t)(h_seg[2] + 1) * 8));
+      uint32_t *os = ctx->offs_s.as<uint32_t>(), *om = ctx->offs_m.as<uint32_t>();
+      uint32_t *ou = with_u ? ctx->offs_u.as<uint32_t>() : nullptr;
+      classify_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, ctx->sorted_vals,
+                                                                          ctx->segs.as<Segment>(), nseg, cmask, unc, os, om, ou);
+      ++launches;
+      LS_CK(ls_scan_exclusive_u32(os, os, nseg + 1, d_tot_s, ctx->scan_tmp, st));
+      LS_CK(ls_scan_exclusive_u32(om, om, nseg + 1, d_tot_m, ctx->scan_tmp, st));
+      launches += 6;
+      if (with_u) {
+        LS_CK(ls_scan_exclusive_u32(ou, ou, nseg + 1, d_tot_u, ctx->scan_tmp, st));
+        launches += 3;
+      }
+      ExpandArgs ea;
+      ea.keys = ctx->sorted_keys;
+      ea.vals = ctx->sorted_vals;
+      ea.segs = ctx->segs.as<Segment>();
+      ea.pieces = ctx->pieces.as<Piece>();
+      ea.n = nseg;
+      ea.cmask = cmask;
+      ea.unc = unc;
+      ea.offs_s = os;
+      ea.offs_m = om;
+      ea.offs_u = ou;
+      ea.tot_s = d_tot_s;
+      ea.tot_m = d_tot_m;
+      ea.units = ctx->units.as<uint2>();
+      expand_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ea);
+      ++launches;
+      LS_CK(cudaGetLastError());
+    }
     LS_CK(cudaEventRecord(ctx->ev[2], st));
 
     LS_CK(ctx->slot_out.ensure((size_t)n_slots * LS_SITE_WORDS * LS_TILE * 4));
@@ -302,15 +346,15 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.slot_done = ctx->slot_done.as<uint32_t>();
     ca.n_parts = d_nparts;
     ca.acbuf = params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr;
-    ca.flag = ctx->flag.as<uint16_t>();
-    ca.pieces = ctx->pieces.as<Piece>();
-    ca.base_off = ctx->base_off.as<uint64_t>();
-    ca.lq = ctx->lq.as<int32_t>();
-    ca.seq4 = ctx->seq4.as<uint8_t>();
-    ca.qual = ctx->qual.as<uint8_t>();
-    ca.segs = ctx->segs.as<Segment>();
+    ca.units = ctx->units.as<uint2>();
+    ca.offs_s = ctx->offs_s.as<uint32_t>();
+    ca.offs_m = ctx->offs_m.as<uint32_t>();
+    ca.offs_u = params->min_ac > 0 ? ctx->offs_u.as<uint32_t>() : nullptr;
+    ca.tot_s = d_tot_s;
+    ca.tot_m = d_tot_m;
+    ca.seq4 = ctx->seq4_d();
+    ca.qual = ctx->qual_d();
     ca.keys = ctx->sorted_keys;
-    ca.vals = ctx->sorted_vals;
     ca.slot_tile = ctx->slot_tile.as<int64_t>();
     ca.slot_lo = ctx->slot_lo.as<uint32_t>();
     ca.n_windows = ctx->n_windows;
@@ -329,12 +373,6 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.min_dp = params->min_dp;
     ca.min_cc = params->min_cc;
     ca.min_ac = params->min_ac;
-    {
-      // chunk-level L2 prefetch policy of the count kernel: low 4 bits = query-byte lines per segment (0 = off),
-      // 32 = also the segment's first piece line.  Measured on C2: 17.4 ms off, 16.7 ms with the default.
-      const char *e = getenv("LS_K1_PREFETCH");
-      ca.prefetch = e ? atoi(e) : 36;
-    }
     if (!ctx->k1_attr_set) {
       LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(TileSmemT<true>)));
@@ -343,6 +381,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       ctx->k1_attr_set = true;
     }
     // 12-bit packed counters unless some cell has > K1_MAX_RUN_PACKED reads in one tile
+    ca.cnt1 = packed ? (1u << K1_CNT_SHIFT) : 0u;
     if (packed)
       pileup_count_kernel<true><<<(unsigned)max_parts, K1_THREADS, sizeof(TileSmemT<true>), st>>>(ca);
     else

@@ -17,6 +17,8 @@ struct SegArgs {
   const uint16_t *flag;
   const uint8_t *mapq;
   const uint32_t *cigar_off, *cigar;
+  const uint64_t *base_off;
+  const int32_t *lq;
   int64_t n_windows;
   const int32_t *wtid, *wstart, *wend;
   const int64_t *wtile_base;
@@ -56,7 +58,7 @@ __device__ __forceinline__ bool is_dropped(const SegArgs &a, int64_t w, uint32_t
 }
 
 struct WalkOut {
-  uint32_t nseg, npiece;
+  uint32_t nseg, npiece, nunit;
   uint64_t aligned;
   int32_t end;
   int64_t wfirst;  // first_window(tid, pos) when the walk happened to look it up, else -1
@@ -79,7 +81,7 @@ struct SegStage {
   Piece piece[SEG_STAGE_PIECES];
   uint64_t tile[SEG_STAGE_SEGS];
   uint32_t p0[SEG_STAGE_SEGS];  // first piece of the segment, relative to the read
-  uint32_t y0[SEG_STAGE_SEGS], y1[SEG_STAGE_SEGS];  // query extent of the segment's pieces
+  uint32_t nu[SEG_STAGE_SEGS];  // 32-base units of the segment's pieces
 };
 
 // A window cached in registers while the read stays inside it.
@@ -108,11 +110,14 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
   const uint32_t k0 = a.cigar_off[r], kend = a.cigar_off[r + 1];
   const int32_t tid = a.tid[r];
   const uint32_t flag = a.flag[r];
+  const uint64_t boff = a.base_off[r];
+  const uint32_t lq = (uint32_t)a.lq[r];
   int32_t x = a.pos[r];
   uint32_t y = 0;
   WalkOut o;
   o.nseg = 0;
   o.npiece = 0;
+  o.nunit = 0;
   o.aligned = 0;
   o.wfirst = -1;
   const bool engine_ok = read_passes_engine(flag, a.mapq[r], a.min_mq) && tid >= 0;
@@ -125,7 +130,32 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
   cur.ws = cur.we = 0;
   cur.tb = 0;
   int64_t last_tile = -1;
-  uint32_t seg_p0 = 0, seg_y0 = 0, seg_y1 = 0;
+  uint32_t seg_p0 = 0, seg_nu = 0;
+  auto close_segment = [&]() {  // the segment that ends here: o.nseg - 1
+    if (EMIT) {
+      Segment s;
+      s.p0 = sink.piece_base + seg_p0;
+      s.np_nu = (o.npiece - seg_p0) | (seg_nu << 16);
+      s.boff16 = (uint32_t)(boff >> 4);
+      s.flags = (flag & LS_FLAG_REVERSE) ? 1u : 0u;
+      sink.segs[sink.seg_base + o.nseg - 1] = s;
+    } else if (o.nseg <= (uint32_t)SEG_STAGE_SEGS) {
+      stage->nu[o.nseg - 1] = seg_nu;
+    }
+  };
+  auto put_piece = [&](uint32_t ya, uint32_t col, uint32_t n, uint32_t del, uint32_t ind, uint32_t virt) {
+    Piece p;
+    p.ya = ya;
+    p.meta = piece_meta(col, n, del, ind, virt);
+    if (EMIT)
+      sink.pieces[sink.piece_base + o.npiece] = p;
+    else if (o.npiece < (uint32_t)SEG_STAGE_PIECES)
+      stage->piece[o.npiece] = p;
+    const uint32_t pu = piece_units(p.meta);
+    seg_nu += pu;
+    o.nunit += pu;
+    ++o.npiece;
+  };
   uint32_t cnext = k0 < kend ? cig[k0] : 0xfu;
   for (uint32_t k = k0; k < kend; ++k) {
     const uint32_t c = cnext;
@@ -171,47 +201,35 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
               const int32_t shi = hi < tend ? hi : tend;
               const int64_t tile = ww.tb + (int64_t)trel;
               if (tile != last_tile) {
+                if (o.nseg > 0) close_segment();
                 if (EMIT) {
-                  if (o.nseg > 0) {
-                    Segment s;
-                    s.read = (uint32_t)r;
-                    s.p0 = sink.piece_base + seg_p0;
-                    s.np = segment_np_word(o.npiece - seg_p0, seg_y0, seg_y1);
-                    s.y0 = seg_y0;
-                    sink.segs[sink.seg_base + o.nseg - 1] = s;
-                  }
                   sink.keys[sink.seg_base + o.nseg] = ((uint64_t)tile << sink.cell_bits) | sink.cell_key;
-                } else {
-                  if (o.nseg > 0 && o.nseg <= (uint32_t)SEG_STAGE_SEGS) {
-                    stage->y0[o.nseg - 1] = seg_y0;
-                    stage->y1[o.nseg - 1] = seg_y1;
-                  }
-                  if (o.nseg < (uint32_t)SEG_STAGE_SEGS) {
-                    stage->tile[o.nseg] = (uint64_t)tile;
-                    stage->p0[o.nseg] = o.npiece;
-                  }
+                } else if (o.nseg < (uint32_t)SEG_STAGE_SEGS) {
+                  stage->tile[o.nseg] = (uint64_t)tile;
+                  stage->p0[o.nseg] = o.npiece;
                 }
                 seg_p0 = o.npiece;
-                seg_y0 = match ? y + (uint32_t)(lo - x) : y;
-                seg_y1 = seg_y0;
+                seg_nu = 0;
                 ++o.nseg;
                 last_tile = tile;
               }
-              if (EMIT || o.npiece < (uint32_t)SEG_STAGE_PIECES) {
-                Piece p;
-                p.ya = match ? y + (uint32_t)(lo - x) : y;
-                p.meta = piece_meta((uint32_t)(lo - tstart), (uint32_t)(shi - lo), match ? 0u : 1u,
-                                    (shi == x + len) ? indcode : 0u);
-                if (EMIT)
-                  sink.pieces[sink.piece_base + o.npiece] = p;
-                else
-                  stage->piece[o.npiece] = p;
+              const uint32_t col = (uint32_t)(lo - tstart), n = (uint32_t)(shi - lo);
+              const uint32_t pind = (shi == x + len) ? indcode : 0u;
+              if (match) {
+                // query bases [ya, ya + n); positions at or past l_qseq do not exist (malformed record): the
+                // pileup engine reports them with quality 0 and base 'N' -> a separate "virtual" piece
+                const uint32_t ya = y + (uint32_t)(lo - x);
+                if (ya + n <= lq) {
+                  put_piece(ya, col, n, 0u, pind, 0u);
+                } else if (ya >= lq) {
+                  put_piece(ya, col, n, 0u, pind, 1u);
+                } else {
+                  put_piece(ya, col, lq - ya, 0u, 0u, 0u);
+                  put_piece(lq, col + (lq - ya), n - (lq - ya), 0u, pind, 1u);
+                }
+              } else {
+                put_piece(y, col, n, 1u, pind, y >= lq ? 1u : 0u);
               }
-              {
-                const uint32_t pe = match ? y + (uint32_t)(shi - x) : y + 1u;
-                seg_y1 = pe > seg_y1 ? pe : seg_y1;
-              }
-              ++o.npiece;
               lo = shi;
             }
           }
@@ -230,24 +248,14 @@ __device__ __forceinline__ WalkOut walk_read(const SegArgs &a, const uint32_t *_
       y += (uint32_t)len;
     }
   }
-  if (EMIT && o.nseg > 0) {
-    Segment s;
-    s.read = (uint32_t)r;
-    s.p0 = sink.piece_base + seg_p0;
-    s.np = segment_np_word(o.npiece - seg_p0, seg_y0, seg_y1);
-    s.y0 = seg_y0;
-    sink.segs[sink.seg_base + o.nseg - 1] = s;
-  }
-  if (!EMIT && o.nseg > 0 && o.nseg <= (uint32_t)SEG_STAGE_SEGS) {
-    stage->y0[o.nseg - 1] = seg_y0;
-    stage->y1[o.nseg - 1] = seg_y1;
-  }
+  if (o.nseg > 0) close_segment();
   o.end = x;
   return o;
 }
 
 // totals[0] = segments, totals[1] = pieces (both keep counting past the capacities, so that the host can
-// size the buffers exactly and relaunch); nothing is written by a warp whose range does not fit.
+// size the buffers exactly and relaunch), totals[2] = 32-base units the pieces expand to; nothing is written by a
+// warp whose range does not fit.
 __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__restrict__ segs, uint64_t *__restrict__ keys,
                                                         Piece *__restrict__ pieces, uint64_t seg_cap, uint64_t piece_cap,
                                                         unsigned long long *__restrict__ totals,
@@ -279,7 +287,7 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
   sink.cell_key = 0;
   sink.cell_bits = a.cell_bits;
   WalkOut o;
-  o.nseg = o.npiece = 0;
+  o.nseg = o.npiece = o.nunit = 0;
   o.aligned = 0;
   o.end = 0;
   SegStage stage;
@@ -343,12 +351,14 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
     sink.cell_key = counted ? (uint64_t)(uint32_t)cell : (uint64_t)a.uncounted_key;
     if (o.nseg <= (uint32_t)SEG_STAGE_SEGS && o.npiece <= (uint32_t)SEG_STAGE_PIECES) {
       for (uint32_t i = 0; i < o.npiece; ++i) pieces[sink.piece_base + i] = stage.piece[i];
+      const uint32_t boff16 = (uint32_t)(a.base_off[r] >> 4);
+      const uint32_t sflags = (a.flag[r] & LS_FLAG_REVERSE) ? 1u : 0u;
       for (uint32_t i = 0; i < o.nseg; ++i) {
         Segment sg;
-        sg.read = (uint32_t)r;
         sg.p0 = sink.piece_base + stage.p0[i];
-        sg.np = segment_np_word((i + 1 < o.nseg ? stage.p0[i + 1] : o.npiece) - stage.p0[i], stage.y0[i], stage.y1[i]);
-        sg.y0 = stage.y0[i];
+        sg.np_nu = ((i + 1 < o.nseg ? stage.p0[i + 1] : o.npiece) - stage.p0[i]) | (stage.nu[i] << 16);
+        sg.boff16 = boff16;
+        sg.flags = sflags;
         segs[sink.seg_base + i] = sg;
         keys[sink.seg_base + i] = (stage.tile[i] << a.cell_bits) | sink.cell_key;
       }
@@ -357,7 +367,12 @@ __global__ void __launch_bounds__(256) seg_build_kernel(SegArgs a, Segment *__re
     }
   }
   uint64_t al = o.aligned;
+  uint32_t nu = o.nunit;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) al += __shfl_xor_sync(0xffffffffu, al, d);
+  for (int d = 16; d > 0; d >>= 1) {
+    al += __shfl_xor_sync(0xffffffffu, al, d);
+    nu += __shfl_xor_sync(0xffffffffu, nu, d);
+  }
   if (lane == 0 && al) atomicAdd(n_aligned, (unsigned long long)al);
+  if (lane == 0 && nu) atomicAdd(&totals[2], (unsigned long long)nu);
 }
