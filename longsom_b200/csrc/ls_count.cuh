@@ -59,6 +59,8 @@ struct CountArgs {
   const uint2 *units;                        // S stream, then M, then U
   const uint32_t *offs_s, *offs_m, *offs_u;  // [nseg + 1] first unit of sorted segment i in its stream (offs_u may be null)
   const uint64_t *tot_s, *tot_m;             // stream sizes (M starts at *tot_s, U at *tot_s + *tot_m)
+  const uint32_t *goffs;                     // [nseg + 1] first (cell, window) group of the runs starting at or after segment i
+  const uint32_t *gdir;                      // [n_groups + 1] first unit (in M) of every group, in run / window order
   const uint64_t *keys;
   const int64_t *slot_tile;
   const uint32_t *slot_lo;
@@ -363,7 +365,9 @@ struct ExpandArgs {
   int64_t n;
   uint64_t cmask, unc;
   const uint32_t *offs_s, *offs_m, *offs_u;
-  const uint64_t *tot_s, *tot_m;
+  const uint64_t *tot_s, *tot_m, *tot_g;
+  const uint32_t *goffs;
+  uint32_t *gdir;
   uint2 *units;
 };
 
@@ -396,6 +400,32 @@ __device__ __forceinline__ void segment_units(const ExpandArgs &a, int64_t i, F 
   }
 }
 
+// Number of (cell, window) groups of every same-cell run, stored at the run's first segment (0 elsewhere): the
+// windows its pieces touch.  Its exclusive scan places the runs in the group directory.
+__global__ void __launch_bounds__(256) rungroups_kernel(ExpandArgs a, uint32_t *__restrict__ ng) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > a.n) return;
+  uint32_t mask = 0u;
+  if (i < a.n) {
+    const uint64_t key = a.keys[i];
+    const bool first = (key & a.cmask) != a.unc && (i == 0 || a.keys[i - 1] != key);
+    if (first && i + 1 < a.n && a.keys[i + 1] == key) {
+      for (int64_t j = i; j < a.n && a.keys[j] == key; ++j) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(a.segs + a.vals[j]);
+        const uint2 *pp = reinterpret_cast<const uint2 *>(a.pieces) + r.x;
+        const uint32_t np = r.y & 0xffffu;
+        for (uint32_t k = 0; k < np; ++k) {
+          const uint32_t meta = __ldg(pp + k).y;
+          const uint32_t col = meta & 511u, len = (meta >> 9) & 1023u;
+          const uint32_t wa = col >> 5, wb = (col + len - 1u) >> 5;
+          mask |= (0xffffu >> (15u - wb)) & (0xffffu << wa);
+        }
+      }
+    }
+  }
+  ng[i] = (uint32_t)__popc(mask);
+}
+
 // One thread per run start (a single segment is a run of one): the run's units go to its place in its stream; the
 // units of a same-cell run are written window-major (all units of window 0, then window 1, ...), the first unit of
 // each window group flagged, so that the count kernel can give a whole (cell, window) group to one lane.
@@ -403,6 +433,7 @@ __global__ void __launch_bounds__(256) expand_kernel(ExpandArgs a) {
   __shared__ uint32_t cnt[16][256];  // per thread: units per window of its run, then the write cursors
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
+  if (i == 0) a.gdir[*a.tot_g] = (uint32_t)*a.tot_m;  // sentinel: end of the last group
   const uint64_t key = a.keys[i];
   const bool isunc = (key & a.cmask) == a.unc;
   if (isunc && !a.offs_u) return;
@@ -418,16 +449,19 @@ __global__ void __launch_bounds__(256) expand_kernel(ExpandArgs a) {
     });
     return;
   }
-  uint2 *q = a.units + *a.tot_s + a.offs_m[i];
+  const uint32_t mbase = a.offs_m[i];
+  uint2 *q = a.units + *a.tot_s + mbase;
   const int t = threadIdx.x;
 #pragma unroll
   for (int w = 0; w < 16; ++w) cnt[w][t] = 0u;
   for (int64_t j = i; j < i + klen; ++j) segment_units(a, j, [&](uint32_t w, uint2) { ++cnt[w][t]; });
   uint32_t run = 0;
+  uint32_t *gd = a.gdir + a.goffs[i];
 #pragma unroll
   for (int w = 0; w < 16; ++w) {
     const uint32_t c = cnt[w][t];
     cnt[w][t] = run | (c ? 0x80000000u : 0u);  // cursor; top bit = the next unit written opens the window group
+    if (c) *gd++ = mbase + run;
     run += c;
   }
   for (int64_t j = i; j < i + klen; ++j)
@@ -547,53 +581,66 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
     }
   }
 
-  // ---- phase 2: the same-cell runs that start in the part.  A lane takes the (cell, window) groups that start
-  // inside its K consecutive units and follows the last one to its end ---------------------------------------
+  // ---- phase 2: the same-cell runs that start in the part.  Every lane works through whole (cell, window) groups,
+  // which it claims one ahead from the part's slice of the group directory ---------------------------------------
   {
     uint32_t r_lo = my_lo, r_hi = my_hi;
     if (nparts > 1) {
       r_lo = run_start_at_or_after(a.keys, my_lo, slot_lo, slot_hi, lane);
       r_hi = run_start_at_or_after(a.keys, my_hi, slot_lo, slot_hi, lane);
     }
-    const uint32_t m_lo = a.offs_m[r_lo];
-    const uint32_t nM = a.offs_m[r_hi] - m_lo;
-    const uint2 *um = a.units + *a.tot_s + m_lo;
-    for (;;) {
-      uint32_t g = 0, K = 0;
-      if (lane == 0) {
-        const uint32_t seen_next = *(volatile uint32_t *)&sm.next2;
-        const uint32_t left = seen_next < nM ? nM - seen_next : 0u;
-        K = left / (64u * K1_WARPS);
-        K = K < 4u ? 4u : (K > 32u ? 32u : K);
-        g = atomicAdd(&sm.next2, 32u * K);
+    const uint32_t g_lo = a.goffs[r_lo];
+    const uint32_t ngr = a.goffs[r_hi] - g_lo;
+    const uint32_t *gd = a.gdir + g_lo;
+    const uint2 *um = a.units + *a.tot_s;
+    const uint32_t lt = (1u << lane) - 1u;
+    // claim the next group for the lanes that ask; a lane that gets none keeps pn == en
+    auto claim = [&](bool want, uint32_t &pn, uint32_t &en) {
+      const uint32_t m = __ballot_sync(0xffffffffu, want);
+      if (m == 0u) return;
+      uint32_t base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(&sm.next2, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (want) {
+        const uint32_t gi = base + (uint32_t)__popc(m & lt);
+        pn = en = 0u;
+        if (gi < ngr) {
+          pn = __ldg(gd + gi);
+          en = __ldg(gd + gi + 1u);
+        }
       }
-      g = __shfl_sync(0xffffffffu, g, 0);
-      K = __shfl_sync(0xffffffffu, K, 0);
-      if (g >= nM) break;
-      uint32_t p = g + (uint32_t)lane * K;          // next unit to look at
-      const uint32_t pend = p + K;                  // groups that start at or after pend belong to someone else
-      bool done = p >= nM, started = false;
-      uint2 u0 = done ? make_uint2(0u, 0u) : __ldg(um + p);
-      UData d0 = load_unit(a, u0);
-      while (__any_sync(0xffffffffu, !done)) {
-        uint2 u1 = make_uint2(0u, 0u);
-        if (!done && p + 1u < nM) u1 = __ldg(um + p + 1u);
-        UData d1 = load_unit(a, u1);
-        const bool gs = (u0.y & UM_GSTART) != 0u;
-        if (!done && gs && p >= pend) done = true;
-        if (!done && gs) {
-          started = true;
+    };
+    uint32_t p = 0, e = 0, pn = 0, en = 0;
+    claim(true, p, e);
+    claim(true, pn, en);
+    uint2 u0 = p < e ? __ldg(um + p) : make_uint2(0u, 0u);
+    UData d0 = load_unit(a, u0);
+    bool fresh = true;  // the unit in hand opens its group
+    while (__any_sync(0xffffffffu, p < e)) {
+      // the unit after this one: the next of the group, or the first of the group claimed ahead
+      const bool last = p + 1u >= e;
+      const uint32_t q = last ? pn : p + 1u;
+      const bool more = last ? (pn < en) : true;
+      uint2 u1 = (p < e && more) ? __ldg(um + q) : make_uint2(0u, 0u);
+      UData d1 = load_unit(a, u1);
+      if (fresh) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) seen[i] = 0u;
-        }
-        count_unit<PACKED, true>(c, (!done && started) ? u0.y : 0u, d0, lane, seen);
-        if (!done) {
-          ++p;
-          if (p >= nM) done = true;
-        }
-        u0 = u1;
-        d0 = d1;
+        for (int i = 0; i < 8; ++i) seen[i] = 0u;
       }
+      count_unit<PACKED, true>(c, u0.y, d0, lane, seen);
+      const bool want = p < e && last;
+      if (p < e) {
+        if (last) {
+          p = pn;
+          e = en;
+        } else {
+          ++p;
+        }
+      }
+      fresh = want;
+      claim(want, pn, en);
+      u0 = u1;
+      d0 = d1;
     }
   }
 

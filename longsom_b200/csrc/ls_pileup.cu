@@ -179,12 +179,13 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   uint32_t *d_capflag = reinterpret_cast<uint32_t *>(d_aligned + 7);
 
   LS_CK(cudaEventRecord(ctx->ev[0], st));
-  uint64_t h_tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t h_tot[16] = {0};
   uint64_t h_seg[3] = {0, 0, 0};
   uint64_t *d_seg_totals = reinterpret_cast<uint64_t *>(d_aligned + 8);  // [0] segments, [1] pieces, [2] units
   uint64_t *d_tot_s = reinterpret_cast<uint64_t *>(d_aligned + 11);      // sizes of the S / M / U unit streams
   uint64_t *d_tot_m = reinterpret_cast<uint64_t *>(d_aligned + 12);
   uint64_t *d_tot_u = reinterpret_cast<uint64_t *>(d_aligned + 13);
+  uint64_t *d_tot_g = reinterpret_cast<uint64_t *>(d_aligned + 14);      // number of (cell, window) groups in M
   if (n > 0 && ctx->n_windows > 0) {
     ctx->n_drop = 0;
     sa.n_drop = 0;
@@ -271,27 +272,21 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
                                                                       (uint64_t)(uint32_t)(ctx->max_cell + 1), d_longrun);
       ++launches;
     }
-    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 48, cudaMemcpyDeviceToHost, st));
-    LS_CK(cudaStreamSynchronize(st));
-    n_slots = (int64_t)h_tot[3];
-    const bool packed = (h_tot[5] & 0xffffffffull) == 0;
-    LS_CK(ctx->slot_tile.ensure((size_t)n_slots * 8));
-    LS_CK(ctx->slot_lo.ensure((size_t)(n_slots + 1) * 4));
-    slot_fill_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(
-        ctx->sorted_keys, nseg, ctx->cell_bits, ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), n_slots,
-        ctx->slot_tile.as<int64_t>(), ctx->slot_lo.as<uint32_t>());
-    ++launches;
+    const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
+    const uint64_t unc = (uint64_t)(uint32_t)(ctx->max_cell + 1);
+    const bool with_u = params->min_ac > 0;
+    uint32_t *os = nullptr, *om = nullptr, *ou = nullptr, *og = nullptr;
+    ExpandArgs ea;
     {
-      // sorted segments -> unit streams (S: single segments, M: same-cell runs, U: uncounted reads)
-      const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
-      const uint64_t unc = (uint64_t)(uint32_t)(ctx->max_cell + 1);
-      const bool with_u = params->min_ac > 0;
+      // sorted segments -> unit streams (S: single segments, M: same-cell runs, U: uncounted reads): sizes first
       LS_CK(ctx->offs_s.ensure((size_t)(nseg + 1) * 4));
       LS_CK(ctx->offs_m.ensure((size_t)(nseg + 1) * 4));
+      LS_CK(ctx->goffs.ensure((size_t)(nseg + 1) * 4));
       if (with_u) LS_CK(ctx->offs_u.ensure((size_t)(nseg + 1) * 4));
-      LS_CK(ctx->units.ensure((size_t)(h_seg[2] + 1) * 8));
-      uint32_t *os = ctx->offs_s.as<uint32_t>(), *om = ctx->offs_m.as<uint32_t>();
-      uint32_t *ou = with_u ? ctx->offs_u.as<uint32_t>() : nullptr;
+      os = ctx->offs_s.as<uint32_t>();
+      om = ctx->offs_m.as<uint32_t>();
+      og = ctx->goffs.as<uint32_t>();
+      ou = with_u ? ctx->offs_u.as<uint32_t>() : nullptr;
       classify_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, ctx->sorted_vals,
                                                                           ctx->segs.as<Segment>(), nseg, cmask, unc, os, om, ou);
       ++launches;
@@ -302,7 +297,6 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
         LS_CK(ls_scan_exclusive_u32(ou, ou, nseg + 1, d_tot_u, ctx->scan_tmp, st));
         launches += 3;
       }
-      ExpandArgs ea;
       ea.keys = ctx->sorted_keys;
       ea.vals = ctx->sorted_vals;
       ea.segs = ctx->segs.as<Segment>();
@@ -315,6 +309,30 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       ea.offs_u = ou;
       ea.tot_s = d_tot_s;
       ea.tot_m = d_tot_m;
+      ea.tot_g = d_tot_g;
+      ea.goffs = og;
+      ea.gdir = nullptr;
+      ea.units = nullptr;
+      rungroups_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(ea, og);
+      ++launches;
+      LS_CK(ls_scan_exclusive_u32(og, og, nseg + 1, d_tot_g, ctx->scan_tmp, st));
+      launches += 3;
+      LS_CK(cudaGetLastError());
+    }
+    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 128, cudaMemcpyDeviceToHost, st));
+    LS_CK(cudaStreamSynchronize(st));
+    n_slots = (int64_t)h_tot[3];
+    const bool packed = (h_tot[5] & 0xffffffffull) == 0;
+    LS_CK(ctx->slot_tile.ensure((size_t)n_slots * 8));
+    LS_CK(ctx->slot_lo.ensure((size_t)(n_slots + 1) * 4));
+    slot_fill_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(
+        ctx->sorted_keys, nseg, ctx->cell_bits, ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), n_slots,
+        ctx->slot_tile.as<int64_t>(), ctx->slot_lo.as<uint32_t>());
+    ++launches;
+    {
+      LS_CK(ctx->units.ensure((size_t)(h_seg[2] + 1) * 8));
+      LS_CK(ctx->gdir.ensure((size_t)(h_tot[14] + 1) * 4));
+      ea.gdir = ctx->gdir.as<uint32_t>();
       ea.units = ctx->units.as<uint2>();
       expand_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ea);
       ++launches;
@@ -352,6 +370,8 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.offs_u = params->min_ac > 0 ? ctx->offs_u.as<uint32_t>() : nullptr;
     ca.tot_s = d_tot_s;
     ca.tot_m = d_tot_m;
+    ca.goffs = ctx->goffs.as<uint32_t>();
+    ca.gdir = ctx->gdir.as<uint32_t>();
     ca.seq4 = ctx->seq4_d();
     ca.qual = ctx->qual_d();
     ca.keys = ctx->sorted_keys;
