@@ -111,7 +111,7 @@ struct ls_ctx {
   DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;
   DBuf drop_keys, rend, wcount, part_slot, part_k, slot_nparts, slot_done, acbuf;
-  DBuf offs_s, offs_m, offs_u, units, goffs, gdir;
+  DBuf offs_s, offs_m, offs_u, units, goffs, gdir, mrank, mlist;
   int64_t n_drop = 0;
   bool k1_attr_set = false;
   int64_t n_segments = 0, n_pieces = 0, n_slots = 0, n_sites = 0;

@@ -92,7 +92,7 @@ struct TileSmemT {
   uint32_t dup[8][K1_ROWW];               // per class: (cell, class) duplicates | (cell) duplicates << 16
   uint32_t acx[K1_ROWW];                  // alt entries of visible-but-uncounted reads (--min_ac > 0)
   alignas(64) uint32_t lut[16];           // BAM nibble code -> byte offset of the class's row pair (dump rows if ignored)
-  uint32_t lut2[2][16];                   // [deletion-like][code] -> class bit | byte offset of the class's dup row << 8
+  uint32_t lut2[2][16];                   // [deletion-like][code] -> 0x80 | class bit (A..D) | byte offset of the class's dup row << 8
   uint8_t ref[LS_TILE];
   uint32_t next1, next2, next3, npass, ticket;
 };
@@ -142,64 +142,82 @@ struct UData {
   uint32_t qlast;  // quality of the base at column hi - 1 (the one that carries a following indel)
 };
 
-__device__ __forceinline__ UData load_unit(const CountArgs &a, uint2 u) {
-  UData d;
+// What a unit's loads return, untouched: the loads are issued one step ahead of their use, so nothing here may depend
+// on the loaded values (the alignment happens in align_unit, at the start of the step that counts the unit).
+struct URaw {
+  uint32_t w[10];  // 40 bytes of qualities from the 8-byte boundary at or below column 0 (deletion-like: w[0] = the byte)
+  uint32_t h[6];   // 24 bytes of base nibbles, likewise
+  uint32_t qlast;
+};
+
+__device__ __forceinline__ URaw issue_unit(const CountArgs &a, uint2 u) {
+  URaw r;
   const uint32_t meta = u.y;
   const uint32_t lo = (meta >> 8) & 31u, hi = (meta >> 13) & 63u;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) d.qw[i] = 0u;
+  for (int i = 0; i < 10; ++i) r.w[i] = 0u;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) d.hw[i] = ~0u;  // 'N': what deletion-like and virtual units run as
-  d.qlast = 0u;
-  if (hi == 0u) return d;  // empty lane
+  for (int i = 0; i < 6; ++i) r.h[i] = 0u;
+  r.qlast = 0u;
+  if (hi == 0u || (meta & UM_VIRT)) return r;  // empty lane / positions past the stored sequence: nothing to load
   const int64_t q = (int64_t)(((uint64_t)(meta & 15u) << 32) | u.x);
-  if (meta & UM_VIRT) {
-    // query positions past the stored sequence: quality 0, base 'N'
-  } else if (meta & UM_DEL) {
-    const uint32_t qv = a.qual[q];
-    const uint32_t q4 = qv * 0x01010101u;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d.qw[i] = q4;
-    d.qlast = qv;
+  if (meta & UM_DEL) {
+    r.w[0] = a.qual[q];
   } else {
     const int64_t q0 = q - (int64_t)lo;  // where column 0 of the window would be (possibly before the read)
-    {
-      const uint8_t *p = a.qual + (q0 & ~(int64_t)7);
-      const uint32_t sh = (uint32_t)q0 & 7u;
-      uint32_t w[10];
+    const uint8_t *pq = a.qual + (q0 & ~(int64_t)7);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        const uint2 t = ldg_v2(p + 8 * i);
-        w[2 * i] = t.x;
-        w[2 * i + 1] = t.y;
-      }
-      const bool o = (sh & 4u) != 0u;
-      uint32_t x[9];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) x[i] = o ? w[i + 1] : w[i];
-      const uint32_t sel = 0x3210u + 0x1111u * (sh & 3u);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) d.qw[i] = prmt_var(x[i], x[i + 1], sel);
+    for (int i = 0; i < 5; ++i) {
+      const uint2 t = ldg_v2(pq + 8 * i);
+      r.w[2 * i] = t.x;
+      r.w[2 * i + 1] = t.y;
     }
-    {
-      const int64_t b0 = q0 >> 1;  // byte of nibble q0 (arithmetic shift: q0 may be slightly negative)
-      const uint8_t *p = a.seq4 + (b0 & ~(int64_t)7);
-      const uint32_t shift = 4u * ((uint32_t)q0 & 15u);
-      uint32_t h[6];
+    const uint8_t *ph = a.seq4 + ((q0 >> 1) & ~(int64_t)7);  // arithmetic shift: q0 may be slightly negative
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const uint2 t = ldg_v2(p + 8 * i);
-        h[2 * i] = t.x;
-        h[2 * i + 1] = t.y;
-      }
-      const bool o = (shift & 32u) != 0u;
-      uint32_t y[5];
-#pragma unroll
-      for (int i = 0; i < 5; ++i) y[i] = o ? h[i + 1] : h[i];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) d.hw[i] = __funnelshift_r(y[i], y[i + 1], shift & 31u);
+    for (int i = 0; i < 3; ++i) {
+      const uint2 t = ldg_v2(ph + 8 * i);
+      r.h[2 * i] = t.x;
+      r.h[2 * i + 1] = t.y;
     }
-    if ((meta >> 21) & 3u) d.qlast = a.qual[q + (int64_t)(hi - 1u - lo)];
+    if ((meta >> 21) & 3u) r.qlast = a.qual[q + (int64_t)(hi - 1u - lo)];
+  }
+  return r;
+}
+
+__device__ __forceinline__ UData align_unit(const URaw &r, uint2 u) {
+  UData d;
+  const uint32_t meta = u.y;
+  const uint32_t lo = (meta >> 8) & 31u;
+  d.qlast = r.qlast;
+  if (meta & (UM_DEL | UM_VIRT)) {
+    // deletion-like units carry one quality on every column and run as 'N' (virtual ones: quality 0)
+    const uint32_t q4 = r.w[0] * 0x01010101u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d.qw[i] = q4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d.hw[i] = ~0u;
+    d.qlast = r.w[0];
+    return d;
+  }
+  const uint32_t q0 = u.x - lo;  // only its low bits matter here
+  {
+    const uint32_t sh = q0 & 7u;
+    const bool o = (sh & 4u) != 0u;
+    uint32_t x[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) x[i] = o ? r.w[i + 1] : r.w[i];
+    const uint32_t sel = 0x3210u + 0x1111u * (sh & 3u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d.qw[i] = prmt_var(x[i], x[i + 1], sel);
+  }
+  {
+    const uint32_t shift = 4u * (q0 & 15u);
+    const bool o = (shift & 32u) != 0u;
+    uint32_t y[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) y[i] = o ? r.h[i + 1] : r.h[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d.hw[i] = __funnelshift_r(y[i], y[i + 1], shift & 31u);
   }
   return d;
 }
@@ -224,24 +242,26 @@ struct BaseLoop {
     constexpr int pos = 4 * (J & 7);  // bit position of column J's nibble in its word
     const uint32_t idx = pos >= 2 ? ((d.hw[J >> 3] >> (pos >= 2 ? pos - 2 : 0)) & 0x3cu) : ((d.hw[J >> 3] << 2) & 0x3cu);
     const uint32_t off = lds_u32(idx | c.lut_s);  // the table is 64-byte aligned
-    uint32_t vz, okm;  // vz = v, okm = 0xff if column J is inside [lo, hi) and v >= thr; else 0
+    uint32_t vz, okm;  // vz = v, okm = 0x3c if column J is inside [lo, hi) and v >= thr; else 0
     asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %3, %4;\n setp.ne.u32 p, t, 0;\n setp.ge.and.u32 p, %2, %5, p;\n"
-        " selp.u32 %0, %2, 0, p;\n selp.u32 %1, 255, 0, p;\n}"
+        " selp.u32 %0, %2, 0, p;\n selp.u32 %1, 60, 0, p;\n}"
         : "=r"(vz), "=r"(okm)
         : "r"(v), "r"(vm), "n"(1u << J), "r"(c.thr));
     const uint32_t addr = hs + off + 4u * J;
     if (PACKED) {
       red_shared_add(addr, vz);
     } else {
-      red_shared_add(addr, okm & 1u);
+      red_shared_add(addr, okm >> 5);
       red_shared_add(addr + QOFF, vz);
     }
     if (SEEN) {
-      const uint32_t w2 = lds_u32(idx | lut2p);  // class bit | dup row offset << 8
-      constexpr int sh = 8 * (J & 3);
-      const uint32_t bsh = (w2 & okm) << sh;
+      // table 2, looked up at code 0 (an ignored code: word 0) when the column does not count:
+      // byte 0 = 0x80 | class bit (classes A..D: bits 0-5), bits 8.. = byte offset of the class's dup row
+      const uint32_t w2 = lds_u32((idx & okm) | lut2p);
+      const uint32_t bsh = prmt_sel<(J & 3) == 0 ? 0x4440u : ((J & 3) == 1 ? 0x4404u : ((J & 3) == 2 ? 0x4044u : 0x0444u))>(w2, 0u);
       const uint32_t sw = seen[J >> 2];
-      const uint32_t dv = ((sw & bsh) ? 1u : 0u) + ((bsh && (sw & (0xffu << sh))) ? 65536u : 0u);
+      // the 0x80 markers meet iff the cell already has an entry at this column; the class bits iff of this class
+      const uint32_t dv = (sw & bsh & 0x3f3f3f3fu) ? 0x10001u : ((sw & bsh) ? 0x10000u : 0u);
       seen[J >> 2] = sw | bsh;
       red_shared_add(ds + (w2 >> 8) + 4u * J, dv);
     }
@@ -288,8 +308,8 @@ __device__ __forceinline__ void count_unit(const WarpCtx &c, uint32_t meta, cons
         uint32_t sw = 0u;
 #pragma unroll
         for (int i = 0; i < 8; ++i) sw = (uint32_t)i == r ? seen[i] : sw;
-        const uint32_t bsh = (1u << cls) << sh;
-        const uint32_t dv = ((sw & bsh) ? 1u : 0u) + ((sw & (0xffu << sh)) ? 65536u : 0u);
+        const uint32_t bsh = (0x80u | (1u << cls)) << sh;  // cls is I or D here
+        const uint32_t dv = (sw & bsh & 0x3f3f3f3fu) ? 0x10001u : ((sw & bsh) ? 0x10000u : 0u);
 #pragma unroll
         for (int i = 0; i < 8; ++i) seen[i] = (uint32_t)i == r ? (sw | bsh) : seen[i];
         if (dv) red_shared_add(ds + cls * K1_ROW_BYTES + 4u * jl, dv);
@@ -341,12 +361,14 @@ __device__ __forceinline__ int segment_class(const uint64_t *__restrict__ keys, 
 __global__ void __launch_bounds__(256) classify_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                        const Segment *__restrict__ segs, int64_t n, uint64_t cmask,
                                                        uint64_t unc, uint32_t *__restrict__ nu_s,
-                                                       uint32_t *__restrict__ nu_m, uint32_t *__restrict__ nu_u) {
+                                                       uint32_t *__restrict__ nu_m, uint32_t *__restrict__ nu_u,
+                                                       uint32_t *__restrict__ is_m) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   if (i == n) {  // the arrays have n + 1 entries: after the exclusive scans entry n holds the stream size
     nu_s[n] = 0u;
     nu_m[n] = 0u;
+    is_m[n] = 0u;
     if (nu_u) nu_u[n] = 0u;
     return;
   }
@@ -354,7 +376,16 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint64_t *__restric
   const uint32_t nu = segs[vals[i]].np_nu >> 16;
   nu_s[i] = cls == 0 ? nu : 0u;
   nu_m[i] = cls == 1 ? nu : 0u;
+  is_m[i] = cls == 1 ? 1u : 0u;
   if (nu_u) nu_u[i] = cls == 2 ? nu : 0u;
+}
+
+// mlist[rank of i among the run members] = i
+__global__ void __launch_bounds__(256) mlist_kernel(const uint64_t *__restrict__ keys, int64_t n, uint64_t cmask, uint64_t unc,
+                                                    const uint32_t *__restrict__ mrank, uint32_t *__restrict__ mlist) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (segment_class(keys, i, n, cmask, unc) == 1) mlist[mrank[i]] = (uint32_t)i;
 }
 
 struct ExpandArgs {
@@ -365,8 +396,9 @@ struct ExpandArgs {
   int64_t n;
   uint64_t cmask, unc;
   const uint32_t *offs_s, *offs_m, *offs_u;
-  const uint64_t *tot_s, *tot_m, *tot_g;
-  const uint32_t *goffs;
+  const uint64_t *tot_s, *tot_m, *tot_g, *tot_ms;  // stream sizes, groups, run-member segments
+  const uint32_t *mlist;                           // sorted indices of the run members, in order
+  uint32_t *goffs;                                 // rungroups: groups per run at its first segment; then scanned
   uint32_t *gdir;
   uint2 *units;
 };
@@ -400,77 +432,134 @@ __device__ __forceinline__ void segment_units(const ExpandArgs &a, int64_t i, F 
   }
 }
 
-// Number of (cell, window) groups of every same-cell run, stored at the run's first segment (0 elsewhere): the
-// windows its pieces touch.  Its exclusive scan places the runs in the group directory.
-__global__ void __launch_bounds__(256) rungroups_kernel(ExpandArgs a, uint32_t *__restrict__ ng) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i > a.n) return;
-  uint32_t mask = 0u;
-  if (i < a.n) {
-    const uint64_t key = a.keys[i];
-    const bool first = (key & a.cmask) != a.unc && (i == 0 || a.keys[i - 1] != key);
-    if (first && i + 1 < a.n && a.keys[i + 1] == key) {
-      for (int64_t j = i; j < a.n && a.keys[j] == key; ++j) {
-        const uint4 r = *reinterpret_cast<const uint4 *>(a.segs + a.vals[j]);
-        const uint2 *pp = reinterpret_cast<const uint2 *>(a.pieces) + r.x;
-        const uint32_t np = r.y & 0xffffu;
-        for (uint32_t k = 0; k < np; ++k) {
-          const uint32_t meta = __ldg(pp + k).y;
-          const uint32_t col = meta & 511u, len = (meta >> 9) & 1023u;
-          const uint32_t wa = col >> 5, wb = (col + len - 1u) >> 5;
-          mask |= (0xffffu >> (15u - wb)) & (0xffffu << wa);
-        }
-      }
-    }
+// ---- run members, one LANE per segment -----------------------------------------------------------------------
+// A warp takes 32 consecutive run members (mlist) and owns the runs that START among them; the last of those may
+// continue past the 32, and then the warp follows it to its end in further rounds.  f(i, runlane) is called by every
+// lane of every round: i = the lane's sorted segment (-1: nothing this round), runlane = lane (of round 0) that holds
+// the first segment of its run.
+template <typename F>
+__device__ __forceinline__ void warp_runs(const ExpandArgs &a, uint32_t cb, uint32_t nm, int lane, F &&f) {
+  const uint32_t m = cb + (uint32_t)lane;
+  int64_t i = -1;
+  uint64_t key = 0;
+  bool start = false;
+  if (m < nm) {
+    i = a.mlist[m];
+    key = a.keys[i];
+    start = i == 0 || a.keys[i - 1] != key;
   }
-  ng[i] = (uint32_t)__popc(mask);
+  const uint32_t smask = __ballot_sync(0xffffffffu, start);
+  const uint32_t below = smask & (lane == 31 ? 0xffffffffu : ((2u << lane) - 1u));
+  const int runlane = below ? 31 - __clz(below) : -1;  // -1: the run started in an earlier warp's range
+  f(runlane >= 0 ? i : (int64_t)-1, runlane);
+  if (smask == 0u) return;
+  const int jlast = 31 - __clz(smask);
+  const uint64_t klast = __shfl_sync(0xffffffffu, key, jlast);
+  for (uint32_t rb = cb + 32u; rb < nm; rb += 32u) {
+    const uint32_t m2 = rb + (uint32_t)lane;
+    int64_t i2 = -1;
+    bool same = false;
+    if (m2 < nm) {
+      i2 = a.mlist[m2];
+      same = a.keys[i2] == klast;
+    }
+    const uint32_t same_mask = __ballot_sync(0xffffffffu, same);
+    const int cnt = same_mask == 0xffffffffu ? 32 : (__ffs(~same_mask) - 1);
+    if (cnt == 0) break;
+    f(lane < cnt ? i2 : (int64_t)-1, jlast);
+    if (cnt < 32) break;
+  }
 }
 
-// One thread per run start (a single segment is a run of one): the run's units go to its place in its stream; the
-// units of a same-cell run are written window-major (all units of window 0, then window 1, ...), the first unit of
-// each window group flagged, so that the count kernel can give a whole (cell, window) group to one lane.
-__global__ void __launch_bounds__(256) expand_kernel(ExpandArgs a) {
-  __shared__ uint32_t cnt[16][256];  // per thread: units per window of its run, then the write cursors
+// windows a segment's pieces touch (bit w)
+__device__ __forceinline__ uint32_t segment_window_mask(const ExpandArgs &a, int64_t i) {
+  const uint4 r = *reinterpret_cast<const uint4 *>(a.segs + a.vals[i]);
+  const uint2 *pp = reinterpret_cast<const uint2 *>(a.pieces) + r.x;
+  const uint32_t np = r.y & 0xffffu;
+  uint32_t mask = 0u;
+  for (uint32_t k = 0; k < np; ++k) {
+    const uint32_t meta = __ldg(pp + k).y;
+    const uint32_t col = meta & 511u, len = (meta >> 9) & 1023u;
+    const uint32_t wa = col >> 5, wb = (col + len - 1u) >> 5;
+    mask |= (0xffffu >> (15u - wb)) & (0xffffu << wa);
+  }
+  return mask;
+}
+
+// Number of (cell, window) groups of every same-cell run, stored at the run's first segment (the array is zeroed
+// first): the windows its pieces touch.  Its exclusive scan places the runs in the group directory.
+__global__ void __launch_bounds__(256) rungroups_kernel(ExpandArgs a) {
+  __shared__ uint32_t wmask[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nm = (uint32_t)*a.tot_ms;
+  const uint32_t cb = (blockIdx.x * 8u + (uint32_t)warp) * 32u;
+  if (cb >= nm) return;
+  wmask[warp][lane] = 0u;
+  __syncwarp();
+  int64_t first = -1;
+  bool round0 = true;
+  warp_runs(a, cb, nm, lane, [&](int64_t i, int runlane) {
+    if (round0 && runlane == lane) first = i;
+    round0 = false;
+    if (i >= 0) atomicOr(&wmask[warp][runlane], segment_window_mask(a, i));
+  });
+  __syncwarp();
+  if (first >= 0) a.goffs[first] = (uint32_t)__popc(wmask[warp][lane]);
+}
+
+// Singles and uncounted reads: one thread per sorted segment, units in piece / window order.
+__global__ void __launch_bounds__(256) expand_single_kernel(ExpandArgs a) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  if (i == 0) a.gdir[*a.tot_g] = (uint32_t)*a.tot_m;  // sentinel: end of the last group
-  const uint64_t key = a.keys[i];
-  const bool isunc = (key & a.cmask) == a.unc;
-  if (isunc && !a.offs_u) return;
-  if (!isunc && i > 0 && a.keys[i - 1] == key) return;  // not the first segment of its run
-  int64_t klen = 1;
-  if (!isunc)
-    while (i + klen < a.n && a.keys[i + klen] == key) ++klen;
-  if (klen == 1) {
-    uint2 *q = a.units + (isunc ? *a.tot_s + *a.tot_m + a.offs_u[i] : (uint64_t)a.offs_s[i]);
-    segment_units(a, i, [&](uint32_t, uint2 u) {
-      u.y |= UM_GSTART;
-      *q++ = u;
-    });
-    return;
-  }
-  const uint32_t mbase = a.offs_m[i];
-  uint2 *q = a.units + *a.tot_s + mbase;
-  const int t = threadIdx.x;
+  const int cls = segment_class(a.keys, i, a.n, a.cmask, a.unc);
+  if (cls == 1 || (cls == 2 && !a.offs_u)) return;
+  uint2 *q = a.units + (cls == 2 ? *a.tot_s + *a.tot_m + a.offs_u[i] : (uint64_t)a.offs_s[i]);
+  segment_units(a, i, [&](uint32_t, uint2 u) { *q++ = u; });
+}
+
+// Run members: the units of a same-cell run are written WINDOW-MAJOR (all units of window 0, then window 1, ...)
+// and the first unit of every non-empty window goes into the group directory, so that the count kernel can give a
+// whole (cell, window) group to one lane.  Pass 1 counts the run's units per window (shared-memory counters of the
+// lane that holds the run's first segment), pass 2 turns the counters into cursors and places the units.
+__global__ void __launch_bounds__(256) expand_runs_kernel(ExpandArgs a) {
+  __shared__ uint32_t cnt[8][32][17];  // [warp][runlane][window] (+1: no bank conflicts between run lanes)
+  __shared__ uint32_t mbase[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t nm = (uint32_t)*a.tot_ms;
+  const uint32_t cb = (blockIdx.x * 8u + (uint32_t)warp) * 32u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.gdir[*a.tot_g] = (uint32_t)*a.tot_m;  // sentinel: end of the last group
+  if (cb >= nm) return;
 #pragma unroll
-  for (int w = 0; w < 16; ++w) cnt[w][t] = 0u;
-  for (int64_t j = i; j < i + klen; ++j) segment_units(a, j, [&](uint32_t w, uint2) { ++cnt[w][t]; });
-  uint32_t run = 0;
-  uint32_t *gd = a.gdir + a.goffs[i];
+  for (int w = 0; w < 16; ++w) cnt[warp][lane][w] = 0u;
+  __syncwarp();
+  int64_t first = -1;
+  bool round0 = true;
+  warp_runs(a, cb, nm, lane, [&](int64_t i, int runlane) {
+    if (round0 && runlane == lane) first = i;
+    round0 = false;
+    if (i >= 0) segment_units(a, i, [&](uint32_t w, uint2) { atomicAdd(&cnt[warp][runlane][w], 1u); });
+  });
+  __syncwarp();
+  if (first >= 0) {
+    const uint32_t mb = a.offs_m[first];
+    mbase[warp][lane] = mb;
+    uint32_t *gd = a.gdir + a.goffs[first];
+    uint32_t run = 0;
 #pragma unroll
-  for (int w = 0; w < 16; ++w) {
-    const uint32_t c = cnt[w][t];
-    cnt[w][t] = run | (c ? 0x80000000u : 0u);  // cursor; top bit = the next unit written opens the window group
-    if (c) *gd++ = mbase + run;
-    run += c;
+    for (int w = 0; w < 16; ++w) {
+      const uint32_t c = cnt[warp][lane][w];
+      cnt[warp][lane][w] = run;
+      if (c) *gd++ = mb + run;
+      run += c;
+    }
   }
-  for (int64_t j = i; j < i + klen; ++j)
-    segment_units(a, j, [&](uint32_t w, uint2 u) {
-      const uint32_t c = cnt[w][t];
-      if (c & 0x80000000u) u.y |= UM_GSTART;
-      q[c & 0x7fffffffu] = u;
-      cnt[w][t] = (c & 0x7fffffffu) + 1u;
-    });
+  __syncwarp();
+  uint2 *um = a.units + *a.tot_s;
+  warp_runs(a, cb, nm, lane, [&](int64_t i, int runlane) {
+    if (i < 0) return;
+    const uint32_t mb = mbase[warp][runlane];
+    segment_units(a, i, [&](uint32_t w, uint2 u) { um[mb + atomicAdd(&cnt[warp][runlane][w], 1u)] = u; });
+  });
 }
 
 // first sorted segment at or after i (inside the slot) that starts a run; warp-uniform
@@ -518,8 +607,8 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
       sm.lut[threadIdx.x] = cls == LS_CLASS_NA ? K1_DUMP_OFF : (uint32_t)cls * 2u * K1_ROW_BYTES;
       // deletion-like units run as 'N' one class up (N -> O): their table carries O's bit and dup row
       const int c0 = cls == LS_CLASS_NA ? -1 : cls, c1 = cls == LS_CLASS_N ? LS_CLASS_O : -1;
-      sm.lut2[0][threadIdx.x] = c0 < 0 ? 0u : ((1u << c0) | (((uint32_t)c0 * K1_ROW_BYTES) << 8));
-      sm.lut2[1][threadIdx.x] = c1 < 0 ? 0u : ((1u << c1) | (((uint32_t)c1 * K1_ROW_BYTES) << 8));
+      sm.lut2[0][threadIdx.x] = c0 < 0 ? 0u : (0x80u | (c0 < 6 ? (1u << c0) : 0u) | (((uint32_t)c0 * K1_ROW_BYTES) << 8));
+      sm.lut2[1][threadIdx.x] = c1 < 0 ? 0u : (0x80u | (((uint32_t)c1 * K1_ROW_BYTES) << 8));
     }
     if (threadIdx.x == 0) {
       sm.next1 = 0;
@@ -563,19 +652,20 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
       g = __shfl_sync(0xffffffffu, g, 0);
       G = __shfl_sync(0xffffffffu, G, 0);
       if (g >= nun) break;
+      // descriptors run two steps ahead of the counting, the unit's loads one step ahead
       uint32_t k = g + (uint32_t)lane;
       uint2 u0 = k < nun ? __ldg(us + k) : make_uint2(0u, 0u);
-      UData d0 = load_unit(a, u0);
+      uint2 u1 = (G > 1u && k + 32u < nun) ? __ldg(us + k + 32u) : make_uint2(0u, 0u);
+      URaw r0 = issue_unit(a, u0);
       for (uint32_t b = 0; b < G; ++b) {
-        uint2 u1 = make_uint2(0u, 0u);
-        UData d1 = d0;
-        if (b + 1u < G) {
-          if (k + 32u < nun) u1 = __ldg(us + k + 32u);
-          d1 = load_unit(a, u1);
-        }
+        uint2 u2 = make_uint2(0u, 0u);
+        if (b + 2u < G && k + 64u < nun) u2 = __ldg(us + k + 64u);
+        const URaw r1 = issue_unit(a, u1);
+        const UData d0 = align_unit(r0, u0);
         count_unit<PACKED, false>(c, u0.y, d0, lane, seen);
         u0 = u1;
-        d0 = d1;
+        u1 = u2;
+        r0 = r1;
         k += 32u;
       }
     }
@@ -610,37 +700,60 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
         }
       }
     };
-    uint32_t p = 0, e = 0, pn = 0, en = 0;
+    // the group in hand [p, e) and the two claimed after it; a lane walks them unit by unit
+    uint32_t p = 0, e = 0, p1 = 0, e1 = 0, p2 = 0, e2 = 0;
     claim(true, p, e);
-    claim(true, pn, en);
+    claim(true, p1, e1);
+    claim(true, p2, e2);
+    // position of the unit k (1 or 2) steps after the one in hand; ok = there is one
+    auto ahead = [&](int k, bool &ok) -> uint32_t {
+      uint32_t a0 = p, b0 = e, a1 = p1, b1 = e1, a2 = p2, b2 = e2;
+      for (int i = 0; i < k; ++i) {
+        if (a0 + 1u < b0) {
+          ++a0;
+        } else {
+          a0 = a1;
+          b0 = b1;
+          a1 = a2;
+          b1 = b2;
+          a2 = b2 = 0u;
+        }
+      }
+      ok = a0 < b0;
+      return a0;
+    };
+    bool ok1, ok2;
     uint2 u0 = p < e ? __ldg(um + p) : make_uint2(0u, 0u);
-    UData d0 = load_unit(a, u0);
+    const uint32_t q1 = ahead(1, ok1);
+    uint2 u1 = ok1 ? __ldg(um + q1) : make_uint2(0u, 0u);
+    URaw r0 = issue_unit(a, u0);
     bool fresh = true;  // the unit in hand opens its group
     while (__any_sync(0xffffffffu, p < e)) {
-      // the unit after this one: the next of the group, or the first of the group claimed ahead
-      const bool last = p + 1u >= e;
-      const uint32_t q = last ? pn : p + 1u;
-      const bool more = last ? (pn < en) : true;
-      uint2 u1 = (p < e && more) ? __ldg(um + q) : make_uint2(0u, 0u);
-      UData d1 = load_unit(a, u1);
+      const uint32_t q2 = ahead(2, ok2);
+      const uint2 u2 = ok2 ? __ldg(um + q2) : make_uint2(0u, 0u);
+      const URaw r1 = issue_unit(a, u1);
+      const UData d0 = align_unit(r0, u0);
       if (fresh) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) seen[i] = 0u;
       }
       count_unit<PACKED, true>(c, u0.y, d0, lane, seen);
-      const bool want = p < e && last;
+      const bool want = p < e && p + 1u >= e;
       if (p < e) {
-        if (last) {
-          p = pn;
-          e = en;
+        if (want) {
+          p = p1;
+          e = e1;
+          p1 = p2;
+          e1 = e2;
         } else {
           ++p;
         }
       }
       fresh = want;
-      claim(want, pn, en);
+      claim(want, p2, e2);
       u0 = u1;
-      d0 = d1;
+      u1 = u2;
+      r0 = r1;
     }
   }
 

@@ -186,6 +186,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   uint64_t *d_tot_m = reinterpret_cast<uint64_t *>(d_aligned + 12);
   uint64_t *d_tot_u = reinterpret_cast<uint64_t *>(d_aligned + 13);
   uint64_t *d_tot_g = reinterpret_cast<uint64_t *>(d_aligned + 14);      // number of (cell, window) groups in M
+  uint64_t *d_tot_ms = reinterpret_cast<uint64_t *>(d_aligned + 15);     // number of run-member segments
   if (n > 0 && ctx->n_windows > 0) {
     ctx->n_drop = 0;
     sa.n_drop = 0;
@@ -282,17 +283,24 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       LS_CK(ctx->offs_s.ensure((size_t)(nseg + 1) * 4));
       LS_CK(ctx->offs_m.ensure((size_t)(nseg + 1) * 4));
       LS_CK(ctx->goffs.ensure((size_t)(nseg + 1) * 4));
+      LS_CK(ctx->mrank.ensure((size_t)(nseg + 1) * 4));
+      LS_CK(ctx->mlist.ensure((size_t)(nseg + 1) * 4));
       if (with_u) LS_CK(ctx->offs_u.ensure((size_t)(nseg + 1) * 4));
       os = ctx->offs_s.as<uint32_t>();
       om = ctx->offs_m.as<uint32_t>();
       og = ctx->goffs.as<uint32_t>();
       ou = with_u ? ctx->offs_u.as<uint32_t>() : nullptr;
+      uint32_t *mr = ctx->mrank.as<uint32_t>();
       classify_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, ctx->sorted_vals,
-                                                                          ctx->segs.as<Segment>(), nseg, cmask, unc, os, om, ou);
+                                                                          ctx->segs.as<Segment>(), nseg, cmask, unc, os, om, ou, mr);
       ++launches;
       LS_CK(ls_scan_exclusive_u32(os, os, nseg + 1, d_tot_s, ctx->scan_tmp, st));
       LS_CK(ls_scan_exclusive_u32(om, om, nseg + 1, d_tot_m, ctx->scan_tmp, st));
-      launches += 6;
+      LS_CK(ls_scan_exclusive_u32(mr, mr, nseg + 1, d_tot_ms, ctx->scan_tmp, st));
+      launches += 9;
+      mlist_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, cmask, unc, mr,
+                                                                   ctx->mlist.as<uint32_t>());
+      ++launches;
       if (with_u) {
         LS_CK(ls_scan_exclusive_u32(ou, ou, nseg + 1, d_tot_u, ctx->scan_tmp, st));
         launches += 3;
@@ -310,10 +318,14 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       ea.tot_s = d_tot_s;
       ea.tot_m = d_tot_m;
       ea.tot_g = d_tot_g;
+      ea.tot_ms = d_tot_ms;
+      ea.mlist = ctx->mlist.as<uint32_t>();
       ea.goffs = og;
       ea.gdir = nullptr;
       ea.units = nullptr;
-      rungroups_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(ea, og);
+      // one warp per 32 run members; the grid covers the worst case (every segment a run member)
+      LS_CK(cudaMemsetAsync(og, 0, (size_t)(nseg + 1) * 4, st));
+      rungroups_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ea);
       ++launches;
       LS_CK(ls_scan_exclusive_u32(og, og, nseg + 1, d_tot_g, ctx->scan_tmp, st));
       launches += 3;
@@ -334,8 +346,10 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       LS_CK(ctx->gdir.ensure((size_t)(h_tot[14] + 1) * 4));
       ea.gdir = ctx->gdir.as<uint32_t>();
       ea.units = ctx->units.as<uint2>();
-      expand_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ea);
-      ++launches;
+      expand_single_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ea);
+      const int64_t n_members = (int64_t)h_tot[15];
+      if (n_members > 0) expand_runs_kernel<<<(unsigned)((n_members + 255) / 256), 256, 0, st>>>(ea);
+      launches += 2;
       LS_CK(cudaGetLastError());
     }
     LS_CK(cudaEventRecord(ctx->ev[2], st));

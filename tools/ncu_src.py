@@ -4,9 +4,20 @@ between marker instructions.  usage: ncu_src.py report.ncu-rep [n_top]"""
 import csv, subprocess, sys
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
-hdr = rows[1]
+# one block per kernel: a "Kernel Name" row, a header row, then one row per instruction
+blocks, cur_rows = [], None
+for r in rows:
+    if r and r[0] == "Kernel Name":
+        cur_rows = [r]
+        blocks.append(cur_rows)
+    elif cur_rows is not None:
+        cur_rows.append(r)
+which = sys.argv[3] if len(sys.argv) > 3 else "pileup_count"
+blk = [b for b in blocks if which in b[0][1]][-1]
+print(blk[0][1])
+hdr = blk[1]
 ia, isrc, isamp, iex, ithr = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
-data = rows[2:]
+data = [r for r in blk[2:] if len(r) == len(hdr)]
 tot_ex = sum(int(r[iex] or 0) for r in data)
 tot_s = sum(int(r[isamp] or 0) for r in data)
 print("instructions", len(data), "executed", tot_ex, "samples", tot_s)
