@@ -228,50 +228,74 @@ struct WarpCtx {
   uint32_t cnt1;                  // PACKED: 1 << 20, else 0
 };
 
-// One column of a unit.  A column that must not count -- outside [lo, hi), below the quality threshold -- adds ZERO to
-// the word it would have hit, and an ignored base code adds to a dump row through the nibble table: the 32 unrolled
-// columns are straight-line code.  SEEN adds the same-cell bookkeeping on the lane's per-window state `seen` (one
-// byte of class bits per column): a class bit that was already set is a (cell, class) duplicate, any bit already set
-// a (cell) duplicate; both go to the class's dup word with one more (possibly zero) add.
-template <bool PACKED, bool SEEN, int J>
-struct BaseLoop {
+// A column that must not count -- outside [lo, hi), below the quality threshold -- adds ZERO to the word it would have
+// hit, and an ignored base code adds to a dump row through the nibble table: the 32 unrolled columns are straight-line
+// code.  SEEN adds the same-cell bookkeeping on the lane's per-window state `seen` (one byte per column: 0x80 = the
+// cell has an entry here, bits 0-5 = classes A..D it has shown): the duplicates go to the class's dup word with one
+// more (possibly zero) add.
+__device__ __forceinline__ uint32_t lds_u32_pinned(uint32_t addr) {
+  uint32_t v;  // volatile: stays where it is written, i.e. ahead of the block's adds (see ColumnBlock)
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// Eight columns of a unit.  All table lookups of the block are issued first and only then the adds: a shared-memory
+// load cannot be moved above an earlier shared-memory atomic by the compiler (it cannot prove they do not alias), so
+// written column by column every column would wait for its own lookup.
+template <bool PACKED, bool SEEN, int B>
+struct ColumnBlock {
   static __device__ __forceinline__ void run(const WarpCtx &c, const UData &d, uint32_t hs, uint32_t vm, uint32_t ds,
                                              uint32_t lut2p, uint32_t (&seen)[8]) {
     constexpr uint32_t QOFF = (uint32_t)K1_CROWS * K1_ROW_BYTES;
-    const uint32_t v = prmt_sel<0x4640u | (uint32_t)(J & 3)>(d.qw[J >> 2], c.cnt1);
-    constexpr int pos = 4 * (J & 7);  // bit position of column J's nibble in its word
-    const uint32_t idx = pos >= 2 ? ((d.hw[J >> 3] >> (pos >= 2 ? pos - 2 : 0)) & 0x3cu) : ((d.hw[J >> 3] << 2) & 0x3cu);
-    const uint32_t off = lds_u32(idx | c.lut_s);  // the table is 64-byte aligned
-    uint32_t vz, okm;  // vz = v, okm = 0x3c if column J is inside [lo, hi) and v >= thr; else 0
-    asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %3, %4;\n setp.ne.u32 p, t, 0;\n setp.ge.and.u32 p, %2, %5, p;\n"
-        " selp.u32 %0, %2, 0, p;\n selp.u32 %1, 60, 0, p;\n}"
-        : "=r"(vz), "=r"(okm)
-        : "r"(v), "r"(vm), "n"(1u << J), "r"(c.thr));
-    const uint32_t addr = hs + off + 4u * J;
-    if (PACKED) {
-      red_shared_add(addr, vz);
-    } else {
-      red_shared_add(addr, okm >> 5);
-      red_shared_add(addr + QOFF, vz);
+    uint32_t idx[8], off[8], vz[8], okm[8], w2[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int pos = 4 * t;  // bit position of column (8B + t)'s nibble in word B
+      idx[t] = pos >= 2 ? ((d.hw[B] >> (pos >= 2 ? pos - 2 : 0)) & 0x3cu) : ((d.hw[B] << 2) & 0x3cu);
+      off[t] = lds_u32_pinned(idx[t] | c.lut_s);  // the table is 64-byte aligned
     }
-    if (SEEN) {
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int J = 8 * B + t;
+      // c.cnt1 = 1 << 20 (0 when !PACKED) lives in a register so that the byte selector can be the immediate
+      const uint32_t v = (t & 3) == 0   ? prmt_sel<0x4640u>(d.qw[J >> 2], c.cnt1)
+                         : (t & 3) == 1 ? prmt_sel<0x4641u>(d.qw[J >> 2], c.cnt1)
+                         : (t & 3) == 2 ? prmt_sel<0x4642u>(d.qw[J >> 2], c.cnt1)
+                                        : prmt_sel<0x4643u>(d.qw[J >> 2], c.cnt1);
+      // vz = v, okm = 0x3c if column J is inside [lo, hi) and v >= thr; else 0
+      asm("{\n .reg .pred p;\n .reg .b32 t;\n and.b32 t, %3, %4;\n setp.ne.u32 p, t, 0;\n setp.ge.and.u32 p, %2, %5, p;\n"
+          " selp.u32 %0, %2, 0, p;\n selp.u32 %1, 60, 0, p;\n}"
+          : "=r"(vz[t]), "=r"(okm[t])
+          : "r"(v), "r"(vm), "r"(1u << J), "r"(c.thr));
       // table 2, looked up at code 0 (an ignored code: word 0) when the column does not count:
       // byte 0 = 0x80 | class bit (classes A..D: bits 0-5), bits 8.. = byte offset of the class's dup row
-      const uint32_t w2 = lds_u32((idx & okm) | lut2p);
-      const uint32_t bsh = prmt_sel<(J & 3) == 0 ? 0x4440u : ((J & 3) == 1 ? 0x4404u : ((J & 3) == 2 ? 0x4044u : 0x0444u))>(w2, 0u);
-      const uint32_t sw = seen[J >> 2];
-      // the 0x80 markers meet iff the cell already has an entry at this column; the class bits iff of this class
-      const uint32_t dv = (sw & bsh & 0x3f3f3f3fu) ? 0x10001u : ((sw & bsh) ? 0x10000u : 0u);
-      seen[J >> 2] = sw | bsh;
-      red_shared_add(ds + (w2 >> 8) + 4u * J, dv);
+      if (SEEN) w2[t] = lds_u32_pinned((idx[t] & okm[t]) | lut2p);
     }
-    BaseLoop<PACKED, SEEN, J + 1>::run(c, d, hs, vm, ds, lut2p, seen);
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int J = 8 * B + t;
+      const uint32_t addr = hs + off[t] + 4u * J;
+      if (PACKED) {
+        red_shared_add(addr, vz[t]);
+      } else {
+        red_shared_add(addr, okm[t] >> 5);
+        red_shared_add(addr + QOFF, vz[t]);
+      }
+      if (SEEN) {
+        const uint32_t bsh = (t & 3) == 0   ? prmt_sel<0x4440u>(w2[t], 0u)
+                             : (t & 3) == 1 ? prmt_sel<0x4404u>(w2[t], 0u)
+                             : (t & 3) == 2 ? prmt_sel<0x4044u>(w2[t], 0u)
+                                            : prmt_sel<0x0444u>(w2[t], 0u);
+        const uint32_t sw = seen[J >> 2];
+        // the 0x80 markers meet iff the cell already has an entry at this column; the class bits iff of this class
+        const uint32_t dv = (sw & bsh & 0x3f3f3f3fu) ? 0x10001u : ((sw & bsh) ? 0x10000u : 0u);
+        seen[J >> 2] = sw | bsh;
+        red_shared_add(ds + (w2[t] >> 8) + 4u * J, dv);
+      }
+    }
   }
-};
-template <bool PACKED, bool SEEN>
-struct BaseLoop<PACKED, SEEN, 32> {
-  static __device__ __forceinline__ void run(const WarpCtx &, const UData &, uint32_t, uint32_t, uint32_t, uint32_t,
-                                             uint32_t (&)[8]) {}
 };
 
 // One unit per lane: 32 unrolled columns.  The strand selects the row inside the class's row pair through the base
@@ -290,7 +314,11 @@ __device__ __forceinline__ void count_unit(const WarpCtx &c, uint32_t meta, cons
   const uint32_t sb = w * 132u;
   const uint32_t hs = c.hist_s + sb + strand * K1_ROW_BYTES + del * (2u * K1_ROW_BYTES);
   const uint32_t ds = c.dup_s + sb;
-  BaseLoop<PACKED, SEEN, 0>::run(c, d, hs, vm, ds, c.lut_s + 64u + del * 64u, seen);
+  const uint32_t lut2p = c.lut_s + 64u + del * 64u;
+  ColumnBlock<PACKED, SEEN, 0>::run(c, d, hs, vm, ds, lut2p, seen);
+  ColumnBlock<PACKED, SEEN, 1>::run(c, d, hs, vm, ds, lut2p, seen);
+  ColumnBlock<PACKED, SEEN, 2>::run(c, d, hs, vm, ds, lut2p, seen);
+  ColumnBlock<PACKED, SEEN, 3>::run(c, d, hs, vm, ds, lut2p, seen);
   if (ind) {  // last base of the op, followed by an insertion / deletion: class I / D instead of its letter
     const uint32_t v = PACKED ? ((1u << K1_CNT_SHIFT) | d.qlast) : d.qlast;
     if (v >= c.thr) {
