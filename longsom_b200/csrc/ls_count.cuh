@@ -90,11 +90,11 @@ struct TileSmemT {
   // [0..17] counts, [18..35] quality sums.  Column s of a row is word k1_col(s).
   uint32_t hist[PACKED ? K1_CROWS : 2 * K1_CROWS][K1_ROWW];
   uint32_t dup[8][K1_ROWW];               // per class: (cell, class) duplicates | (cell) duplicates << 16
-  uint32_t acx[K1_ROWW];                  // alt entries of visible-but-uncounted reads (--min_ac > 0)
   alignas(64) uint32_t lut[16];           // BAM nibble code -> byte offset of the class's row pair (dump rows if ignored)
   uint32_t lut2[2][16];                   // [deletion-like][code] -> 0x80 | class bit (A..D) | byte offset of the class's dup row << 8
   uint8_t ref[LS_TILE];
   uint32_t next1, next2, next3, npass, ticket;
+  uint32_t acx[K1_ROWW];                  // alt entries of visible-but-uncounted reads; LAST: only allocated with --min_ac > 0
 };
 
 __device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t tile) {
@@ -604,8 +604,8 @@ __device__ __forceinline__ uint32_t run_start_at_or_after(const uint64_t *__rest
   }
 }
 
-template <bool PACKED>
-__global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a) {
+template <bool PACKED, int MIN_CTAS>
+__global__ void __launch_bounds__(K1_THREADS, MIN_CTAS) pileup_count_kernel(CountArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
   const uint32_t part = blockIdx.x;
@@ -626,8 +626,10 @@ __global__ void __launch_bounds__(K1_THREADS, 3) pileup_count_kernel(CountArgs a
 
   {  // zero the accumulators, stage the reference bases, build the nibble tables
     uint4 *z = reinterpret_cast<uint4 *>(&sm);
-    constexpr int NZ = ((PACKED ? K1_CROWS : 2 * K1_CROWS) + 8 + 1) * K1_ROWW / 4;  // hist + dup + acx
+    constexpr int NZ = ((PACKED ? K1_CROWS : 2 * K1_CROWS) + 8) * K1_ROWW / 4;  // hist + dup
     for (int i = threadIdx.x; i < NZ; i += K1_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (a.min_ac > 0)
+      for (int i = threadIdx.x; i < K1_ROWW; i += K1_THREADS) sm.acx[i] = 0u;
     for (int i = threadIdx.x; i < LS_TILE; i += K1_THREADS)
       sm.ref[i] = (tile_start + i < tile_end) ? upper_ascii(a.ref[ref_base + i]) : (uint8_t)'N';
     if (threadIdx.x < 16) {

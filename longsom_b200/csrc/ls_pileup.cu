@@ -19,6 +19,7 @@
 //      "reads minus same-cell duplicates", the duplicates found with a per-warp
 //      T-byte seen[] mask that is only touched for runs longer than one segment.
 //   4. site epilogue applies the reference's gates and writes [slot][field][T] words.
+#include <cstddef>
 #include <cstdlib>
 
 #include "ls_common.cuh"
@@ -407,19 +408,34 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.min_dp = params->min_dp;
     ca.min_cc = params->min_cc;
     ca.min_ac = params->min_ac;
-    if (!ctx->k1_attr_set) {
-      LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(TileSmemT<true>)));
-      LS_CK(cudaFuncSetAttribute(pileup_count_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(TileSmemT<false>)));
-      ctx->k1_attr_set = true;
+    {
+      // shared memory per CTA: the acx row sits last and is only allocated with --min_ac > 0; without it four packed
+      // CTAs would fit an SM, but the 64-register build they need spills and measured 9 % slower (LS_K1_CTAS=4 selects it)
+      const size_t sm_p = params->min_ac > 0 ? sizeof(TileSmemT<true>) : offsetof(TileSmemT<true>, acx);
+      const size_t sm_u = params->min_ac > 0 ? sizeof(TileSmemT<false>) : offsetof(TileSmemT<false>, acx);
+      static int ctas = -1;
+      if (ctas < 0) {
+        const char *e = getenv("LS_K1_CTAS");
+        ctas = (e && atoi(e) == 4) ? 4 : 3;
+      }
+      if (!ctx->k1_attr_set) {
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(TileSmemT<true>)));
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(TileSmemT<true>)));
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(TileSmemT<false>)));
+        ctx->k1_attr_set = true;
+      }
+      ca.cnt1 = packed ? (1u << K1_CNT_SHIFT) : 0u;
+      // 12-bit packed counters unless some cell has > K1_MAX_RUN_PACKED reads in one tile
+      if (!packed)
+        pileup_count_kernel<false, 1><<<(unsigned)max_parts, K1_THREADS, sm_u, st>>>(ca);
+      else if (ctas == 3)
+        pileup_count_kernel<true, 3><<<(unsigned)max_parts, K1_THREADS, sm_p, st>>>(ca);
+      else
+        pileup_count_kernel<true, 4><<<(unsigned)max_parts, K1_THREADS, sm_p, st>>>(ca);
     }
-    // 12-bit packed counters unless some cell has > K1_MAX_RUN_PACKED reads in one tile
-    ca.cnt1 = packed ? (1u << K1_CNT_SHIFT) : 0u;
-    if (packed)
-      pileup_count_kernel<true><<<(unsigned)max_parts, K1_THREADS, sizeof(TileSmemT<true>), st>>>(ca);
-    else
-      pileup_count_kernel<false><<<(unsigned)max_parts, K1_THREADS, sizeof(TileSmemT<false>), st>>>(ca);
     ++launches;
     LS_CK(cudaGetLastError());
     LS_CK(cudaEventRecord(ctx->ev[3], st));

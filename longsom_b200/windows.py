@@ -30,35 +30,71 @@ def _merge(iv, d):
     return [tuple(x) for x in out]
 
 
+def _by_chrom(iv):
+    d = {}
+    for c, s, e in iv:
+        d.setdefault(c, []).append((s, e))
+    return d
+
+
 def _intersect(a, b):
+    """bedtools intersect: for every interval of a, in order, its overlap with every interval of b (in b's order).
+    b is indexed by chromosome with a running maximum of the ends, so an exome-sized --bed costs a bisection per
+    interval instead of a scan of all of b."""
+    import bisect
+    idx = {}
+    for c, lst in _by_chrom(b).items():
+        order = sorted(range(len(lst)), key=lambda k: lst[k][0])
+        starts = [lst[k][0] for k in order]
+        maxend, m = [], -1
+        for k in order:
+            m = max(m, lst[k][1])
+            maxend.append(m)
+        idx[c] = (lst, order, starts, maxend)
     out = []
     for c, s, e in a:
-        for c2, s2, e2 in b:
-            if c == c2:
-                lo, hi = max(s, s2), min(e, e2)
-                if lo < hi:
-                    out.append((c, lo, hi))
+        if c not in idx:
+            continue
+        lst, order, starts, maxend = idx[c]
+        hi = bisect.bisect_left(starts, e)          # candidates start before e ...
+        lo = bisect.bisect_right(maxend, s, 0, hi)  # ... and nothing before lo reaches past s
+        for k in sorted(order[lo:hi]):              # b's own order, like bedtools
+            s2, e2 = lst[k]
+            l2, h2 = max(s, s2), min(e, e2)
+            if l2 < h2:
+                out.append((c, l2, h2))
     return out
 
 
 def _subtract(a, b):
+    """bedtools subtract: every interval of a minus the union of b, pieces left to right."""
+    import bisect
+    union = {}
+    for c, lst in _by_chrom(b).items():
+        m = []
+        for s, e in sorted(lst):
+            if e <= s:
+                continue
+            if m and s <= m[-1][1]:
+                m[-1][1] = max(m[-1][1], e)
+            else:
+                m.append([s, e])
+        union[c] = ([x[0] for x in m], [x[1] for x in m])
     out = []
     for c, s, e in a:
-        pieces = [(s, e)]
-        for c2, s2, e2 in b:
-            if c2 != c:
-                continue
-            nxt = []
-            for ps, pe in pieces:
-                if e2 <= ps or s2 >= pe:
-                    nxt.append((ps, pe))
-                else:
-                    if ps < s2:
-                        nxt.append((ps, s2))
-                    if e2 < pe:
-                        nxt.append((e2, pe))
-            pieces = nxt
-        out.extend((c, ps, pe) for ps, pe in pieces)
+        if c not in union:
+            out.append((c, s, e))
+            continue
+        us, ue = union[c]
+        k = bisect.bisect_right(ue, s)  # first removed block that ends after s
+        cur = s
+        while k < len(us) and us[k] < e:
+            if us[k] > cur:
+                out.append((c, cur, us[k]))
+            cur = max(cur, ue[k])
+            k += 1
+        if cur < e:
+            out.append((c, cur, e))
     return out
 
 

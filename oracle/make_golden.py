@@ -188,24 +188,59 @@ def step3_only(cases):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def bed_stage(case, work, log):
+    """BaseCellCounter --bed / --bed_out (MakeWindows over the pybedtools stand-in) -> {golden name: path}."""
+    import pipeline_inputs as pi
+    p, d = pi.write_inputs(case, work)
+    bed, bed_out = pi.write_beds(case, work, d)
+    out = os.path.join(work, "out", "counts_bed")
+    os.makedirs(out, exist_ok=True)
+    res = {}
+    for name, extra in (("bed", ["--bed", bed, "--chrom", "all"]),
+                        ("bed_out", ["--bed", bed, "--bed_out", bed_out, "--chrom", d.contig_names[0]]),
+                        ("bedout_only", ["--bed_out", bed_out, "--bin", 20000, "--chrom", "all"])):
+        run_ref("SNVCalling/BaseCellCounter.py", ["--bam", p["full"], "--ref", p["ref"], "--out_folder", out, "--id", "full." + name,
+                "--min_bq", 20, "--min_mq", 60, "--min_dp", 3, "--min_cc", 2, "--nprocs", 1, "--tmp_dir",
+                os.path.join(work, "tmp_" + name)] + extra, log, produces=os.path.join(out, "full.%s.tsv" % name))
+        res["counts.full_%s.tsv" % name] = os.path.join(out, "full.%s.tsv" % name)
+    return res
+
+
+def bed_only(cases):
+    """`make_golden.py --bed [case ...]`: add the --bed / --bed_out BaseCellCounter goldens to existing cases."""
+    for case in cases:
+        work = tempfile.mkdtemp(prefix="ls_golden_bed_")
+        log, gdir = [], os.path.join(ROOT, "tests", "golden", case)
+        res = bed_stage(case, work, log)
+        sizes = write_golden(gdir, res)
+        manifest = json.load(open(os.path.join(gdir, "manifest.json")))
+        manifest.setdefault("bytes", {}).update(sizes)
+        manifest["reference_commands"] = [c for c in manifest.get("reference_commands", []) if "--bed" not in c] + log
+        json.dump(manifest, open(os.path.join(gdir, "manifest.json"), "w"), indent=1, default=str)
+        print(case, "->", gdir, sizes)
+        shutil.rmtree(work, ignore_errors=True)
+
+
 def reference_pipeline(case, work, log):
     import pipeline_inputs as pi
     p, d = pi.write_inputs(case, work)
     out = os.path.join(work, "out")
     os.makedirs(os.path.join(out, "counts"), exist_ok=True)
     res = {}
+    core_only = case in pi.CORE_ONLY
     for name, bam in (("Cancer", p["cancer"]), ("Non-Cancer", p["normal"])):
         run_ref("SNVCalling/BaseCellCounter.py", ["--bam", bam, "--ref", p["ref"], "--chrom", "all", "--out_folder",
                 os.path.join(out, "counts"), "--min_bq", 20, "--min_mq", 60, "--nprocs", 1, "--tmp_dir",
                 os.path.join(work, "tmp_" + name)], log, produces=os.path.join(out, "counts", "s.%s.tsv" % name))
         res["counts.%s.tsv" % name] = os.path.join(out, "counts", "s.%s.tsv" % name)
-    # a second parameterisation on the un-split BAM: min_ac > 0 exercises the AC pre-gate (Q4)
-    os.makedirs(os.path.join(out, "counts_ac"), exist_ok=True)
-    run_ref("SNVCalling/BaseCellCounter.py", ["--bam", p["full"], "--ref", p["ref"], "--chrom", d.contig_names[0],
-            "--out_folder", os.path.join(out, "counts_ac"), "--id", "full.ac", "--min_bq", 30, "--min_mq", 0, "--min_ac", 2,
-            "--min_dp", 3, "--min_cc", 2, "--bin", 30000, "--nprocs", 1, "--tmp_dir", os.path.join(work, "tmp_ac")], log,
-            produces=os.path.join(out, "counts_ac", "full.ac.tsv"))
-    res["counts.full_ac.tsv"] = os.path.join(out, "counts_ac", "full.ac.tsv")
+    if not core_only:
+        # a second parameterisation on the un-split BAM: min_ac > 0 exercises the AC pre-gate (Q4)
+        os.makedirs(os.path.join(out, "counts_ac"), exist_ok=True)
+        run_ref("SNVCalling/BaseCellCounter.py", ["--bam", p["full"], "--ref", p["ref"], "--chrom", d.contig_names[0],
+                "--out_folder", os.path.join(out, "counts_ac"), "--id", "full.ac", "--min_bq", 30, "--min_mq", 0, "--min_ac", 2,
+                "--min_dp", 3, "--min_cc", 2, "--bin", 30000, "--nprocs", 1, "--tmp_dir", os.path.join(work, "tmp_ac")], log,
+                produces=os.path.join(out, "counts_ac", "full.ac.tsv"))
+        res["counts.full_ac.tsv"] = os.path.join(out, "counts_ac", "full.ac.tsv")
     merged = os.path.join(out, "merged.tsv")
     run_ref("SNVCalling/MergeBaseCellCounts.py", ["--tsv_folder", os.path.join(out, "counts"), "--outfile", merged], log)
     res["merged.tsv"] = merged
@@ -218,6 +253,18 @@ def reference_pipeline(case, work, log):
             "--pon_SR", p["pon_sr"], "--pon_LR", p["pon_lr"], "--gnomAD_db", p["gnomad"], "--gnomAD_max", 0.01,
             "--min_distance", 0], log)  # the workflow passes 0 (SNVCalling.smk)
     res["step2.tsv"] = step2
+    cand = os.path.join(out, "candidates.tsv")
+    if core_only:
+        candidates_from_step2(step2, cand)
+        res["candidates.tsv"] = cand
+        pre = os.path.join(out, "geno_All")
+        run_ref("CellClustering/SingleCellGenotype.py", ["--bam", p["full"], "--infile", cand, "--ref", p["ref"], "--meta",
+                p["meta"], "--fusions", "--outfile", pre, "--alt_flag", "All", "--nprocs", 1, "--min_mq", 60, "--pvalue", 0.01,
+                "--alpha2", pi.ALPHA2, "--beta2", pi.BETA2, "--chrM_contaminant", "True", "--tmp_dir",
+                os.path.join(work, "tmp_gAll")], log)
+        for suf in ("SingleCellGenotype", "DpMatrix", "AltMatrix", "VAFMatrix", "BinaryMatrix"):
+            res["geno_All.%s.tsv" % suf] = "%s.%s.tsv" % (pre, suf)
+        return res
     # the shipped config points --editing at a .gz file: the filter is silently off (Q9)
     step2gz = os.path.join(out, "s.gz.calling.step2.tsv")
     run_ref("SNVCalling/BaseCellCalling.step2.py", ["--infile", res["step1.tsv"], "--outfile", os.path.join(out, "s.gz"), "--editing",
@@ -226,7 +273,6 @@ def reference_pipeline(case, work, log):
     res["step2_gz.tsv"] = step2gz
     res.update(step3_stage(step2, out, log))
     res.update(hccv_variants_stage(step2, out, log))
-    cand = os.path.join(out, "candidates.tsv")
     candidates_from_step2(step2, cand)
     res["candidates.tsv"] = cand
     for flag in ("All", "Alt"):
@@ -250,7 +296,9 @@ def reference_pipeline(case, work, log):
 def main():
     import pipeline_inputs as pi
     if sys.argv[1:2] == ["--step3"]:
-        return step3_only(sys.argv[2:] or list(pi.CASES) + ["s3"])
+        return step3_only(sys.argv[2:] or [c for c in pi.CASES if c not in pi.CORE_ONLY] + ["s3"])
+    if sys.argv[1:2] == ["--bed"]:
+        return bed_only(sys.argv[2:] or ["g1"])
     cases = sys.argv[1:] or list(pi.CASES)
     for case in cases:
         work = os.path.join(tempfile.gettempdir(), "ls_golden_work_%s" % case)

@@ -18,8 +18,9 @@
  *                           (workflow/scripts/CellClustering/SingleCellGenotype.py:114-178).
  *
  * The structure deliberately differs from the CUDA path: per window, dense per-column
- * accumulators and an explicit (site, cell, class) triple list that is sorted and
- * uniqued for the NC / CC set cardinalities (the reference's len(set(...)), :283,292).
+ * accumulators; the window's reads are visited cell by cell, and the NC / CC set
+ * cardinalities (the reference's len(set(...)), :283,292) count a cell the first time a
+ * per-site / per-(site, class) stamp sees it.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -89,17 +90,14 @@ static int32_t read_end(const ls_read_batch *b, int64_t r) {
 }
 
 typedef struct {
-  int32_t site;
   int32_t cell;
-  int32_t cls;
-} triple;
+  int64_t r;
+} cellread;
 
-static int cmp_triple(const void *pa, const void *pb) {
-  const triple *a = (const triple *)pa, *b = (const triple *)pb;
-  if (a->site != b->site) return a->site < b->site ? -1 : 1;
+static int cmp_cellread(const void *pa, const void *pb) {
+  const cellread *a = (const cellread *)pa, *b = (const cellread *)pb;
   if (a->cell != b->cell) return a->cell < b->cell ? -1 : 1;
-  if (a->cls != b->cls) return a->cls < b->cls ? -1 : 1;
-  return 0;
+  return a->r < b->r ? -1 : (a->r > b->r);
 }
 
 static int cmp_i32(const void *a, const void *b) {
@@ -212,8 +210,19 @@ static void count_window(const ls_read_batch *b, const ls_windows *w, int64_t wi
   uint32_t *cf = (uint32_t *)calloc((size_t)L * 8, 4);
   uint32_t *cr = (uint32_t *)calloc((size_t)L * 8, 4);
   uint32_t *bq = (uint32_t *)calloc((size_t)L * 8, 4);
-  triple *tr = NULL;
-  int64_t ntr = 0, trcap = 0;
+  /* Distinct cells per site (NC) and per (site, class) (CC): the reads are visited cell by cell (every per-site sum
+   * is order independent), so "this cell has already been seen here" is one stamp per site / per (site, class). */
+  uint32_t *nc = (uint32_t *)calloc((size_t)L, 4);
+  uint32_t *cc = (uint32_t *)calloc((size_t)L * 8, 4);
+  uint32_t *stamp_any = (uint32_t *)calloc((size_t)L, 4);
+  uint32_t *stamp_cls = (uint32_t *)calloc((size_t)L * 8, 4);
+  {
+    cellread *cr2 = (cellread *)malloc((size_t)nr * sizeof(cellread));
+    for (int64_t li = 0; li < nr; ++li) { cr2[li].cell = b->cell[list[li]]; cr2[li].r = list[li]; }
+    qsort(cr2, (size_t)nr, sizeof(cellread), cmp_cellread);
+    for (int64_t li = 0; li < nr; ++li) list[li] = cr2[li].r;
+    free(cr2);
+  }
   const uint8_t *ref = w->ref + w->ref_off[wi];
   for (int64_t li = 0; li < nr; ++li) {
     const int64_t r = list[li];
@@ -253,14 +262,11 @@ static void count_window(const ls_read_batch *b, const ls_windows *w, int64_t wi
           if (!counted) continue;
           if (rev) cr[(size_t)s * 8 + cls]++; else cf[(size_t)s * 8 + cls]++;
           bq[(size_t)s * 8 + cls] += qv;
-          if (ntr == trcap) {
-            trcap = trcap ? trcap * 2 : 65536;
-            tr = (triple *)realloc(tr, (size_t)trcap * sizeof(triple));
+          {
+            const uint32_t tag = (uint32_t)b->cell[r] + 1u;
+            if (stamp_any[s] != tag) { stamp_any[s] = tag; nc[s]++; }
+            if (stamp_cls[(size_t)s * 8 + cls] != tag) { stamp_cls[(size_t)s * 8 + cls] = tag; cc[(size_t)s * 8 + cls]++; }
           }
-          tr[ntr].site = s;
-          tr[ntr].cell = b->cell[r];
-          tr[ntr].cls = cls;
-          ++ntr;
         }
       }
       if (is_match(op)) { x += len; y += (uint32_t)len; }
@@ -269,17 +275,8 @@ static void count_window(const ls_read_batch *b, const ls_windows *w, int64_t wi
     }
   }
   free(list);
-  qsort(tr, (size_t)ntr, sizeof(triple), cmp_triple);
-  /* per site: distinct cells overall and per class */
-  uint32_t *nc = (uint32_t *)calloc((size_t)L, 4);
-  uint32_t *cc = (uint32_t *)calloc((size_t)L * 8, 4);
-  for (int64_t i = 0; i < ntr; ++i) {
-    int newcell = (i == 0 || tr[i].site != tr[i - 1].site || tr[i].cell != tr[i - 1].cell);
-    int newcls = newcell || tr[i].cls != tr[i - 1].cls;
-    if (newcell) nc[tr[i].site]++;
-    if (newcls) cc[(size_t)tr[i].site * 8 + tr[i].cls]++;
-  }
-  free(tr);
+  free(stamp_any);
+  free(stamp_cls);
   out->pos = (int32_t *)malloc((size_t)L * 4);
   out->ref = (uint8_t *)malloc((size_t)L);
   out->counts = (uint32_t *)malloc((size_t)L * LS_SITE_WORDS * 4);

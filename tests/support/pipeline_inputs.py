@@ -15,7 +15,30 @@ CASES = {
                n_extra_cells=3, variants_per_gene=6, p_mismatch=5e-4, p_ins=2e-4, p_del=2e-4),
     "g2": dict(seed=202, contig_lens=[70000, 60000], n_genes=7, n_reads=2500, n_cells=40, n_extra_cells=2,
                variants_per_gene=5, p_ins=4e-3, p_del=4e-3),
+    # 1 000 cells / 20 000 reads: the size SURVEY 8(d) asks for as a full reference-script run (core stages only, see
+    # CORE_ONLY: the pure-Python pysam stand-in makes the reference scripts minutes per thousand reads)
+    "g3": dict(seed=303, contig_lens=[260000], n_genes=14, n_reads=20000, n_cells=1000, n_extra_cells=5,
+               variants_per_gene=6),
 }
+CORE_ONLY = ("g3",)  # BaseCellCounter x2, merge, step1, step2, SingleCellGenotype (All) only
+
+
+def write_beds(case, workdir, d):
+    """--bed / --bed_out files for BaseCellCounter (MakeWindows, BaseCellCounter.py:87-110): unsorted-free, touching
+    and overlapping focus intervals (merge -d 1), one past the contig end (clipped by the intersect), and ignore
+    intervals that split, trim and swallow focus pieces."""
+    n0, l0 = d.contig_names[0], int(d.contig_lens[0])
+    bed, bed_out = os.path.join(workdir, "focus.bed"), os.path.join(workdir, "ignore.bed")
+    with open(bed, "w") as f:
+        f.write("track name=focus\n")
+        for s, e in ((0, 900), (900, 1800), (1801, 2500), (5000, 30000), (29000, 52000), (70000, 70001), (l0 - 700, l0 + 5000)):
+            f.write("%s\t%d\t%d\n" % (n0, s, e))
+        if len(d.contig_names) > 1:
+            f.write("%s\t%d\t%d\n" % (d.contig_names[1], 10, min(9000, int(d.contig_lens[1]))))
+    with open(bed_out, "w") as f:
+        for s, e in ((1000, 1200), (4000, 6000), (20000, 20001), (51000, 60000), (l0 - 100, l0)):
+            f.write("%s\t%d\t%d\n" % (n0, s, e))
+    return bed, bed_out
 
 # CB:Z suffix per case: "-1" (10x style; the HCCV script then never matches a barcode, quirk a12 of SURVEY.md)
 # or none (HCCVSingleCellGenotype works)

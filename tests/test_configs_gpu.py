@@ -35,6 +35,58 @@ def test_config_shapes_match_oracle(engine, name, scale):
         assert st["n_segments"] / max(1, st["n_tiles"]) > 100
 
 
+def _compare_in_window_chunks(engine, d, prm, n_chunks, threads=None):
+    """GPU table of the whole batch vs the oracle run chunk of windows by chunk of windows (bounds the oracle's
+    output buffers at full scale); the GPU table is ordered by (window, position), so the chunks are slices of it."""
+    import os
+    import oracle
+    iv = make_windows(d.contig_lens, 50000)
+    seqs = d.contig_seqs()
+    got = engine.pileup_count(d.batch, Windows.from_intervals(iv, seqs), prm)
+    st = dict(engine.last_stats)
+    threads = threads or min(32, os.cpu_count() or 8)
+    off, step = 0, (len(iv) + n_chunks - 1) // n_chunks
+    for c0 in range(0, len(iv), step):
+        want, _ = oracle.pileup_count(d.batch, Windows.from_intervals(iv[c0:c0 + step], seqs), prm, threads=threads)
+        n = want.n_sites
+        assert off + n <= got.n_sites, "GPU table is short at window %d" % c0
+        assert np.array_equal(got.tid[off:off + n], want.tid) and np.array_equal(got.pos[off:off + n], want.pos), c0
+        assert np.array_equal(got.ref[off:off + n], want.ref), c0
+        assert np.array_equal(got.counts[off:off + n], want.counts), c0
+        off += n
+    assert off == got.n_sites
+    return got, st
+
+
+def test_c1_full_scale(engine):
+    """BASELINE.json configs[0] at scale 1.0: chr21 + chrM, 2e5 reads, 1 000 cells."""
+    d = synth.generate(**synth.config("C1", scale=1.0))
+    got, st = _compare_in_window_chunks(engine, d, CountParams(min_bq=20, min_mq=60), 4)
+    assert got.n_sites > 100000 and st["n_aligned"] == d.batch.aligned_bases()
+
+
+def test_c2_full_scale(engine):
+    """BASELINE.json configs[1] at scale 1.0 (the bench workload): 5e6 reads x ~1.5 kb, 5 000 cells, every one of
+    the ~1.7e7 emitted sites bit-compared with the oracle."""
+    d = synth.generate(**synth.config("C2", scale=1.0))
+    got, st = _compare_in_window_chunks(engine, d, CountParams(min_bq=20, min_mq=60, min_dp=5, min_cc=5), 16)
+    assert got.n_sites > 10_000_000 and st["n_events"] > 4_000_000_000
+
+
+def test_c4_full_scale_real_depth_cap(engine):
+    """BASELINE.json configs[3] at scale 1.0 (2.6e6 reads, 10 000 cells) with eight hot genes instead of twenty, so
+    that one locus holds > 2.5e5 reads and the REAL pileup max_depth = 200000 drops records."""
+    cfg = synth.config("C4", scale=1.0)
+    cfg["n_hot_genes"] = 8
+    d = synth.generate(**cfg)
+    prm = CountParams(min_bq=20, min_mq=60, max_depth=200000)
+    got, st = _compare_in_window_chunks(engine, d, prm, 8)
+    assert st["n_segments"] / max(1, st["n_tiles"]) > 100  # deep tiles: many parts merged in HBM
+    w = _windows(d)
+    uncapped = engine.pileup_count(d.batch, w, CountParams(min_bq=20, min_mq=60, max_depth=0))
+    assert int(uncapped.counts[:, 0].astype(np.int64).sum()) > int(got.counts[:, 0].astype(np.int64).sum())  # the cap fired
+
+
 def test_c4_depth_cap_fires_at_a_hotspot(engine):
     """One locus deeper than max_depth (dedicated cap test), cap lowered to keep it small."""
     import oracle
@@ -49,11 +101,12 @@ def test_c4_depth_cap_fires_at_a_hotspot(engine):
     assert uncapped.counts[:, 0].sum() > want.counts[:, 0].sum()  # the cap really dropped records
 
 
-@pytest.mark.parametrize("n_sites,n_cells", [(1000, 1000), (10000, 1000), (3000, 5000)])
-def test_c5_genotyping_sweep(engine, n_sites, n_cells):
+@pytest.mark.parametrize("n_sites,n_cells,scale", [(1000, 1000, 0.02), (10000, 1000, 0.02), (3000, 5000, 0.02),
+                                                   (50000, 5000, 0.2)])
+def test_c5_genotyping_sweep(engine, n_sites, n_cells, scale):
     import oracle
     from scipy.stats import betabinom
-    cfg = synth.config("C5", scale=0.02)
+    cfg = synth.config("C5", scale=scale)
     cfg["n_cells"] = n_cells
     d = synth.generate(**cfg)
     w = _windows(d)

@@ -18,10 +18,12 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "support"))
 GOLD = os.path.join(ROOT, "tests", "golden")
-CASES = [c for c in ("g1", "g2") if os.path.isdir(os.path.join(GOLD, c))]
+CASES = [c for c in ("g1", "g2", "g3") if os.path.isdir(os.path.join(GOLD, c))]
 
 
 def gold_lines(case, name):
+    if not os.path.exists(os.path.join(GOLD, case, name + ".gz")):
+        return HashedGold(os.path.join(GOLD, case, name + ".sha256.json"))
     with gzip.open(os.path.join(GOLD, case, name + ".gz"), "rt") as f:
         return [l for l in f if not l.startswith("##fileDate")]
 
@@ -31,7 +33,25 @@ def file_lines(path):
         return [l for l in f if not l.startswith("##fileDate")]
 
 
+def has_gold(case, name):
+    return os.path.exists(os.path.join(GOLD, case, name + ".gz")) or os.path.exists(os.path.join(GOLD, case, name + ".sha256.json"))
+
+
+class HashedGold:
+    """A golden too large to commit (g3's 176 MB per-cell genotype table): line count + SHA-256 of its text."""
+
+    def __init__(self, path):
+        import json
+        meta = json.load(open(path))
+        self.sha256, self.lines = meta["sha256"], meta["lines"]
+
+
 def assert_same(got, want, what):
+    if isinstance(want, HashedGold):
+        import hashlib
+        assert len(got) == want.lines, "%s: %d lines vs %d" % (what, len(got), want.lines)
+        assert hashlib.sha256("".join(got).encode()).hexdigest() == want.sha256, what + ": SHA-256 differs"
+        return
     assert len(got) == len(want), "%s: %d lines vs %d" % (what, len(got), len(want))
     for i, (a, b) in enumerate(zip(got, want)):
         assert a == b, "%s differs at line %d:\n got: %s\nwant: %s" % (what, i, a[:400], b[:400])
@@ -85,14 +105,14 @@ class OracleEngine:
         return np.isin(query, keys).astype(np.uint8)
 
 
-def _count_with_oracle(bam, ref, chrom, bin_size, prm, ID, out):
+def _count_with_oracle(bam, ref, chrom, bin_size, prm, ID, out, bed="", bed_out=""):
     from longsom_b200 import bamio
     from longsom_b200.batch import Windows
     from longsom_b200.pipeline import load_bam_for_counting, prune_and_sort_windows, read_ends, write_counter_tsv
     from longsom_b200.windows import make_windows
     import oracle
     fa = bamio.Fasta(ref)
-    named = make_windows(fa.references, fa.lengths, chrom, bin_size)
+    named = make_windows(fa.references, fa.lengths, chrom, bin_size, bed=bed, bed_out=bed_out)
     bd, batch, _ = load_bam_for_counting(bam)
     iv = prune_and_sort_windows(named, bd.contig_names, batch, read_ends(batch))
     win = Windows.from_intervals(iv, {t: fa.contig(bd.contig_names[t]) for t in {w[0] for w in iv}})
@@ -107,10 +127,46 @@ def test_oracle_pileup_matches_reference_tables(work):
         out = os.path.join(d, "o_%s.tsv" % name)
         _count_with_oracle(bam, p["ref"], "all", 50000, CountParams(min_bq=20, min_mq=60), "s." + name, out)
         assert_same(file_lines(out), gold_lines(case, "counts.%s.tsv" % name), "BaseCellCounter " + name)
+    if not has_gold(case, "counts.full_ac.tsv"):
+        return  # core-stages-only case (g3)
     out = os.path.join(d, "o_ac.tsv")
     _count_with_oracle(p["full"], p["ref"], data.contig_names[0], 30000,
                        CountParams(min_bq=30, min_mq=0, min_ac=2, min_dp=3, min_cc=2), "full.ac", out)
     assert_same(file_lines(out), gold_lines(case, "counts.full_ac.tsv"), "BaseCellCounter --min_ac 2")
+
+
+def test_bed_and_bed_out_windows_match_reference(work):
+    """MakeWindows with --bed / --bed_out (BaseCellCounter.py:87-110): the host interval arithmetic of
+    longsom_b200/windows.py against tables the reference wrote over the pybedtools stand-in (golden g1)."""
+    import pipeline_inputs as pi
+    from longsom_b200.engine import CountParams
+    case, d, p, data = work
+    if not has_gold(case, "counts.full_bed.tsv"):
+        return  # the --bed goldens were generated for g1
+    bed, bed_out = pi.write_beds(case, d, data)
+    prm = CountParams(min_bq=20, min_mq=60, min_dp=3, min_cc=2)
+    for name, kw, chrom, bin_size in (("bed", dict(bed=bed), "all", 50000),
+                                      ("bed_out", dict(bed=bed, bed_out=bed_out), data.contig_names[0], 50000),
+                                      ("bedout_only", dict(bed_out=bed_out), "all", 20000)):
+        out = os.path.join(d, "o_%s.tsv" % name)
+        _count_with_oracle(p["full"], p["ref"], chrom, bin_size, prm, "full." + name, out, **kw)
+        assert_same(file_lines(out), gold_lines(case, "counts.full_%s.tsv" % name), "BaseCellCounter --" + name)
+
+
+def test_windows_with_1e5_intervals_are_fast():
+    """bedtools does these as sorted sweeps; the stand-alone arithmetic must not be quadratic."""
+    import time
+    from longsom_b200 import windows as W
+    rng = np.random.default_rng(3)
+    starts = np.sort(rng.integers(0, 50_000_000, size=100_000))
+    a = [("chr1", int(s), int(s) + 120) for s in starts]
+    b = [("chr1", int(s) + 60, int(s) + 90) for s in starts[::2]] + [("chr2", 5, 10)]
+    t0 = time.time()
+    m = W._merge(a, 1)
+    i = W._intersect(m, [("chr1", 1, 40_000_000), ("chr2", 1, 1000)])
+    r = W._subtract(i, b)
+    assert time.time() - t0 < 20.0
+    assert len(r) >= len(i) and all(e > s for _, s, e in r)
 
 
 def test_merge_matches_reference(work):
@@ -148,6 +204,8 @@ def test_step2_host_logic_matches_reference(work):
     variant_calling_step2(os.path.join(d, "step1.tsv"), 0, p["editing"], p["pon_sr"], p["pon_lr"], p["gnomad"], 0.01, out,
                           OracleEngine())
     assert_same(file_lines(out), gold_lines(case, "step2.tsv"), "BaseCellCalling.step2")
+    if not has_gold(case, "step2_gz.tsv"):
+        return
     out = os.path.join(d, "step2gz_mine.tsv")
     variant_calling_step2(os.path.join(d, "step1.tsv"), 5, p["editing_gz"], p["pon_sr"], "", p["gnomad"], 0.01, out,
                           OracleEngine())
@@ -167,6 +225,8 @@ def test_genotype_host_logic_matches_reference(work, monkeypatch):
     case, d, p, data = work
     monkeypatch.setattr(G, "Engine", _GenoOracleEngine)
     for flag in ("All", "Alt"):
+        if not has_gold(case, "geno_%s.DpMatrix.tsv" % flag):
+            continue
         pre = os.path.join(d, "geno_" + flag)
         G.main(["--bam", p["full"], "--infile", os.path.join(d, "candidates.tsv"), "--ref", p["ref"], "--meta", p["meta"],
                 "--fusions", "--outfile", pre, "--alt_flag", flag, "--min_mq", "60", "--alpha2", str(pi.ALPHA2), "--beta2",
@@ -174,6 +234,8 @@ def test_genotype_host_logic_matches_reference(work, monkeypatch):
         for suf in ("SingleCellGenotype", "DpMatrix", "AltMatrix", "VAFMatrix", "BinaryMatrix"):
             assert_same(file_lines("%s.%s.tsv" % (pre, suf)), gold_lines(case, "geno_%s.%s.tsv" % (flag, suf)),
                         "SingleCellGenotype %s %s" % (flag, suf))
+    if not has_gold(case, "hccv.tsv"):
+        return
     out = os.path.join(d, "hccv_mine.tsv")
     G.main(["--bam", p["full"], "--infile", os.path.join(d, "candidates.tsv"), "--ref", p["ref"], "--meta", p["meta"],
             "--outfile", out, "--alt_flag", "All", "--min_mq", "60", "--tmp_dir", os.path.join(d, "tmph")], hccv=True)
@@ -288,6 +350,8 @@ def test_reannotation_matches_reference(work):
     table and the committed fabricated fusion table; three (min_variants, min_frac) settings."""
     from longsom_b200.cli.reannotate import main
     case, d, p, data = work
+    if not has_gold(case, "hccv.tsv"):
+        return  # core-stages-only case (g3)
     for name in ("hccv.tsv", "reannot_fusions.tsv"):
         with gzip.open(os.path.join(GOLD, case, name + ".gz"), "rb") as f, open(os.path.join(d, name), "wb") as o:
             o.write(f.read())
@@ -320,7 +384,7 @@ def test_step1_worker_processes_do_not_change_the_output(work):
     import pipeline_inputs as pi
     from longsom_b200.cli.step1 import variant_calling_step1
     case, d, p, data = work
-    for procs in (2, 3, 5):
+    for procs in ((3,) if case == "g3" else (2, 3, 5)):
         out = os.path.join(d, "step1_mp%d.tsv" % procs)
         n_rows, n_q = variant_calling_step1(os.path.join(d, "merged.tsv"), out, p["ref"], pi.ALPHA1, pi.BETA1, pi.ALPHA2, pi.BETA2,
                                             2, 3, 5, 5, 2, 1, 1, OracleEngine(), procs=procs)
