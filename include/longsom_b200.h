@@ -183,6 +183,26 @@ int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int32_t *site_
                       const uint8_t *alt_class, int64_t n_sites, int32_t n_cells,
                       const ls_geno_params *params, int32_t *dp, int32_t *alt, ls_run_stats *stats);
 
+/* Sparse form of the same computation, for candidate lists whose dense [site][cell] tensors would not fit (2e5 sites
+ * x 2e4 cells = 32 GB): only the TOUCHED (site, cell) pairs -- Dp > 0 -- leave the device, sorted by (site, cell), with
+ * the beta-binomial tail of SingleCellGenotype.py:204 / HCCVSingleCellGenotype.py:204 already evaluated on the device:
+ *   p = betabinom.sf(Alt - eps, Dp, alpha, beta)  for pairs with Alt > 0 at sites with skip_p[site] == 0, NaN otherwise
+ * (skip_p marks the sites that take the chrM shortcut, :195-199; may be NULL).  run keeps the tuples in HBM and returns
+ * their number, fetch copies them out; the dense rows of the reference are an expansion of these tuples.            */
+typedef struct ls_geno_tuples {
+  int64_t capacity;  /* in */
+  int64_t n_tuples;  /* out */
+  int32_t *site;     /* [capacity] index into the site arrays of the run */
+  int32_t *cell;     /* [capacity] */
+  int32_t *dp;       /* [capacity] */
+  int32_t *alt;      /* [capacity] */
+  double *p;         /* [capacity] */
+} ls_geno_tuples;
+int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, const int32_t *site_pos, const uint8_t *alt_class,
+                           const uint8_t *skip_p, int64_t n_sites, int32_t n_cells, const ls_geno_params *params,
+                           double alpha, double beta, int64_t *n_tuples, ls_run_stats *stats);
+int ls_genotype_sparse_fetch(ls_ctx *ctx, ls_geno_tuples *out);
+
 /* ---- K2: beta-binomial tails ---------------------------------------------------------------
  * Replaces scipy.stats.betabinom.sf / 1-cdf as called at BaseCellCalling.step1.py:196,201,
  * 329-330,427-428, SingleCellGenotype.py:204, HCCVSingleCellGenotype.py:204.

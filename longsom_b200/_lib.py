@@ -16,10 +16,11 @@ CLASS_NAMES = ["A", "C", "T", "G", "I", "D", "N", "O"]
 CLASS_ID = {c: i for i, c in enumerate(CLASS_NAMES)}
 LS_CLASS_NA = 8
 
-# every symbol include/longsom_b200.h declares (checked by tests/test_abi.py)
+# every symbol include/longsom_b200.h declares (checked by tests/test_cpu.py::test_abi_exports_every_declared_symbol)
 ABI_SYMBOLS = [
     "ls_abi_version", "ls_ctx_create", "ls_ctx_destroy", "ls_last_error", "ls_host_alloc", "ls_host_free",
     "ls_pileup_upload", "ls_pileup_run", "ls_pileup_fetch", "ls_pileup_count", "ls_genotype_count",
+    "ls_genotype_sparse_run", "ls_genotype_sparse_fetch",
     "ls_betabinom_sf", "ls_site_mask", "ls_device_synchronize", "ls_flush_l2",
 ]
 
@@ -48,6 +49,11 @@ class LsCountParams(C.Structure):
 class LsGenoParams(C.Structure):
     _fields_ = [("min_bq", C.c_int32), ("min_mq", C.c_int32), ("max_depth", C.c_int32), ("alt_only", C.c_int32),
                 ("bin_size", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LsGenoTuples(C.Structure):
+    _fields_ = [("capacity", C.c_int64), ("n_tuples", C.c_int64), ("site", C.c_void_p), ("cell", C.c_void_p),
+                ("dp", C.c_void_p), ("alt", C.c_void_p), ("p", C.c_void_p)]
 
 
 class LsRunStats(C.Structure):
@@ -97,6 +103,9 @@ def load():
                                     P(LsRunStats)]
     lib.ls_genotype_count.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
                                       P(LsGenoParams), C.c_void_p, C.c_void_p, P(LsRunStats)]
+    lib.ls_genotype_sparse_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                           P(LsGenoParams), C.c_double, C.c_double, P(C.c_int64), P(LsRunStats)]
+    lib.ls_genotype_sparse_fetch.argtypes = [C.c_void_p, P(LsGenoTuples)]
     lib.ls_betabinom_sf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                                     C.c_int64, P(LsRunStats)]
     lib.ls_site_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

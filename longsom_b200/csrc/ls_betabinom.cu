@@ -51,6 +51,49 @@ __global__ void __launch_bounds__(128) bb_sum_kernel(const int32_t *__restrict__
   p[q] = ls_sf_finish(k[q], n[q], cdf);
 }
 
+// Queries with k <= BB_SMALL (every beta-binomial call of the genotype path, most of step1's): one thread per
+// query, the pmf terms stay in the thread's local array and numpy's pairwise order is replayed on them -- nothing is
+// staged in HBM.  k <= 0 (no query / k - eps < 0) and k > n follow ls_sf_finish; a query past BB_SMALL gets p = -1 and
+// is counted in *nbig (the staged kernels above take it).  no_query_nan: k == 0 means "no query" -> NaN.
+constexpr int BB_SMALL = 128;
+
+__global__ void __launch_bounds__(128) bb_small_kernel(const int32_t *__restrict__ k, const int32_t *__restrict__ n, int64_t m,
+                                                       double a, double b, const double *__restrict__ lab_p,
+                                                       double *__restrict__ p, uint32_t *__restrict__ nbig, int no_query_nan) {
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= m) return;
+  const int kk = k[q], nn = n[q];
+  if (kk == 0 && no_query_nan) {
+    p[q] = NAN;
+    return;
+  }
+  if (nn < 0 || kk <= 0 || kk > nn) {
+    p[q] = ls_sf_finish(kk, nn, 0.0);
+    return;
+  }
+  if (kk > BB_SMALL) {
+    p[q] = -1.0;
+    if (nbig) atomicAdd(nbig, 1u);
+    return;
+  }
+  double t[BB_SMALL];
+  const double lab = lab_p[0], dn = (double)nn, lnp1 = log(dn + 1.0);
+  for (int i = 0; i < kk; ++i) t[i] = exp(ls_betabinom_logpmf((double)i, dn, a, b, lnp1, lab));
+  p[q] = ls_sf_finish(kk, nn, ls_pairwise_sum(t, kk));
+}
+
+// device arrays in, device array out (used by the sparse genotype path)
+int ls_betabinom_device(ls_ctx *ctx, const int32_t *d_k, const int32_t *d_n, double a, double b, double *d_p, int64_t m,
+                        uint32_t *d_nbig) {
+  if (m <= 0) return LS_OK;
+  cudaStream_t st = ctx->stream;
+  LS_CK(ctx->g_c.ensure(64));
+  bb_const_kernel<<<1, 1, 0, st>>>(a, b, ctx->g_c.as<double>());
+  bb_small_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_k, d_n, m, a, b, ctx->g_c.as<double>(), d_p, d_nbig, 1);
+  LS_CK(cudaGetLastError());
+  return LS_OK;
+}
+
 extern "C" int ls_betabinom_sf(ls_ctx *ctx, const int32_t *k, const int32_t *n, double a, double b, double *p,
                                int64_t m, ls_run_stats *stats) {
   if (!ctx) return LS_E_ARG;
@@ -65,11 +108,49 @@ extern "C" int ls_betabinom_sf(ls_ctx *ctx, const int32_t *k, const int32_t *n, 
     return LS_OK;
   }
   const uint64_t CAP = (uint64_t)1 << 26;  // pmf terms staged per chunk (512 MB of doubles)
-  LS_CK(cudaDeviceSetLimit(cudaLimitStackSize, 4096));
   LS_CK(ctx->g_e.ensure(64));
   bb_const_kernel<<<1, 1, 0, st>>>(a, b, ctx->g_e.as<double>());
   int launches = 1;
   float ms_total = 0.f;
+  // pass 1: every query with k <= BB_SMALL, in registers / local memory
+  std::vector<int64_t> big;
+  {
+    LS_CK(ctx->g_a.ensure((size_t)m * 4));
+    LS_CK(ctx->g_b.ensure((size_t)m * 4));
+    LS_CK(ctx->g_d.ensure((size_t)m * 8));
+    LS_CK(cudaMemcpyAsync(ctx->g_a.p, k, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaMemcpyAsync(ctx->g_b.p, n, (size_t)m * 4, cudaMemcpyHostToDevice, st));
+    LS_CK(cudaEventRecord(ctx->ev[0], st));
+    bb_small_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(ctx->g_a.as<int32_t>(), ctx->g_b.as<int32_t>(), m, a, b,
+                                                                 ctx->g_e.as<double>(), ctx->g_d.as<double>(), nullptr, 0);
+    ++launches;
+    LS_CK(cudaGetLastError());
+    LS_CK(cudaEventRecord(ctx->ev[1], st));
+    LS_CK(cudaMemcpyAsync(p, ctx->g_d.p, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    LS_CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    LS_CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    ms_total += ms;
+    for (int64_t i = 0; i < m; ++i) {
+      if (k[i] > BB_SMALL && n[i] >= 0 && k[i] <= n[i]) big.push_back(i);
+      if (k[i] > 0 && k[i] <= BB_SMALL && n[i] >= 0 && k[i] <= n[i]) S.n_events += k[i];
+    }
+  }
+  // pass 2: the long tails (k > BB_SMALL), pmf terms staged in HBM, one thread per term
+  std::vector<int32_t> bk(big.size()), bn(big.size());
+  std::vector<double> bp(big.size());
+  for (size_t j = 0; j < big.size(); ++j) {
+    bk[j] = k[big[j]];
+    bn[j] = n[big[j]];
+  }
+  const int32_t *k_all = k, *n_all = n;
+  double *p_all = p;
+  (void)k_all;
+  (void)n_all;
+  k = bk.data();
+  n = bn.data();
+  p = bp.data();
+  m = (int64_t)big.size();
   std::vector<uint64_t> off;
   int64_t q0 = 0;
   while (q0 < m) {
@@ -115,6 +196,7 @@ extern "C" int ls_betabinom_sf(ls_ctx *ctx, const int32_t *k, const int32_t *n, 
     S.n_events += (int64_t)tot;
     q0 = q1;
   }
+  for (size_t j = 0; j < big.size(); ++j) p_all[big[j]] = bp[j];
   S.ms_count = ms_total;
   S.ms_total = ms_total;
   S.count_launches = launches;

@@ -124,6 +124,10 @@ struct ls_ctx {
   DBuf out_tid, out_pos, out_ref, out_counts;
   DBuf l2_scratch;
   DBuf g_a, g_b, g_c, g_d, g_e;  // genotype / betabinom / mask scratch
+  DBuf gs_cnt, gs_hits_a, gs_hits_b, gs_flag, gs_tup, gs_p, gs_skip;  // sparse genotyping
+  int64_t n_tuples = 0;
+  bool have_tuples = false;
+  double gs_alpha = 0.0, gs_beta = 0.0;
 };
 
 #define LS_CK(call)                                                                        \

@@ -32,7 +32,10 @@ struct GenoArgs {
   int min_bq, min_mq, alt_only;
   const uint64_t *drop_keys;  // (bin<<32 | read) removed by the depth cap
   int64_t n_drop;
-  int32_t *dp, *alt;
+  int32_t *dp, *alt;            // dense [site][cell] tensors (dense mode), else null
+  uint32_t *hit_cnt;            // sparse pass 1: hits per read
+  const uint32_t *hit_off;      // sparse pass 2: first hit slot of every read (exclusive scan of hit_cnt)
+  uint64_t *hits;               // sparse pass 2: (site * n_cells + cell) << 1 | (class == ALT_expected)
   unsigned long long *n_events;
 };
 
@@ -62,10 +65,13 @@ __device__ __forceinline__ bool geno_dropped(const GenoArgs &a, uint32_t bin, ui
   return lo < a.n_drop && a.drop_keys[lo] == key;
 }
 
+// MODE 0: dense atomics, 1: count the read's hits, 2: write them at the read's slots
+template <int MODE>
 __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long nev = 0;
   if (r < a.n_reads) {
+    uint64_t *hp = MODE == 2 ? a.hits + a.hit_off[r] : nullptr;
     const uint32_t flag = a.flag[r];
     const int32_t cell = a.cell[r];
     const int32_t tid = a.tid[r];
@@ -109,8 +115,12 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
               const int ac = a.alt_class[s];
               const bool use = a.alt_only ? (cls == ac && cls != LS_CLASS_NA) : (cls != LS_CLASS_NA && cls != LS_CLASS_O);
               if (use) {
-                atomicAdd(&a.dp[(size_t)s * a.n_cells + cell], 1);
-                if (cls == ac) atomicAdd(&a.alt[(size_t)s * a.n_cells + cell], 1);
+                if (MODE == 0) {
+                  atomicAdd(&a.dp[(size_t)s * a.n_cells + cell], 1);
+                  if (cls == ac) atomicAdd(&a.alt[(size_t)s * a.n_cells + cell], 1);
+                } else if (MODE == 2) {
+                  *hp++ = (((uint64_t)s * (uint64_t)a.n_cells + (uint64_t)cell) << 1) | (cls == ac ? 1u : 0u);
+                }
                 ++nev;
               }
             }
@@ -127,10 +137,42 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
         }
       }
     }
+    if (MODE == 1) a.hit_cnt[r] = (uint32_t)nev;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nev += __shfl_xor_sync(0xffffffffu, nev, o);
   if ((threadIdx.x & 31) == 0 && nev) atomicAdd(a.n_events, nev);
+}
+
+// ---- sparse output: sorted hits -> one (site, cell, Dp, Alt) tuple per touched pair ---------------------------
+__global__ void __launch_bounds__(256) hit_flag_kernel(const uint64_t *__restrict__ hits, int64_t n, uint32_t *__restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  flag[i] = (i < n && (i == 0 || (hits[i] >> 1) != (hits[i - 1] >> 1))) ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256) hit_reduce_kernel(const uint64_t *__restrict__ hits, int64_t n,
+                                                         const uint32_t *__restrict__ rank, int32_t n_cells,
+                                                         const uint8_t *__restrict__ skip_p, int32_t *__restrict__ t_site,
+                                                         int32_t *__restrict__ t_cell, int32_t *__restrict__ t_dp,
+                                                         int32_t *__restrict__ t_alt, int32_t *__restrict__ t_k) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t key = hits[i] >> 1;
+  if (i > 0 && (hits[i - 1] >> 1) == key) return;  // not the first hit of its pair
+  int32_t dp = 0, alt = 0;
+  for (int64_t j = i; j < n && (hits[j] >> 1) == key; ++j) {  // the hits of a pair are adjacent; the alt ones last
+    ++dp;
+    alt += (int32_t)(hits[j] & 1u);
+  }
+  const uint32_t t = rank[i];
+  const int32_t site = (int32_t)(key / (uint64_t)n_cells);
+  t_site[t] = site;
+  t_cell[t] = (int32_t)(key - (uint64_t)site * (uint64_t)n_cells);
+  t_dp[t] = dp;
+  t_alt[t] = alt;
+  // beta-binomial query of the pair: k = Alt (0: none needed -- no alt reads, or the site takes the chrM shortcut)
+  t_k[t] = (skip_p && skip_p[site]) ? 0 : alt;
 }
 
 // read end (exclusive) per read, for the depth-cap pre-pass
@@ -262,6 +304,219 @@ static int geno_depth_cap(ls_ctx *ctx, const std::vector<int32_t> &btid, const s
   return LS_OK;
 }
 
+// Site table of a genotype call: sorted keys, the pileup() call (bin) of every site, and the bins.
+struct GenoSites {
+  std::vector<uint64_t> keys;
+  std::vector<uint32_t> sbin;
+  std::vector<int32_t> btid, bstart, bend;
+};
+
+static int geno_prepare_sites(ls_ctx *ctx, const int32_t *site_tid, const int32_t *site_pos, int64_t n_sites, int32_t bin,
+                              GenoSites &g) {
+  g.keys.resize((size_t)n_sites);
+  g.sbin.resize((size_t)n_sites);
+  for (int64_t i = 0; i < n_sites; ++i) {
+    if (site_tid[i] < 0 || site_pos[i] < 0) LS_FAIL(LS_E_ARG, "ls_genotype: negative site coordinate");
+    g.keys[i] = ((uint64_t)(uint32_t)site_tid[i] << 32) | (uint32_t)site_pos[i];
+    if (i > 0 && g.keys[i] <= g.keys[i - 1]) LS_FAIL(LS_E_ARG, "ls_genotype: sites must be sorted and unique");
+    // build_dict_variants: CHROM_floor(POS / bin) with the 1-based POS of the TSV (:253-274)
+    const int64_t code = ((int64_t)site_pos[i] + 1) / bin;
+    if (i == 0 || site_tid[i] != site_tid[i - 1] || code != ((int64_t)site_pos[i - 1] + 1) / bin) {
+      g.btid.push_back(site_tid[i]);
+      g.bstart.push_back(site_pos[i] - 1 < 0 ? 0 : site_pos[i] - 1);
+      g.bend.push_back(site_pos[i] + 1);
+    } else {
+      g.bend.back() = site_pos[i] + 1;
+    }
+    g.sbin[i] = (uint32_t)(g.btid.size() - 1);
+  }
+  return LS_OK;
+}
+
+static void geno_fill_args(ls_ctx *ctx, GenoArgs &a, int64_t n_sites, int32_t n_cells, const ls_geno_params *params) {
+  a.n_reads = ctx->n_reads;
+  a.tid = ctx->tid.as<int32_t>();
+  a.pos = ctx->pos.as<int32_t>();
+  a.cell = ctx->cell.as<int32_t>();
+  a.lq = ctx->lq.as<int32_t>();
+  a.flag = ctx->flag.as<uint16_t>();
+  a.mapq = ctx->mapq.as<uint8_t>();
+  a.cigar_off = ctx->cigar_off.as<uint32_t>();
+  a.cigar = ctx->cigar.as<uint32_t>();
+  a.base_off = ctx->base_off.as<uint64_t>();
+  a.seq4 = ctx->seq4_d();
+  a.qual = ctx->qual_d();
+  a.site_key = ctx->g_a.as<uint64_t>();
+  a.alt_class = ctx->g_b.as<uint8_t>();
+  a.site_bin = ctx->g_e.as<uint32_t>();
+  a.n_sites = n_sites;
+  a.n_cells = n_cells;
+  a.min_bq = params->min_bq;
+  a.min_mq = params->min_mq;
+  a.alt_only = params->alt_only;
+  a.drop_keys = ctx->drop_keys.as<uint64_t>();
+  a.n_drop = ctx->n_drop;
+  a.dp = a.alt = nullptr;
+  a.hit_cnt = nullptr;
+  a.hit_off = nullptr;
+  a.hits = nullptr;
+  a.n_events = ctx->counters.as<unsigned long long>();
+}
+
+int ls_betabinom_device(ls_ctx *ctx, const int32_t *d_k, const int32_t *d_n, double a, double b, double *d_p, int64_t m,
+                        uint32_t *d_nbig);
+
+// ---- sparse genotyping: only the touched (site, cell) pairs leave the device -------------------------------------
+extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, const int32_t *site_pos,
+                                      const uint8_t *alt_class, const uint8_t *skip_p, int64_t n_sites, int32_t n_cells,
+                                      const ls_geno_params *params, double alpha, double beta, int64_t *n_tuples,
+                                      ls_run_stats *stats) {
+  if (!ctx) return LS_E_ARG;
+  if (!params) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: params is null");
+  if (!ctx->have_batch) LS_FAIL(LS_E_STATE, "ls_genotype_sparse_run: no batch uploaded");
+  if (n_sites < 0 || n_cells < 0) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: negative size");
+  if (!(alpha > 0.0) || !(beta > 0.0)) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: alpha and beta must be > 0");
+  ls_run_stats S;
+  memset(&S, 0, sizeof S);
+  ctx->n_tuples = 0;
+  ctx->have_tuples = false;
+  ctx->gs_alpha = alpha;
+  ctx->gs_beta = beta;
+  if (n_tuples) *n_tuples = 0;
+  if (n_sites == 0 || n_cells == 0 || ctx->n_reads == 0) {
+    ctx->have_tuples = true;
+    if (stats) *stats = S;
+    return LS_OK;
+  }
+  if (!site_tid || !site_pos || !alt_class) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: null array");
+  if ((uint64_t)n_sites * (uint64_t)n_cells >= ((uint64_t)1 << 62)) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: too many pairs");
+  const int32_t bin = params->bin_size > 0 ? params->bin_size : 50000;
+  GenoSites g;
+  int rc = geno_prepare_sites(ctx, site_tid, site_pos, n_sites, bin, g);
+  if (rc != LS_OK) return rc;
+  LS_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  rc = geno_depth_cap(ctx, g.btid, g.bstart, g.bend, params->min_mq, params->max_depth);
+  if (rc != LS_OK) return rc;
+  const int64_t n = ctx->n_reads;
+  LS_CK(ctx->g_a.ensure((size_t)n_sites * 8));
+  LS_CK(ctx->g_b.ensure((size_t)n_sites));
+  LS_CK(ctx->g_e.ensure((size_t)n_sites * 4));
+  LS_CK(ctx->gs_skip.ensure((size_t)n_sites));
+  LS_CK(ctx->gs_cnt.ensure((size_t)(n + 1) * 4));
+  LS_CK(ctx->counters.ensure(128));
+  LS_CK(cudaMemcpyAsync(ctx->g_a.p, g.keys.data(), (size_t)n_sites * 8, cudaMemcpyHostToDevice, st));
+  LS_CK(cudaMemcpyAsync(ctx->g_b.p, alt_class, (size_t)n_sites, cudaMemcpyHostToDevice, st));
+  LS_CK(cudaMemcpyAsync(ctx->g_e.p, g.sbin.data(), (size_t)n_sites * 4, cudaMemcpyHostToDevice, st));
+  if (skip_p) LS_CK(cudaMemcpyAsync(ctx->gs_skip.p, skip_p, (size_t)n_sites, cudaMemcpyHostToDevice, st));
+  LS_CK(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
+  LS_CK(cudaMemsetAsync((uint32_t *)ctx->gs_cnt.p + n, 0, 4, st));
+  LS_CK(cudaEventRecord(ctx->ev[0], st));
+  GenoArgs a;
+  geno_fill_args(ctx, a, n_sites, n_cells, params);
+  unsigned long long *d_cnt = ctx->counters.as<unsigned long long>();
+  uint64_t *d_nhits = reinterpret_cast<uint64_t *>(d_cnt + 1), *d_ntup = reinterpret_cast<uint64_t *>(d_cnt + 2);
+  uint32_t *d_nbig = reinterpret_cast<uint32_t *>(d_cnt + 3);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  // pass 1: hits per read, their exclusive scan places every read's hits
+  a.hit_cnt = ctx->gs_cnt.as<uint32_t>();
+  genotype_kernel<1><<<grid, 256, 0, st>>>(a);
+  LS_CK(ls_scan_exclusive_u32(ctx->gs_cnt.as<uint32_t>(), ctx->gs_cnt.as<uint32_t>(), n + 1, d_nhits, ctx->scan_tmp, st));
+  uint64_t h[4] = {0, 0, 0, 0};
+  LS_CK(cudaMemcpyAsync(h, d_cnt, 32, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaStreamSynchronize(st));
+  const int64_t nh = (int64_t)h[1];
+  S.n_events = nh;
+  int launches = 4;
+  int64_t nt = 0;
+  if (nh >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: more than 2^32 hits; split the site list");
+  if (nh > 0) {
+    LS_CK(ctx->gs_hits_a.ensure((size_t)nh * 8));
+    LS_CK(ctx->gs_hits_b.ensure((size_t)nh * 8));
+    LS_CK(ctx->gs_flag.ensure((size_t)(nh + 1) * 4));
+    // pass 2: the hits themselves
+    a.hit_cnt = nullptr;
+    a.hit_off = ctx->gs_cnt.as<uint32_t>();
+    a.hits = ctx->gs_hits_a.as<uint64_t>();
+    LS_CK(cudaMemsetAsync(d_cnt, 0, 8, st));
+    genotype_kernel<2><<<grid, 256, 0, st>>>(a);
+    uint64_t *sorted = nullptr;
+    const int key_bits = ls_bits_for((uint64_t)n_sites * (uint64_t)n_cells * 2u);
+    LS_CK(ls_radix_sort_keys(ctx->gs_hits_a.as<uint64_t>(), ctx->gs_hits_b.as<uint64_t>(), nh, key_bits, ctx->rs_hist, &sorted,
+                             ctx->num_sms, st, &launches));
+    hit_flag_kernel<<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>());
+    LS_CK(ls_scan_exclusive_u32(ctx->gs_flag.as<uint32_t>(), ctx->gs_flag.as<uint32_t>(), nh + 1, d_ntup, ctx->scan_tmp, st));
+    LS_CK(cudaMemcpyAsync(h, d_cnt, 32, cudaMemcpyDeviceToHost, st));
+    LS_CK(cudaStreamSynchronize(st));
+    nt = (int64_t)h[2];
+    LS_CK(ctx->gs_tup.ensure((size_t)nt * 5 * 4 + 16));
+    LS_CK(ctx->gs_p.ensure((size_t)nt * 8 + 16));
+    int32_t *t_site = ctx->gs_tup.as<int32_t>(), *t_cell = t_site + nt, *t_dp = t_cell + nt, *t_alt = t_dp + nt,
+            *t_k = t_alt + nt;
+    hit_reduce_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
+                                                                    skip_p ? ctx->gs_skip.as<uint8_t>() : nullptr, t_site, t_cell,
+                                                                    t_dp, t_alt, t_k);
+    launches += 6;
+    LS_CK(cudaGetLastError());
+    LS_CK(cudaEventRecord(ctx->ev[1], st));
+    // K2 on the device: p = betabinom.sf(Alt - eps, Dp, alpha, beta) for the pairs with a query
+    rc = ls_betabinom_device(ctx, t_k, t_dp, alpha, beta, ctx->gs_p.as<double>(), nt, d_nbig);
+    if (rc != LS_OK) return rc;
+    launches += 2;
+  } else {
+    LS_CK(cudaEventRecord(ctx->ev[1], st));
+  }
+  LS_CK(cudaEventRecord(ctx->ev[2], st));
+  LS_CK(cudaStreamSynchronize(st));
+  LS_CK(cudaEventElapsedTime(&S.ms_count, ctx->ev[0], ctx->ev[1]));
+  LS_CK(cudaEventElapsedTime(&S.ms_sort, ctx->ev[1], ctx->ev[2]));  // here: the beta-binomial kernel
+  LS_CK(cudaEventElapsedTime(&S.ms_total, ctx->ev[0], ctx->ev[2]));
+  S.n_segments = nt;
+  S.count_launches = launches;
+  ctx->n_tuples = nt;
+  ctx->have_tuples = true;
+  ctx->n_drop = 0;
+  if (n_tuples) *n_tuples = nt;
+  if (stats) *stats = S;
+  return LS_OK;
+}
+
+extern "C" int ls_genotype_sparse_fetch(ls_ctx *ctx, ls_geno_tuples *out) {
+  if (!ctx) return LS_E_ARG;
+  if (!out) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_fetch: out is null");
+  if (!ctx->have_tuples) LS_FAIL(LS_E_STATE, "ls_genotype_sparse_fetch: ls_genotype_sparse_run has not completed");
+  const int64_t nt = ctx->n_tuples;
+  out->n_tuples = nt;
+  if (nt == 0) return LS_OK;
+  if (out->capacity < nt) LS_FAIL(LS_E_CAPACITY, "ls_genotype_sparse_fetch: capacity < n_tuples");
+  if (!out->site || !out->cell || !out->dp || !out->alt || !out->p) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_fetch: null array");
+  LS_CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const int32_t *t = ctx->gs_tup.as<int32_t>();
+  LS_CK(cudaMemcpyAsync(out->site, t, (size_t)nt * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(out->cell, t + nt, (size_t)nt * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(out->dp, t + 2 * nt, (size_t)nt * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(out->alt, t + 3 * nt, (size_t)nt * 4, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaMemcpyAsync(out->p, ctx->gs_p.p, (size_t)nt * 8, cudaMemcpyDeviceToHost, st));
+  LS_CK(cudaStreamSynchronize(st));
+  // pairs whose Alt count is past the in-register kernel's range (marked p = -1): the staged path
+  std::vector<int64_t> big;
+  for (int64_t i = 0; i < nt; ++i)
+    if (out->p[i] == -1.0) big.push_back(i);
+  if (!big.empty()) {
+    std::vector<int32_t> k(big.size()), nn(big.size());
+    std::vector<double> pp(big.size());
+    for (size_t j = 0; j < big.size(); ++j) {
+      k[j] = out->alt[big[j]];
+      nn[j] = out->dp[big[j]];
+    }
+    int rc = ls_betabinom_sf(ctx, k.data(), nn.data(), ctx->gs_alpha, ctx->gs_beta, pp.data(), (int64_t)big.size(), nullptr);
+    if (rc != LS_OK) return rc;
+    for (size_t j = 0; j < big.size(); ++j) out->p[big[j]] = pp[j];
+  }
+  return LS_OK;
+}
+
 extern "C" int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int32_t *site_pos,
                                  const uint8_t *alt_class, int64_t n_sites, int32_t n_cells,
                                  const ls_geno_params *params, int32_t *dp, int32_t *alt, ls_run_stats *stats) {
@@ -340,7 +595,10 @@ extern "C" int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int
   a.alt = ctx->g_d.as<int32_t>();
   a.n_events = ctx->counters.as<unsigned long long>();
   LS_CK(cudaEventRecord(ctx->ev[1], st));
-  if (ctx->n_reads > 0) genotype_kernel<<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, st>>>(a);
+  a.hit_cnt = nullptr;
+  a.hit_off = nullptr;
+  a.hits = nullptr;
+  if (ctx->n_reads > 0) genotype_kernel<0><<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, st>>>(a);
   LS_CK(cudaGetLastError());
   LS_CK(cudaEventRecord(ctx->ev[2], st));
   LS_CK(cudaMemcpyAsync(dp, ctx->g_c.p, cells * 4, cudaMemcpyDeviceToHost, st));

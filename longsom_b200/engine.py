@@ -115,6 +115,32 @@ class Engine:
         self.last_stats = st.as_dict()
         return dp, alt
 
+    def genotype_sparse(self, site_tid, site_pos, alt_class, n_cells, alpha, beta, skip_p=None, min_bq=30, min_mq=255,
+                        max_depth=200000, alt_only=False, bin_size=50000, fetch=True):
+        """Touched (site, cell) pairs only, sorted by (site, cell): (site, cell, dp, alt, p) arrays, p = beta-binomial
+        tail of pairs with alt > 0 at sites with skip_p == 0 (NaN elsewhere), evaluated on the device.
+        fetch=False leaves the tuples in HBM and returns their number (bench: device-resident rate)."""
+        site_tid = np.ascontiguousarray(site_tid, np.int32)
+        site_pos = np.ascontiguousarray(site_pos, np.int32)
+        alt_class = np.ascontiguousarray(alt_class, np.uint8)
+        n = site_pos.shape[0]
+        sk = None if skip_p is None else np.ascontiguousarray(skip_p, np.uint8)
+        gp = L.LsGenoParams(int(min_bq), int(min_mq), int(max_depth), 1 if alt_only else 0, int(bin_size), 0)
+        st, nt = L.LsRunStats(), C.c_int64(0)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+        self._check(self._lib.ls_genotype_sparse_run(self._ctx, vp(site_tid), vp(site_pos), vp(alt_class), vp(sk), n,
+                                                     int(n_cells), C.byref(gp), float(alpha), float(beta), C.byref(nt),
+                                                     C.byref(st)), "ls_genotype_sparse_run")
+        self.last_stats = st.as_dict()
+        m = int(nt.value)
+        if not fetch:
+            return m
+        site, cell, dp, alt = (np.zeros(m, np.int32) for _ in range(4))
+        p = np.zeros(m, np.float64)
+        t = L.LsGenoTuples(m, 0, vp(site), vp(cell), vp(dp), vp(alt), vp(p))
+        self._check(self._lib.ls_genotype_sparse_fetch(self._ctx, C.byref(t)), "ls_genotype_sparse_fetch")
+        return site, cell, dp, alt, p
+
     # ---- K2 ------------------------------------------------------------------------------
     def betabinom_sf(self, k, n, a, b):
         """p[i] = scipy.stats.betabinom.sf(k[i] - eps, n[i], a, b) for any 0 < eps < 1 (integer k)."""

@@ -126,6 +126,72 @@ def test_c5_genotyping_sweep(engine, n_sites, n_cells, scale):
     assert len(ri) > 0
 
 
+def _check_sparse_against_dense(engine, tid, pos, alt, n_cells, dp, al, a2, b2, skip=None):
+    """The sparse tuples must be exactly the non-zero entries of the dense tensors, in (site, cell) order, with the
+    device-side beta-binomial tails equal to the separately evaluated ones."""
+    from scipy.stats import betabinom
+    site, cell, sdp, sal, p = engine.genotype_sparse(tid, pos, alt, n_cells, a2, b2, skip_p=skip, min_bq=30, min_mq=60)
+    ri, ci = np.nonzero(dp > 0)
+    assert np.array_equal(site, ri) and np.array_equal(cell, ci)
+    assert np.array_equal(sdp, dp[ri, ci]) and np.array_equal(sal, al[ri, ci])
+    q = sal > 0
+    if skip is not None:
+        q &= skip[site] == 0
+    assert np.all(np.isnan(p[~q]))
+    ref = betabinom.sf(sal[q] - 0.001, sdp[q], a2, b2)
+    assert np.all(np.abs(p[q] - ref) <= 1e-9 * ref + 1e-12)
+    assert np.array_equal(np.round(p[q], 4), np.round(ref, 4))
+    return int(q.sum())
+
+
+def test_sparse_genotyping_equals_dense(engine):
+    import oracle
+    cfg = synth.config("C5", scale=0.02)
+    cfg["n_cells"] = 2000
+    d = synth.generate(**cfg)
+    sc = engine.pileup_count(d.batch, _windows(d), CountParams(min_mq=60))
+    rng = np.random.default_rng(7)
+    idx = np.sort(rng.choice(sc.n_sites, size=min(5000, sc.n_sites), replace=False))
+    alt = rng.integers(0, 6, size=idx.shape[0]).astype(np.uint8)
+    a2, b2 = 0.2474528917555431, 162.03696139428595
+    odp, oal = oracle.genotype_count(d.batch, sc.tid[idx], sc.pos[idx], alt, 2000, min_bq=30, min_mq=60)
+    assert _check_sparse_against_dense(engine, sc.tid[idx], sc.pos[idx], alt, 2000, odp, oal, a2, b2) > 100
+    skip = (np.arange(idx.shape[0]) % 3 == 0).astype(np.uint8)  # every third site takes the chrM shortcut: no tail
+    _check_sparse_against_dense(engine, sc.tid[idx], sc.pos[idx], alt, 2000, odp, oal, a2, b2, skip=skip)
+    # --alt_flag Alt
+    odp, oal = oracle.genotype_count(d.batch, sc.tid[idx], sc.pos[idx], alt, 2000, min_bq=30, min_mq=60, alt_only=True)
+    site, cell, sdp, sal, p = engine.genotype_sparse(sc.tid[idx], sc.pos[idx], alt, 2000, a2, b2, min_bq=30, min_mq=60,
+                                                     alt_only=True)
+    ri, ci = np.nonzero(odp > 0)
+    assert np.array_equal(site, ri) and np.array_equal(cell, ci) and np.array_equal(sdp, odp[ri, ci])
+    assert np.array_equal(sal, oal[ri, ci])
+
+
+def test_c5_top_of_grid_sparse(engine):
+    """BASELINE.json configs[4] at the top of its grid: 200 000 candidate sites x 20 000 cells (dense tensors would be
+    32 GB).  The sparse tuples are compared with the oracle's dense tensors site chunk by site chunk."""
+    import oracle
+    d = synth.generate(**synth.config("C5", scale=1.0))
+    sc = engine.pileup_count(d.batch, _windows(d), CountParams(min_mq=60))
+    n_cells = 20000
+    rng = np.random.default_rng(11)
+    idx = np.sort(rng.choice(sc.n_sites, size=200000, replace=False))
+    alt = rng.integers(0, 4, size=idx.shape[0]).astype(np.uint8)
+    a2, b2 = 0.2474528917555431, 162.03696139428595
+    site, cell, sdp, sal, p = engine.genotype_sparse(sc.tid[idx], sc.pos[idx], alt, n_cells, a2, b2, min_bq=30, min_mq=60)
+    assert engine.last_stats["ms_total"] < 10000.0
+    step = 10000
+    for c0 in range(0, idx.shape[0], step * 4):  # every fourth chunk: 5 x (10 000 x 20 000) dense oracle tensors
+        j = idx[c0:c0 + step]
+        odp, oal = oracle.genotype_count(d.batch, sc.tid[j], sc.pos[j], alt[c0:c0 + step], n_cells, min_bq=30, min_mq=60)
+        ri, ci = np.nonzero(odp > 0)
+        lo, hi = np.searchsorted(site, c0), np.searchsorted(site, c0 + len(j))
+        assert np.array_equal(site[lo:hi] - c0, ri) and np.array_equal(cell[lo:hi], ci)
+        assert np.array_equal(sdp[lo:hi], odp[ri, ci]) and np.array_equal(sal[lo:hi], oal[ri, ci])
+    q = sal > 0
+    assert q.sum() > 0 and np.all(np.isfinite(p[q])) and np.all((p[q] >= 0) & (p[q] <= 1)) and np.all(np.isnan(p[~q]))
+
+
 def test_linearity_over_disjoint_cell_sets(engine):
     """Size-independent property on a larger batch (250k reads): every output word is additive over
     batches with disjoint cells -- counts(all) == counts(even cells) + counts(odd cells)."""
