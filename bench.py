@@ -8,7 +8,8 @@ Workload (BASELINE.json configs[1]/[2]): whole-transcriptome synthetic PacBio-Ki
 batch, 5M reads x ~1.5 kb, 5k cells; at N > 1 the SAME batch is sharded by coverage-balanced
 genomic bins across the GPUs (strong scaling, no collective on the data path).
 A "step" is one pass of the hot path over the resident batch: segment build -> (tile, cell)
-sort -> pileup-count kernel -> per-tile site tables in HBM.  `value` is device-resident
+sort -> unit expansion -> pileup-count kernel -> compaction of the passing sites into the reference's
+output order (the compacted site list in HBM is what BaseCellCounter emits).  `value` is device-resident
 throughput, `e2e` is the same metric from pinned HOST buffers (H2D of the batch and D2H of the compacted
 site table inside the timing): the batch cut into --e2e-shards window shards, the C-ABI call ls_pileup_count()
 per shard on --e2e-lanes CUDA contexts of the GPU (pipeline.count_shards_pipelined), so that transfers and
@@ -299,29 +300,33 @@ def run_ours(args, rank, world, local_rank):
     n_sites = 0
     for _ in range(args.warmup):
         n_sites = eng.run(prm)
+        eng.compact()
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
     barrier()
     t0 = time.perf_counter()
-    ms_count, ms_total, launches = [], [], 0
+    ms_count, ms_total, ms_compact, launches = [], [], [], 0
     for _ in range(args.steps):
         n_sites = eng.run(prm)
         st = eng.last_stats
         ms_count.append(st["ms_count"])
         ms_total.append(st["ms_total"])
         launches += st["count_launches"]
+        eng.compact()
+        ms_compact.append(eng.last_stats["ms_compact"])
+        launches += 1
     barrier()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
     dt = reduce_max(dt)
     ms_per_step = 1e3 * dt / args.steps
     value = total_units / (dt / args.steps)
-    st = eng.last_stats
 
     # ---- roofline of the dominant kernel (pileup_count_kernel), live CUDA-event timing ---------
     peak, peak_src = measured_peak()
     alg = algorithmic_bytes(batch, st["n_tiles"], tile, n_sites)
+    c_ms = float(np.mean(ms_compact))
     k_ms = float(np.mean(ms_count))
     achieved = alg / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     traffic = None
@@ -334,7 +339,9 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "pileup_count_kernel", "kernel_ms": k_ms,
                 "algorithmic_bytes_per_launch": alg, "bytes_per_aligned_base": alg / max(1, info["batch_aligned"]),
-                "peak_source": peak_src, "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None}
+                "peak_source": peak_src, "kernel_share_of_step": k_ms / ms_per_step if ms_per_step else None,
+                "issue_slot_ceiling": "see profiles/README.md: the kernel is bound by instruction issue and shared-memory "
+                                      "wavefronts, not by HBM"}
 
     # ---- end to end through the C-ABI with pinned host buffers ---------------------------------
     def pin(a):
@@ -399,30 +406,79 @@ def run_ours(args, rank, world, local_rank):
             l.close()
         del shards, outs
 
-    # ---- second half of BASELINE.json's metric: candidate sites genotyped / s (K1' + K2), N=1 only -----------------
+    # ---- second half of BASELINE.json's metric: candidate sites genotyped / s (K1' + K2), every N -------------------
+    # 200 000 candidate sites over the whole batch (each rank takes the ones inside its window shard), all cells of
+    # the workload; sparse path: touched (site, cell) tuples + on-device beta-binomial tails.
     secondary = None
-    if world == 1:
+    if not args.no_secondary:
         got = eng.fetch(n_sites) if n_sites else None
-        if got is not None and got.n_sites >= 1000:
-            rng = np.random.default_rng(0)
-            n_cand, n_cells = min(10000, got.n_sites), info["cfg"]["n_cells"]
+        share = wl["owned_aligned"] / max(1.0, total_units)
+        n_cand = int(min(got.n_sites if got is not None else 0, round(200000 * args.scale * share)))
+        n_cells = info["cfg"]["n_cells"]
+        g_dev_ms, g_e2e_ms, n_tup, gk_ms, bb_ms, hits = 0.0, 0.0, 0, 0.0, 0.0, 0
+        if n_cand >= 100:
+            rng = np.random.default_rng(rank)
             idx = np.sort(rng.choice(got.n_sites, size=n_cand, replace=False))
             alt = rng.integers(0, 4, size=n_cand).astype(np.uint8)
-            eng.genotype_count(got.tid[idx], got.pos[idx], alt, n_cells, min_bq=30, min_mq=60)  # warm
+            gt, gp = got.tid[idx].copy(), got.pos[idx].copy()
+            a2, b2 = 0.2474528917555431, 162.03696139428595
+            eng.genotype_sparse(gt, gp, alt, n_cells, a2, b2, min_bq=30, min_mq=60, fetch=False)  # warm
+            barrier()
             t0 = time.perf_counter()
-            dp, al = eng.genotype_count(got.tid[idx], got.pos[idx], alt, n_cells, min_bq=30, min_mq=60)
-            t_geno = time.perf_counter() - t0
-            k_ms = eng.last_stats["ms_count"]
-            ri, ci = np.nonzero(al > 0)
+            n_tup = eng.genotype_sparse(gt, gp, alt, n_cells, a2, b2, min_bq=30, min_mq=60, fetch=False)
+            barrier()
+            g_dev_ms = 1e3 * (time.perf_counter() - t0)
+            gs = eng.last_stats
+            gk_ms, bb_ms, hits = gs["ms_count"], gs["ms_sort"], gs["n_events"]
             t0 = time.perf_counter()
-            pv = eng.betabinom_sf(al[ri, ci], dp[ri, ci], 0.2474528917555431, 162.03696139428595)
-            t_bb = time.perf_counter() - t0
-            secondary = {"metric": "candidate sites genotyped/sec (K1' pileup + K2 beta-binomial tails)",
-                         "sites": int(n_cand), "cells": int(n_cells), "sites_per_s": n_cand / (t_geno + t_bb),
-                         "genotype_call_ms": 1e3 * t_geno, "genotype_kernel_ms": k_ms, "betabinom_pairs": int(len(ri)),
-                         "betabinom_call_ms": 1e3 * t_bb, "betabinom_kernel_ms": eng.last_stats["ms_count"],
-                         "note": "calls include H2D of the site table and D2H of the dense [site][cell] Dp/Alt tensors"}
+            tup = eng.genotype_sparse(gt, gp, alt, n_cells, a2, b2, min_bq=30, min_mq=60)
+            barrier()
+            g_e2e_ms = 1e3 * (time.perf_counter() - t0)
+            del tup
+        else:
+            for _ in range(3):
+                barrier()
+        tot_cand = reduce_sum(float(n_cand))
+        g_dev_ms, g_e2e_ms = reduce_max(g_dev_ms), reduce_max(g_e2e_ms)
+        # K1' algorithmic bytes: 19 B per read + 4 B per CIGAR op + 13 B per site + 8 B per touched pair
+        g_alg = 19.0 * batch.n_reads + 4.0 * batch.cigar.shape[0] + 13.0 * n_cand + 8.0 * n_tup
+        secondary = {"metric": "candidate sites genotyped/sec (K1' sparse pileup + K2 beta-binomial tails, on device)",
+                     "value": tot_cand / (g_dev_ms * 1e-3) if g_dev_ms else None, "unit": "sites/s",
+                     "sites": int(tot_cand), "cells": int(n_cells), "ms": g_dev_ms,
+                     "e2e": {"value": tot_cand / (g_e2e_ms * 1e-3) if g_e2e_ms else None, "ms": g_e2e_ms,
+                             "note": "host site table in, touched (site, cell, Dp, Alt, p) tuples out"},
+                     "rank0": {"sites": int(n_cand), "touched_pairs": int(n_tup), "pileup_hits": int(hits),
+                               "k1p_ms": gk_ms, "k2_ms": bb_ms,
+                               "roofline": {"bound": "hbm", "kernel": "genotype_kernel x2 + hit sort + reduce",
+                                            "achieved": g_alg / (gk_ms * 1e-3) / 1e9 if gk_ms else None, "peak": peak,
+                                            "unit": "GB/s", "frac": g_alg / (gk_ms * 1e-3) / 1e9 / peak if gk_ms else None,
+                                            "algorithmic_bytes": g_alg}}}
         del got
+    # ---- BASELINE.json configs[3] (hotspot stress: 20 genes at > 1e5 reads / locus, 10k cells), N = 1 only --------
+    c4 = None
+    if world == 1 and not args.no_secondary and args.scale >= 1.0:
+        from longsom_b200 import synth
+        from longsom_b200.batch import Windows as _W, make_windows as _mw
+        d4 = synth.generate(**synth.config("C4", scale=1.0))
+        w4 = _W.from_intervals(_mw(d4.contig_lens, 50000), d4.contig_seqs())
+        eng.upload(d4.batch, w4)
+        for _ in range(2):
+            eng.run(prm)
+            eng.compact()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n4 = eng.run(prm)
+        s4 = eng.last_stats
+        eng.compact()
+        torch.cuda.synchronize()
+        dt4 = time.perf_counter() - t0
+        al4 = d4.batch.aligned_bases()
+        alg4 = algorithmic_bytes(d4.batch, s4["n_tiles"], tile, n4)
+        c4 = {"workload": "C4 hotspot stress: %d reads, %d cells, 20 hot genes" % (d4.batch.n_reads, d4.n_cells),
+              "value": al4 / dt4, "unit": UNIT, "ms_per_step": 1e3 * dt4, "kernel_ms": s4["ms_count"],
+              "segments_per_tile": s4["n_segments"] / max(1, s4["n_tiles"]),
+              "roofline_frac": alg4 / (s4["ms_count"] * 1e-3) / 1e9 / peak}
+        del d4, w4
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------------
     cpu = None
@@ -443,11 +499,11 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u32", "data": "synthetic",
             "config": workload_config(info, scale, l2="inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
                                       % (batch.nbytes() / 1e9)),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "secondary": secondary,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "secondary": secondary, "c4": c4,
             "gpu_launches": int(launches),
             "stats": {"n_segments": st["n_segments"], "n_tiles": st["n_tiles"], "n_sites": int(n_sites),
                       "n_events": st["n_events"], "ms_segments": st["ms_segments"], "ms_sort": st["ms_sort"],
-                      "ms_count": k_ms, "ms_device_total": float(np.mean(ms_total)), "tile": tile,
+                      "ms_count": k_ms, "ms_compact": c_ms, "ms_device_total": float(np.mean(ms_total)) + c_ms, "tile": tile,
                       "aligned_bases_total": total_units},
         }
         emit_json(res)
@@ -468,6 +524,7 @@ def main():
     ap.add_argument("--e2e-shards", type=int, default=8, help="window shards of the pipelined end-to-end leg (1 = off)")
     ap.add_argument("--e2e-lanes", type=int, default=2, help="CUDA contexts the pipelined end-to-end leg alternates on")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the genotyping metric and the C4 line")
     args = ap.parse_args()
     quiet_stdout()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

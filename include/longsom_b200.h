@@ -152,10 +152,12 @@ int ls_host_free(void *ptr);
  * (:152-180) + the htslib pileup engine behind pysam.AlignmentFile.pileup (:190-191).
  *   upload : H2D copy of a batch and its windows (the ctx keeps device copies)
  *   run    : segment build -> (tile,cell) sort -> pileup-count kernel; results stay in HBM
- *   fetch  : compaction of passing sites + D2H into caller arrays
+ *   compact: compaction of the passing sites into output order, still in HBM (fetch does it if it has not been done)
+ *   fetch  : D2H of the compacted sites into caller arrays
  *   count  : upload + run + fetch in one call (the end-to-end entry point)            */
 int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *batch, const ls_windows *windows);
 int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t *n_sites, ls_run_stats *stats);
+int ls_pileup_compact(ls_ctx *ctx, ls_run_stats *stats); /* device-side half of fetch: passing sites in (window, pos) order */
 int ls_pileup_fetch(ls_ctx *ctx, ls_site_counts *out);
 int ls_pileup_count(ls_ctx *ctx, const ls_read_batch *batch, const ls_windows *windows,
                     const ls_count_params *params, ls_site_counts *out, ls_run_stats *stats);

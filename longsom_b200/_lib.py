@@ -19,7 +19,7 @@ LS_CLASS_NA = 8
 # every symbol include/longsom_b200.h declares (checked by tests/test_cpu.py::test_abi_exports_every_declared_symbol)
 ABI_SYMBOLS = [
     "ls_abi_version", "ls_ctx_create", "ls_ctx_destroy", "ls_last_error", "ls_host_alloc", "ls_host_free",
-    "ls_pileup_upload", "ls_pileup_run", "ls_pileup_fetch", "ls_pileup_count", "ls_genotype_count",
+    "ls_pileup_upload", "ls_pileup_run", "ls_pileup_compact", "ls_pileup_fetch", "ls_pileup_count", "ls_genotype_count",
     "ls_genotype_sparse_run", "ls_genotype_sparse_fetch",
     "ls_betabinom_sf", "ls_site_mask", "ls_device_synchronize", "ls_flush_l2",
 ]
@@ -98,6 +98,7 @@ def load():
     lib.ls_host_free.argtypes = [C.c_void_p]
     lib.ls_pileup_upload.argtypes = [C.c_void_p, P(LsReadBatch), P(LsWindows)]
     lib.ls_pileup_run.argtypes = [C.c_void_p, P(LsCountParams), P(C.c_int64), P(LsRunStats)]
+    lib.ls_pileup_compact.argtypes = [C.c_void_p, P(LsRunStats)]
     lib.ls_pileup_fetch.argtypes = [C.c_void_p, P(LsSiteCounts)]
     lib.ls_pileup_count.argtypes = [C.c_void_p, P(LsReadBatch), P(LsWindows), P(LsCountParams), P(LsSiteCounts),
                                     P(LsRunStats)]

@@ -116,19 +116,22 @@ def genotype(args, hccv):
         raise warm["error"]
     with warm["engine"] as eng:
         eng.upload(batch, None)
-        dp, alt = eng.genotype_count(site_tid, site_pos, alt_cls, n_cells, min_bq=args.min_bq, min_mq=args.min_mq,
-                                     max_depth=200000, alt_only=(args.alt_flag != 'All'), bin_size=args.bin)
-        # all (site, cell) pairs that need a beta-binomial tail: ALT > 0, not the chrM shortcut
+        # only the touched (site, cell) pairs come back, each with its beta-binomial tail already evaluated on the
+        # device (ALT > 0, not the chrM shortcut); the dense rows of the reference are expanded from them below
         chrM_rows = np.array([bam.contig_names[t] == 'chrM' for t in site_tid], bool) if len(keys) else np.zeros(0, bool)
-        need = (alt > 0)
-        if args.chrM_contaminant == 'True' and len(keys):
-            need = need & ~chrM_rows[:, None]
-        ri, ci = np.nonzero(need)
-        pv = eng.betabinom_sf(alt[ri, ci], dp[ri, ci], args.alpha2, args.beta2)
-    betabin = {}
-    rp = np.round(pv, 4)
-    for a, b, v in zip(ri.tolist(), ci.tolist(), rp):
-        betabin[(a, b)] = v
+        skip = chrM_rows.astype(np.uint8) if args.chrM_contaminant == 'True' else None
+        t_site, t_cell, t_dp, t_alt, t_p = eng.genotype_sparse(
+            site_tid, site_pos, alt_cls, n_cells, args.alpha2, args.beta2, skip_p=skip, min_bq=args.min_bq,
+            min_mq=args.min_mq, max_depth=200000, alt_only=(args.alt_flag != 'All'), bin_size=args.bin)
+    t_p = np.round(t_p, 4)
+    # per site: {cell: (Dp, Alt, BetaBin)}
+    touched = [None] * len(keys)
+    bounds = np.searchsorted(t_site, np.arange(len(keys) + 1))
+    tc, td, ta, tp = t_cell.tolist(), t_dp.tolist(), t_alt.tolist(), t_p.tolist()
+    for r in range(len(keys)):
+        lo_, hi_ = int(bounds[r]), int(bounds[r + 1])
+        if hi_ > lo_:
+            touched[r] = {tc[i]: (td[i], ta[i], tp[i]) for i in range(lo_, hi_)}
 
     # ---- rows, in the reference's order ------------------------------------------------------------
     blocks = {}
@@ -139,10 +142,10 @@ def genotype(args, hccv):
         for POS in sites:  # CELLS dict comprehension iterates the set (:130)
             Ref_exp, Alt_exp, Cell_type_exp, Num_cells_exp = target[POS]
             r = row_of.get((tid_of.get(chrom, -1), POS))
+            hits = (touched[r] if r is not None else None) or {}
             for c, bc in enumerate(barcodes):
                 CTYPE = meta_dict[bc]
-                DP = int(dp[r, c]) if r is not None else 0
-                ALT = int(alt[r, c]) if r is not None else 0
+                DP, ALT, PV = hits.get(c, (0, 0, None))
                 VAF, BETABIN, MUTATED = '.', '.', 'NoCoverage'
                 if DP > 0:
                     if not hccv:
@@ -153,7 +156,7 @@ def genotype(args, hccv):
                         if args.chrM_contaminant == 'True' and str(chrom) == 'chrM':
                             MUTATED = 'LowVAFChrM' if VAF < 0.3 else 'PASS'
                         else:
-                            BETABIN = betabin[(r, c)]
+                            BETABIN = np.float64(PV)
                             MUTATED = 'PASS' if BETABIN < args.pvalue else 'BetaBin_problem'
                     else:
                         if hccv:

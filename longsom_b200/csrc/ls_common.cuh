@@ -106,7 +106,7 @@ struct ls_ctx {
   int64_t n_tiles_total = 0;
 
   // ---- run state ----
-  bool have_run = false;
+  bool have_run = false, compacted = false;
   ls_count_params params = {};
   DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;

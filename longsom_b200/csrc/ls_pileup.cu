@@ -159,6 +159,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   cudaStream_t st = ctx->stream;
   ctx->params = *params;
   ctx->have_run = false;
+  ctx->compacted = false;
   ls_run_stats S;
   memset(&S, 0, sizeof S);
   int launches = 0;
@@ -464,6 +465,46 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   return LS_OK;
 }
 
+// Compaction of the passing sites into the reference's output order (window, position): device only.  The site table
+// of a run is tile-major with a pass bitmask; this is the step that turns it into the unit the reference emits.
+extern "C" int ls_pileup_compact(ls_ctx *ctx, ls_run_stats *stats) {
+  if (!ctx) return LS_E_ARG;
+  if (!ctx->have_run) LS_FAIL(LS_E_STATE, "ls_pileup_compact: ls_pileup_run has not completed");
+  if (!ctx->compacted && ctx->n_sites > 0) {
+    LS_CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t ns = ctx->n_sites;
+    LS_CK(ctx->out_tid.ensure((size_t)ns * 4));
+    LS_CK(ctx->out_pos.ensure((size_t)ns * 4));
+    LS_CK(ctx->out_ref.ensure((size_t)ns));
+    LS_CK(ctx->out_counts.ensure((size_t)ns * LS_SITE_WORDS * 4));
+    CompactArgs a;
+    a.slot_tile = ctx->slot_tile.as<int64_t>();
+    a.slot_off = ctx->slot_off.as<uint32_t>();
+    a.out = ctx->slot_out.as<uint32_t>();
+    a.mask = ctx->slot_mask.as<uint32_t>();
+    a.n_windows = ctx->n_windows;
+    a.wtid = ctx->wtid.as<int32_t>();
+    a.wstart = ctx->wstart.as<int32_t>();
+    a.wtile_base = ctx->wtile_base.as<int64_t>();
+    a.wref_off = ctx->wref_off.as<uint64_t>();
+    a.ref = ctx->ref.as<uint8_t>();
+    a.o_tid = ctx->out_tid.as<int32_t>();
+    a.o_pos = ctx->out_pos.as<int32_t>();
+    a.o_ref = ctx->out_ref.as<uint8_t>();
+    a.o_counts = ctx->out_counts.as<uint32_t>();
+    LS_CK(cudaEventRecord(ctx->ev[5], st));
+    compact_sites_kernel<<<(unsigned)ctx->n_slots, 256, 0, st>>>(a);
+    LS_CK(cudaGetLastError());
+    LS_CK(cudaEventRecord(ctx->ev[6], st));
+    LS_CK(cudaStreamSynchronize(st));
+    LS_CK(cudaEventElapsedTime(&ctx->stats.ms_compact, ctx->ev[5], ctx->ev[6]));
+  }
+  ctx->compacted = true;
+  if (stats) *stats = ctx->stats;
+  return LS_OK;
+}
+
 extern "C" int ls_pileup_fetch(ls_ctx *ctx, ls_site_counts *out) {
   if (!ctx) return LS_E_ARG;
   if (!out) LS_FAIL(LS_E_ARG, "ls_pileup_fetch: out is null");
@@ -472,38 +513,15 @@ extern "C" int ls_pileup_fetch(ls_ctx *ctx, ls_site_counts *out) {
   if (ctx->n_sites == 0) return LS_OK;
   if (out->capacity < ctx->n_sites) LS_FAIL(LS_E_CAPACITY, "ls_pileup_fetch: capacity < n_sites");
   if (!out->tid || !out->pos || !out->ref || !out->counts) LS_FAIL(LS_E_ARG, "ls_pileup_fetch: null output array");
-  LS_CK(cudaSetDevice(ctx->device));
+  int rc = ls_pileup_compact(ctx, nullptr);
+  if (rc != LS_OK) return rc;
   cudaStream_t st = ctx->stream;
   const int64_t ns = ctx->n_sites;
-  LS_CK(ctx->out_tid.ensure((size_t)ns * 4));
-  LS_CK(ctx->out_pos.ensure((size_t)ns * 4));
-  LS_CK(ctx->out_ref.ensure((size_t)ns));
-  LS_CK(ctx->out_counts.ensure((size_t)ns * LS_SITE_WORDS * 4));
-  CompactArgs a;
-  a.slot_tile = ctx->slot_tile.as<int64_t>();
-  a.slot_off = ctx->slot_off.as<uint32_t>();
-  a.out = ctx->slot_out.as<uint32_t>();
-  a.mask = ctx->slot_mask.as<uint32_t>();
-  a.n_windows = ctx->n_windows;
-  a.wtid = ctx->wtid.as<int32_t>();
-  a.wstart = ctx->wstart.as<int32_t>();
-  a.wtile_base = ctx->wtile_base.as<int64_t>();
-  a.wref_off = ctx->wref_off.as<uint64_t>();
-  a.ref = ctx->ref.as<uint8_t>();
-  a.o_tid = ctx->out_tid.as<int32_t>();
-  a.o_pos = ctx->out_pos.as<int32_t>();
-  a.o_ref = ctx->out_ref.as<uint8_t>();
-  a.o_counts = ctx->out_counts.as<uint32_t>();
-  LS_CK(cudaEventRecord(ctx->ev[5], st));
-  compact_sites_kernel<<<(unsigned)ctx->n_slots, 256, 0, st>>>(a);
-  LS_CK(cudaGetLastError());
-  LS_CK(cudaEventRecord(ctx->ev[6], st));
   LS_CK(cudaMemcpyAsync(out->tid, ctx->out_tid.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
   LS_CK(cudaMemcpyAsync(out->pos, ctx->out_pos.p, (size_t)ns * 4, cudaMemcpyDeviceToHost, st));
   LS_CK(cudaMemcpyAsync(out->ref, ctx->out_ref.p, (size_t)ns, cudaMemcpyDeviceToHost, st));
   LS_CK(cudaMemcpyAsync(out->counts, ctx->out_counts.p, (size_t)ns * LS_SITE_WORDS * 4, cudaMemcpyDeviceToHost, st));
   LS_CK(cudaStreamSynchronize(st));
-  LS_CK(cudaEventElapsedTime(&ctx->stats.ms_compact, ctx->ev[5], ctx->ev[6]));
   return LS_OK;
 }
 

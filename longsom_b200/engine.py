@@ -76,6 +76,12 @@ class Engine:
         self.last_stats = st.as_dict()
         return int(n.value)
 
+    def compact(self):
+        """Passing sites of the last run into output order, on the device (the second half of a bench step)."""
+        st = L.LsRunStats()
+        self._check(self._lib.ls_pileup_compact(self._ctx, C.byref(st)), "ls_pileup_compact")
+        self.last_stats = st.as_dict()
+
     def fetch(self, n_sites):
         out = SiteCounts.empty(n_sites)
         s = out.as_struct()

@@ -218,6 +218,18 @@ class _GenoOracleEngine(OracleEngine):
         k, n = np.asarray(k), np.asarray(n)
         return betabinom.sf(k - 0.001, n, a, b) if len(k) else np.zeros(0)
 
+    def genotype_sparse(self, st, sp, ac, n_cells, alpha, beta, skip_p=None, **kw):
+        """The sparse tuples of Engine.genotype_sparse, from the oracle's dense tensors and scipy."""
+        dp, alt = self.genotype_count(st, sp, ac, n_cells, **kw)
+        ri, ci = np.nonzero(dp > 0)
+        d, a = dp[ri, ci].astype(np.int32), alt[ri, ci].astype(np.int32)
+        q = a > 0
+        if skip_p is not None:
+            q &= np.asarray(skip_p)[ri] == 0
+        p = np.full(len(ri), np.nan)
+        p[q] = self.betabinom_sf(a[q], d[q], alpha, beta)
+        return ri.astype(np.int32), ci.astype(np.int32), d, a, p
+
 
 def test_genotype_host_logic_matches_reference(work, monkeypatch):
     import pipeline_inputs as pi
