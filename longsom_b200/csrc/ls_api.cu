@@ -119,6 +119,7 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
   if (!b) LS_FAIL(LS_E_ARG, "ls_pileup_upload: batch is null");
   ctx->have_batch = false;
   ctx->have_run = false;
+  ctx->cache_valid = false;
   const int64_t n = b->n_reads;
   if (n < 0 || b->n_cigar < 0 || b->n_bases < 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: negative size");
   if (n >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_pileup_upload: more than 2^32-1 reads per batch");

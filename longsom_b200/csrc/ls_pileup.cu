@@ -163,6 +163,11 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
   ls_run_stats S;
   memset(&S, 0, sizeof S);
   int launches = 0;
+  // Replay: a run on the SAME uploaded batch with the SAME parameters has the same intermediate sizes as the last one
+  // (the pipeline is deterministic), so the two size read-backs in the middle are skipped and everything is enqueued
+  // at once; the sizes are verified against the device counters with the final read-back, and the run is repeated
+  // with read-backs if they ever differ.
+  const bool replay = ctx->cache_valid && memcmp(&ctx->cache_params, params, sizeof *params) == 0 && !getenv("LS_NO_REPLAY");
 
   const int64_t n = ctx->n_reads;
   ctx->cell_bits = ls_bits_for((uint64_t)(ctx->max_cell + 1));
@@ -193,7 +198,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ctx->n_drop = 0;
     sa.n_drop = 0;
     // the depth cap can only fire in a window that fetches more than max_depth records
-    const bool cap_possible = params->max_depth > 0 && n > (int64_t)params->max_depth;
+    const bool cap_possible = !replay && params->max_depth > 0 && n > (int64_t)params->max_depth;  // replay: known not to fire
     if (cap_possible) {
       LS_CK(ctx->rend.ensure((size_t)n * 4));
       LS_CK(ctx->wcount.ensure((size_t)ctx->n_windows * 4));
@@ -218,6 +223,11 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
           want_wcount ? ctx->wcount.as<uint32_t>() : nullptr, (uint32_t)params->max_depth, d_capflag);
       ++launches;
       LS_CK(cudaGetLastError());
+      if (replay) {
+        memcpy(h_seg, ctx->cache_seg, sizeof h_seg);
+        h_tot[0] = ctx->cache_tot[0];
+        break;
+      }
       LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 64, cudaMemcpyDeviceToHost, st));
       LS_CK(cudaMemcpyAsync(h_seg, d_seg_totals, 24, cudaMemcpyDeviceToHost, st));
       LS_CK(cudaStreamSynchronize(st));
@@ -333,8 +343,14 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       launches += 3;
       LS_CK(cudaGetLastError());
     }
-    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 128, cudaMemcpyDeviceToHost, st));
-    LS_CK(cudaStreamSynchronize(st));
+    if (replay) {
+      memcpy(h_tot, ctx->cache_tot, sizeof h_tot);
+    } else {
+      LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 128, cudaMemcpyDeviceToHost, st));
+      LS_CK(cudaStreamSynchronize(st));
+    }
+    uint64_t h_mid[16];
+    memcpy(h_mid, h_tot, sizeof h_mid);
     n_slots = (int64_t)h_tot[3];
     const bool packed = (h_tot[5] & 0xffffffffull) == 0;
     LS_CK(ctx->slot_tile.ensure((size_t)n_slots * 8));
@@ -440,13 +456,28 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ++launches;
     LS_CK(cudaGetLastError());
     LS_CK(cudaEventRecord(ctx->ev[3], st));
-    LS_CK(ls_scan_exclusive_u32(ctx->slot_npass.as<uint32_t>(), ctx->slot_off.as<uint32_t>(), n_slots, d_nslot_total,
+    // the number of passing sites goes to counter 2: counter 3 keeps the number of slots for the replay check
+    LS_CK(ls_scan_exclusive_u32(ctx->slot_npass.as<uint32_t>(), ctx->slot_off.as<uint32_t>(), n_slots, d_nseg_total,
                                 ctx->scan_tmp, st));
     launches += 3;
     LS_CK(cudaEventRecord(ctx->ev[4], st));
-    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 32, cudaMemcpyDeviceToHost, st));
+    LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 128, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
-    ctx->n_sites = (int64_t)h_tot[3];
+    if (replay) {
+      // what the device actually produced against what the enqueued sizes assumed
+      bool same = h_tot[0] == h_mid[0] && h_tot[3] == h_mid[3] && (h_tot[5] & 0xffffffffull) == (h_mid[5] & 0xffffffffull);
+      for (int k = 8; k < 16; ++k) same = same && h_tot[k] == (k < 11 ? ctx->cache_seg[k - 8] : h_mid[k]);
+      if (!same) {
+        ctx->cache_valid = false;
+        return ls_pileup_run(ctx, params, n_sites, stats);
+      }
+    } else if (ctx->n_drop == 0 && (h_mid[7] & 0xffffffffull) == 0) {
+      ctx->cache_valid = true;
+      ctx->cache_params = *params;
+      memcpy(ctx->cache_seg, h_seg, sizeof h_seg);
+      memcpy(ctx->cache_tot, h_mid, sizeof h_mid);
+    }
+    ctx->n_sites = (int64_t)h_tot[2];
     S.n_events = (int64_t)h_tot[1];
     LS_CK(cudaEventElapsedTime(&S.ms_segments, ctx->ev[0], ctx->ev[1]));
     LS_CK(cudaEventElapsedTime(&S.ms_sort, ctx->ev[1], ctx->ev[2]));
