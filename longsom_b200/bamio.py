@@ -112,6 +112,98 @@ def read_bam(path, threads=None):
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
 
 
+class BamStream:
+    """Chunked decoder over csrc/host/ls_bamstream.cpp: bounded memory, barcodes interned across chunks.
+
+    next_chunk(target_bytes, alloc, head) decodes the next ~target_bytes of inflated BAM and writes the records into
+    arrays obtained from alloc(n_reads, n_cigar, n_bases) -- pinned staging memory in the counter CLI -- AFTER the
+    `head` reads the caller has already placed at their start (the reads carried over from the previous chunk), and
+    returns the ReadBatch of head + chunk with raw barcode ids in .cell (or None at the end of the file)."""
+
+    def __init__(self, path, threads=None):
+        self.lib = _load_host()
+        lib = self.lib
+        if not hasattr(lib, "_bams_ready"):
+            lib.ls_bams_open.restype = C.c_void_p
+            lib.ls_bams_open.argtypes = [C.c_char_p, C.c_int]
+            lib.ls_bams_error.restype = C.c_char_p
+            lib.ls_bams_error.argtypes = [C.c_void_p]
+            lib.ls_bams_close.argtypes = [C.c_void_p]
+            lib.ls_bams_next.restype = C.c_int64
+            lib.ls_bams_next.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+            lib.ls_bams_fill.restype = C.c_int
+            lib.ls_bams_fill.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+            for f in ("ls_bams_n_contigs", "ls_bams_n_barcodes"):
+                getattr(lib, f).restype = C.c_int32
+                getattr(lib, f).argtypes = [C.c_void_p]
+            lib.ls_bams_contig_name.restype = C.c_char_p
+            lib.ls_bams_contig_name.argtypes = [C.c_void_p, C.c_int]
+            lib.ls_bams_contig_len.restype = C.c_int32
+            lib.ls_bams_contig_len.argtypes = [C.c_void_p, C.c_int]
+            lib.ls_bams_barcode.restype = C.c_char_p
+            lib.ls_bams_barcode.argtypes = [C.c_void_p, C.c_int]
+            lib._bams_ready = True
+        threads = threads or min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+        self.h = lib.ls_bams_open(os.fsencode(path), int(threads))
+        self._check()
+        self.contig_names = [lib.ls_bams_contig_name(self.h, i).decode() for i in range(lib.ls_bams_n_contigs(self.h))]
+        self.contig_lens = [lib.ls_bams_contig_len(self.h, i) for i in range(len(self.contig_names))]
+        self.barcodes = []
+
+    def _check(self):
+        err = self.lib.ls_bams_error(self.h)
+        if err:
+            raise IOError("BAM stream: " + err.decode())
+
+    def close(self):
+        if self.h:
+            self.lib.ls_bams_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def next_chunk(self, target_bytes, alloc, head=None):
+        nc, nb = C.c_int64(0), C.c_int64(0)
+        n = self.lib.ls_bams_next(self.h, int(target_bytes), C.byref(nc), C.byref(nb))
+        if n < 0:
+            self._check()
+            raise IOError("BAM stream: decode failed")
+        if n == 0:
+            return None
+        h_n = head.n_reads if head is not None else 0
+        h_c = int(head.cigar.shape[0]) if head is not None else 0
+        h_b = head.n_bases if head is not None else 0
+        a = alloc(h_n + n, h_c + nc.value, h_b + nb.value)
+        if head is not None and h_n:
+            for f in ("tid", "pos", "flag", "mapq", "cell", "l_qseq"):
+                a[f][:h_n] = getattr(head, f)
+            a["cigar_off"][:h_n + 1] = head.cigar_off
+            a["base_off"][:h_n + 1] = head.base_off
+            a["cigar"][:h_c] = head.cigar
+            a["seq4"][:h_b // 2] = head.seq4
+            a["qual"][:h_b] = head.qual
+        ptr = lambda arr, off: C.c_void_p(arr.ctypes.data + off * arr.itemsize)
+        rc = self.lib.ls_bams_fill(self.h, ptr(a["tid"], h_n), ptr(a["pos"], h_n), ptr(a["flag"], h_n), ptr(a["mapq"], h_n),
+                                   ptr(a["cell"], h_n), ptr(a["l_qseq"], h_n), ptr(a["cigar_off"], h_n),
+                                   ptr(a["base_off"], h_n), ptr(a["cigar"], h_c), ptr(a["seq4"], h_b // 2), ptr(a["qual"], h_b))
+        if rc != 0:
+            self._check()
+            raise IOError("BAM stream: fill failed")
+        if h_n:  # the chunk's offsets start at 0: rebase them behind the carried reads
+            a["cigar_off"][h_n:h_n + n + 1] += np.uint32(h_c)
+            a["base_off"][h_n:h_n + n + 1] += np.uint64(h_b)
+        nbar = self.lib.ls_bams_n_barcodes(self.h)
+        for i in range(len(self.barcodes), nbar):
+            self.barcodes.append(self.lib.ls_bams_barcode(self.h, i).decode())
+        N, NC, NB = h_n + n, h_c + nc.value, h_b + nb.value
+        return ReadBatch(a["tid"][:N], a["pos"][:N], a["flag"][:N], a["mapq"][:N], a["cell"][:N], a["cigar_off"][:N + 1],
+                         a["cigar"][:NC], a["base_off"][:N + 1], a["l_qseq"][:N], a["seq4"][:NB // 2], a["qual"][:NB]), n
+
+
 def _bgzf_block(data, level):
     co = zlib.compressobj(level, zlib.DEFLATED, -15)
     comp = co.compress(data) + co.flush()

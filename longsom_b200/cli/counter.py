@@ -12,7 +12,7 @@ import timeit
 from .. import bamio
 from ..engine import CountParams
 from ..pipeline import (count_sites, devices_from_env, load_bam_for_counting, prewarm, prune_and_sort_windows, read_ends,
-                        write_counter_tsv)
+                        stream_count, write_counter_tsv)
 from ..windows import make_windows
 
 
@@ -58,6 +58,14 @@ def run(args):
     prewarm(devices_from_env())  # CUDA contexts come up while the BAM is decoded
     fa = bamio.Fasta(args.ref)
     named = make_windows(fa.references, fa.lengths, args.chrom, args.bin, args.bed, args.bed_out)
+    params = CountParams(min_bq=args.min_bq, min_mq=args.min_mq, min_dp=args.min_dp, min_cc=args.min_cc,
+                         min_ac=args.min_ac, max_depth=200000)
+    if os.environ.get("LONGSOM_STREAM", "1") != "0":
+        # default: the BAM streams through pinned staging buffers in chunks (bounded host memory, decode / device /
+        # writer overlapped); LONGSOM_STREAM=0 decodes the whole file first (round-1 path)
+        stream_count(args.bam, named, fa, params, out_file, ID, devices_from_env())
+        fa.close()
+        return
     bd, batch, _cells = load_bam_for_counting(args.bam)
     ends = read_ends(batch)
     iv = prune_and_sort_windows(named, bd.contig_names, batch, ends)

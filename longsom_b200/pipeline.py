@@ -209,6 +209,229 @@ def count_shards_pipelined(shards, params: CountParams, outs, device=0, lanes=2,
     return n_sites
 
 
+# ---- streaming BaseCellCounter: BAM chunks -> pinned staging -> GPU -> per-contig row files ---------------------------
+class PinnedSlot:
+    """One staging buffer set in pinned host memory (ls_host_alloc): the BAM decoder writes where the H2D copy reads.
+    Arrays grow on demand and are reused for every chunk that goes through the slot."""
+    FIELDS = (("tid", np.int32, "n"), ("pos", np.int32, "n"), ("flag", np.uint16, "n"), ("mapq", np.uint8, "n"),
+              ("cell", np.int32, "n"), ("l_qseq", np.int32, "n"), ("cigar_off", np.uint32, "n1"),
+              ("base_off", np.uint64, "n1"), ("cigar", np.uint32, "c"), ("seq4", np.uint8, "b2"), ("qual", np.uint8, "b"))
+
+    def __init__(self):
+        from . import _lib as L
+        self.lib = L.load()
+        self.arrays, self.ptrs, self.caps = {}, {}, {}
+
+    def _alloc(self, name, dtype, count):
+        if self.caps.get(name, 0) >= count:
+            return
+        if name in self.ptrs:
+            self.lib.ls_host_free(self.ptrs[name])
+        want = int(count * 1.25) + 1024
+        nbytes = want * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        if self.lib.ls_host_alloc(C.c_size_t(nbytes), C.byref(p)) != 0:
+            raise MemoryError("ls_host_alloc(%d) failed" % nbytes)
+        self.ptrs[name] = p
+        self.caps[name] = want
+        self.arrays[name] = np.frombuffer((C.c_uint8 * nbytes).from_address(p.value), dtype=dtype, count=want)
+
+    def __call__(self, n, nc, nb):
+        size = {"n": n, "n1": n + 1, "c": nc, "b": nb, "b2": nb // 2 + 1}
+        for name, dtype, kind in self.FIELDS:
+            self._alloc(name, dtype, size[kind])
+        return self.arrays
+
+    def free(self):
+        for p in self.ptrs.values():
+            self.lib.ls_host_free(p)
+        self.arrays, self.ptrs, self.caps = {}, {}, {}
+
+
+def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, ID, devices=None, chunk_bytes=None,
+                 stats_out=None):
+    """BaseCellCounter over a BAM of any size with bounded host memory (reference: the per-window pool of
+    BaseCellCounter.py:344-409).  Three stages run concurrently:
+      decoder : next ~chunk_bytes of the BAM -> pinned slot (behind the reads carried over from the previous chunk);
+                decides which windows are COMPLETE (no later read can reach them: reads are coordinate sorted) and which
+                reads must be carried on because they overlap a window that is not;
+      device  : ls_pileup_count on (carried + chunk reads, complete windows), one chunk per engine at a time;
+      writer  : native TSV rows appended to one file per contig; the files are concatenated in the reference's order
+                (contig name, start) at the end.
+    Returns the number of sites written."""
+    import queue
+    import shutil
+    devices = devices or [0]
+    chunk_bytes = int(chunk_bytes or float(os.environ.get("LONGSOM_CHUNK_MB", "256")) * (1 << 20))
+    bs = bamio.BamStream(bam_path)
+    tid_of = {n: i for i, n in enumerate(bs.contig_names)}
+    win = sorted((tid_of[c], s, e) for c, s, e in named_windows if c in tid_of and e > s)
+    wk_end = np.array([(t << 32) | e for t, s, e in win], np.int64)
+    wk_start = np.array([(t << 32) | s for t, s, e in win], np.int64)
+    n_slots = len(devices) + 1
+    free_slots = queue.Queue()
+    slots = [PinnedSlot() for _ in range(n_slots)]
+    for sl in slots:
+        free_slots.put(sl)
+    todo, done = queue.Queue(maxsize=n_slots), queue.Queue()
+    errors = []
+    fasta_lock = threading.Lock()
+    clean_map = {"ids": np.zeros(0, np.int32), "table": {}, "names": []}
+
+    def cell_ids(raw, barcodes):
+        """raw barcode ids of the stream -> dense ids of cleaned barcodes (CB.split('-')[0], BaseCellCounter.py:246)."""
+        ids = clean_map["ids"]
+        if len(barcodes) > ids.shape[0]:
+            new = np.zeros(len(barcodes), np.int32)
+            new[:ids.shape[0]] = ids
+            for i in range(ids.shape[0], len(barcodes)):
+                c = barcodes[i].split("-")[0]
+                j = clean_map["table"].get(c)
+                if j is None:
+                    j = len(clean_map["names"])
+                    clean_map["table"][c] = j
+                    clean_map["names"].append(c)
+                new[i] = j
+            clean_map["ids"] = ids = new
+        out = np.full(raw.shape[0], -1, np.int32)
+        m = raw >= 0
+        out[m] = ids[raw[m]]
+        return out
+
+    def decoder():
+        try:
+            wi, seq, carry = 0, 0, None
+            while True:
+                slot = free_slots.get()
+                got = bs.next_chunk(chunk_bytes, slot, carry)
+                if got is None:
+                    free_slots.put(slot)
+                    batch, last = carry, None
+                    if batch is None or batch.n_reads == 0 or wi >= len(win):
+                        break
+                    slot = None
+                else:
+                    batch, _n_new = got
+                    last = (int(batch.tid[-1]) << 32) | int(batch.pos[-1])
+                # windows no future read can overlap: every later read starts at or after `last`
+                wj = len(win) if last is None else int(np.searchsorted(wk_end, last, side="right"))
+                wj = max(wj, wi)
+                ends = read_ends(batch)
+                rk_end = (batch.tid.astype(np.int64) << 32) | np.maximum(ends, batch.pos.astype(np.int64) + 1)
+                if wj > wi:
+                    iv = prune_and_sort_windows([(bs.contig_names[t], s, e) for t, s, e in win[wi:wj]], bs.contig_names, batch, ends)
+                    if iv:
+                        b2 = ReadBatch(batch.tid, batch.pos, batch.flag, batch.mapq, cell_ids(batch.cell, bs.barcodes),
+                                       batch.cigar_off, batch.cigar, batch.base_off, batch.l_qseq, batch.seq4, batch.qual)
+                        todo.put((seq, b2, iv, slot))
+                        seq += 1
+                        slot_in_use = True
+                    else:
+                        slot_in_use = False
+                else:
+                    slot_in_use = False
+                wi = wj
+                if last is None:
+                    if slot is not None and not slot_in_use:
+                        free_slots.put(slot)
+                    break
+                # reads that overlap a window which is not complete yet travel with the next chunk
+                if wi < len(win):
+                    keep = np.nonzero(rk_end > wk_start[wi])[0]
+                    carry = batch.select(keep) if keep.shape[0] else None
+                else:
+                    carry = None
+                if not slot_in_use:
+                    free_slots.put(slot)
+                if wi >= len(win):
+                    break
+        except Exception as ex:  # surfaced by the caller
+            errors.append(ex)
+        finally:
+            for _ in devices:
+                todo.put(None)
+
+    def device_worker(dev):
+        try:
+            eng = take_engine(dev)
+            try:
+                while True:
+                    item = todo.get()
+                    if item is None:
+                        break
+                    seq, batch, iv, slot = item
+                    with fasta_lock:
+                        contig_seq = {t: fasta.contig(bs.contig_names[t]) for t in sorted({w[0] for w in iv})}
+                    w = Windows.from_intervals(iv, contig_seq)
+                    sites = eng.pileup_count(batch, w, params)
+                    if stats_out is not None:
+                        stats_out.append(dict(device=dev, **eng.last_stats))
+                    if slot is not None:
+                        free_slots.put(slot)
+                    done.put((seq, sites))
+            finally:
+                eng.close()
+        except Exception as ex:
+            errors.append(ex)
+        finally:
+            done.put(None)
+
+    threads = [threading.Thread(target=decoder, daemon=True)] + [threading.Thread(target=device_worker, args=(d,), daemon=True)
+                                                                 for d in devices]
+    for t in threads:
+        t.start()
+    # writer (this thread): chunks in sequence order, rows appended to one temporary file per contig
+    host = bamio._load_host()
+    host.ls_write_counter_rows.argtypes = [C.c_char_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int, C.c_int]
+    host.ls_write_counter_rows.restype = C.c_int
+    parts, pending, want, live, n_sites = {}, {}, 0, len(devices), 0
+    nthreads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    while live:
+        item = done.get()
+        if item is None:
+            live -= 1
+            continue
+        pending[item[0]] = item[1]
+        while want in pending:
+            sites = pending.pop(want)
+            want += 1
+            n_sites += sites.n_sites
+            for t in np.unique(sites.tid).tolist():
+                lo, hi = int(np.searchsorted(sites.tid, t, "left")), int(np.searchsorted(sites.tid, t, "right"))
+                path = parts.setdefault(t, "%s.part.%d.%d" % (out_file, os.getpid(), t))
+                pos = np.ascontiguousarray(sites.pos[lo:hi])
+                ref = np.ascontiguousarray(sites.ref[lo:hi])
+                cnt = np.ascontiguousarray(sites.counts[lo:hi])
+                rc = host.ls_write_counter_rows(os.fsencode(path), bs.contig_names[t].encode(), pos.ctypes.data, ref.ctypes.data,
+                                                cnt.ctypes.data, hi - lo, nthreads, 1)
+                if rc != 0:
+                    errors.append(IOError("ls_write_counter_rows(%s) failed: %d" % (path, rc)))
+    for t in threads:
+        t.join()
+    for sl in slots:
+        sl.free()
+    bs.close()
+    try:
+        if errors:
+            raise errors[0]
+        if n_sites == 0:
+            print("No temporary files found")
+            return 0
+        with open(out_file, "wb") as out:
+            out.write(("##fileDate=%s\n" % time.strftime("%d/%m/%Y")).encode())
+            out.write((COUNTER_CONCEPTS + "\n").encode())
+            out.write(("\t".join(["#CHROM", "POS", "REF", "INFO", str(ID)]) + "\n").encode())
+            for t in sorted(parts, key=lambda t: bs.contig_names[t]):
+                with open(parts[t], "rb") as f:
+                    shutil.copyfileobj(f, out, 1 << 24)
+        return n_sites
+    finally:
+        for path in parts.values():
+            if os.path.exists(path):
+                os.remove(path)
+
+
 def format_counter_lines(chrom, pos, ref, counts):
     """TSV lines of BaseCellCounter.run_interval (:297-309) for one contig."""
     lines = []

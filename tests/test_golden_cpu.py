@@ -85,6 +85,8 @@ class OracleEngine:
     def close(self):
         pass
 
+    last_stats = {}
+
     def upload(self, batch, windows=None):
         self.batch = batch
 
@@ -133,6 +135,41 @@ def test_oracle_pileup_matches_reference_tables(work):
     _count_with_oracle(p["full"], p["ref"], data.contig_names[0], 30000,
                        CountParams(min_bq=30, min_mq=0, min_ac=2, min_dp=3, min_cc=2), "full.ac", out)
     assert_same(file_lines(out), gold_lines(case, "counts.full_ac.tsv"), "BaseCellCounter --min_ac 2")
+
+
+class _NumpySlot:
+    """Stand-in for pipeline.PinnedSlot on a box without a GPU (pinned memory needs a CUDA context)."""
+
+    def __call__(self, n, nc, nb):
+        return dict(tid=np.zeros(n, np.int32), pos=np.zeros(n, np.int32), flag=np.zeros(n, np.uint16),
+                    mapq=np.zeros(n, np.uint8), cell=np.zeros(n, np.int32), l_qseq=np.zeros(n, np.int32),
+                    cigar_off=np.zeros(n + 1, np.uint32), base_off=np.zeros(n + 1, np.uint64), cigar=np.zeros(nc, np.uint32),
+                    seq4=np.zeros(nb // 2 + 1, np.uint8), qual=np.zeros(nb, np.uint8))
+
+    def free(self):
+        pass
+
+
+@pytest.mark.parametrize("chunk_kb", [64, 700])
+def test_streaming_counter_host_logic_matches_reference(work, monkeypatch, chunk_kb):
+    """The streaming BaseCellCounter (chunked BAM decode, reads carried across chunks, windows completed on the fly,
+    per-contig row files merged in name order) with the device calls answered by the oracle: byte-identical tables,
+    with chunks far smaller than a 50 kb window's reads (64 KB) and with a few chunks per contig (700 KB)."""
+    from longsom_b200 import bamio, pipeline
+    from longsom_b200.engine import CountParams
+    from longsom_b200.windows import make_windows
+    case, d, p, data = work
+    monkeypatch.setattr(pipeline, "PinnedSlot", _NumpySlot)
+    monkeypatch.setattr(pipeline, "take_engine", lambda dev: OracleEngine())
+    fa = bamio.Fasta(p["ref"])
+    named = make_windows(fa.references, fa.lengths, "all", 50000)
+    for name, bam in (("Cancer", p["cancer"]), ("Non-Cancer", p["normal"])):
+        out = os.path.join(d, "stream_%s_%d.tsv" % (name, chunk_kb))
+        n = pipeline.stream_count(bam, named, fa, CountParams(min_bq=20, min_mq=60), out, "s." + name, [0],
+                                  chunk_bytes=chunk_kb * 1024)
+        assert n > 0
+        assert_same(file_lines(out), gold_lines(case, "counts.%s.tsv" % name), "streaming BaseCellCounter " + name)
+        assert not [f for f in os.listdir(d) if ".part." in f]  # the per-contig row files are removed
 
 
 def test_bed_and_bed_out_windows_match_reference(work):
