@@ -480,6 +480,37 @@ def run_ours(args, rank, world, local_rank):
               "roofline_frac": alg4 / (s4["ms_count"] * 1e-3) / 1e9 / peak}
         del d4, w4
 
+    # ---- the drop-in CLI, BAM on disk -> TSV on disk (streaming path), rank 0, N = 1 only ---------------------------
+    e2e_cli = None
+    if world == 1 and args.cli_scale > 0:
+        import tempfile
+        from longsom_b200 import bamio, synth
+        dcli = synth.generate(**synth.config("C2", scale=args.cli_scale * scale))
+        tmp = tempfile.mkdtemp(prefix="ls_bench_cli_")
+        bamio.write_fasta(tmp + "/ref.fa", dcli.contig_names, [dcli.contig_seq(i) for i in range(len(dcli.contig_lens))])
+        names = [synth.barcode_of(c) + "-1" for c in range(dcli.n_cells + dcli.n_extra_cells)]
+        bc = dcli.batch
+        bamio.write_bam(tmp + "/x.bam", dcli.contig_names, dcli.contig_lens, bc, lambda i: None if bc.cell[i] < 0 else names[bc.cell[i]])
+        al_cli, n_cli, bam_mb = bc.aligned_bases(), bc.n_reads, os.path.getsize(tmp + "/x.bam") / 1e6
+        del dcli, bc
+        script = os.path.join(ROOT, "workflow", "scripts", "SNVCalling", "BaseCellCounter.py")
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([sys.executable, script, "--bam", tmp + "/x.bam", "--ref", tmp + "/ref.fa", "--chrom", "all",
+                                "--out_folder", tmp, "--id", "x", "--min_bq", "20", "--min_mq", "60", "--tmp_dir", tmp + "/t"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            dtc = time.perf_counter() - t0
+            if r.returncode != 0:
+                raise RuntimeError("drop-in CLI failed: " + r.stderr[-1500:])
+            best = dtc if best is None or dtc < best else best
+        e2e_cli = {"value": al_cli / best, "unit": UNIT, "seconds": best, "reads": int(n_cli), "bam_mb": bam_mb,
+                   "tsv_mb": os.path.getsize(tmp + "/x.tsv") / 1e6, "host_cores": os.cpu_count(),
+                   "api": "workflow/scripts/SNVCalling/BaseCellCounter.py as a subprocess (process start, CUDA context, "
+                          "streaming BGZF decode -> pinned slots -> ls_pileup_count -> native TSV rows); decode-bound (zlib)"}
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -499,7 +530,7 @@ def run_ours(args, rank, world, local_rank):
             "dtype": "u32", "data": "synthetic",
             "config": workload_config(info, scale, l2="inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
                                       % (batch.nbytes() / 1e9)),
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "secondary": secondary, "c4": c4,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "secondary": secondary, "c4": c4, "e2e_cli": e2e_cli,
             "gpu_launches": int(launches),
             "stats": {"n_segments": st["n_segments"], "n_tiles": st["n_tiles"], "n_sites": int(n_sites),
                       "n_events": st["n_events"], "ms_segments": st["ms_segments"], "ms_sort": st["ms_sort"],
@@ -525,6 +556,9 @@ def main():
     ap.add_argument("--e2e-lanes", type=int, default=2, help="CUDA contexts the pipelined end-to-end leg alternates on")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the genotyping metric and the C4 line")
+    ap.add_argument("--cli-scale", type=float, default=0.2,
+                    help="size of the BAM of the disk-to-disk CLI leg as a fraction of the workload (0 = skip; 1.0 = the "
+                         "whole 5 M-read BAM, which takes ~100 s to write)")
     args = ap.parse_args()
     quiet_stdout()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)

@@ -7,6 +7,7 @@ rules stay unchanged), so it comes from the environment: LONGSOM_GPUS="0,1,2,3" 
 """
 import ctypes as C
 import os
+import sys
 import threading
 import time
 
@@ -276,6 +277,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
     todo, done = queue.Queue(maxsize=n_slots), queue.Queue()
     errors = []
     fasta_lock = threading.Lock()
+    busy = {"decode": 0.0, "host_glue": 0.0, "device": 0.0, "writer": 0.0}
     clean_map = {"ids": np.zeros(0, np.int32), "table": {}, "names": []}
 
     def cell_ids(raw, barcodes):
@@ -303,7 +305,10 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
             wi, seq, carry = 0, 0, None
             while True:
                 slot = free_slots.get()
+                t_a = time.time()
                 got = bs.next_chunk(chunk_bytes, slot, carry)
+                busy["decode"] += time.time() - t_a
+                t_a = time.time()
                 if got is None:
                     free_slots.put(slot)
                     batch, last = carry, None
@@ -343,6 +348,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                     carry = None
                 if not slot_in_use:
                     free_slots.put(slot)
+                busy["host_glue"] += time.time() - t_a
                 if wi >= len(win):
                     break
         except Exception as ex:  # surfaced by the caller
@@ -360,6 +366,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                     if item is None:
                         break
                     seq, batch, iv, slot = item
+                    t_a = time.time()
                     with fasta_lock:
                         contig_seq = {t: fasta.contig(bs.contig_names[t]) for t in sorted({w[0] for w in iv})}
                     w = Windows.from_intervals(iv, contig_seq)
@@ -368,6 +375,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                         stats_out.append(dict(device=dev, **eng.last_stats))
                     if slot is not None:
                         free_slots.put(slot)
+                    busy["device"] += time.time() - t_a
                     done.put((seq, sites))
             finally:
                 eng.close()
@@ -393,6 +401,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
             live -= 1
             continue
         pending[item[0]] = item[1]
+        t_w = time.time()
         while want in pending:
             sites = pending.pop(want)
             want += 1
@@ -407,6 +416,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                                                 cnt.ctypes.data, hi - lo, nthreads, 1)
                 if rc != 0:
                     errors.append(IOError("ls_write_counter_rows(%s) failed: %d" % (path, rc)))
+        busy["writer"] += time.time() - t_w
     for t in threads:
         t.join()
     for sl in slots:
@@ -422,9 +432,26 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
             out.write(("##fileDate=%s\n" % time.strftime("%d/%m/%Y")).encode())
             out.write((COUNTER_CONCEPTS + "\n").encode())
             out.write(("\t".join(["#CHROM", "POS", "REF", "INFO", str(ID)]) + "\n").encode())
+            out.flush()
+            t_cat = time.time()
             for t in sorted(parts, key=lambda t: bs.contig_names[t]):
                 with open(parts[t], "rb") as f:
-                    shutil.copyfileobj(f, out, 1 << 24)
+                    left = os.fstat(f.fileno()).st_size
+                    try:  # in-kernel copy
+                        while left > 0:
+                            k = os.sendfile(out.fileno(), f.fileno(), None, min(left, 1 << 30))
+                            if k <= 0:
+                                break
+                            left -= k
+                    except OSError:
+                        pass
+                    if left > 0:
+                        shutil.copyfileobj(f, out, 1 << 24)
+            busy["concat"] = time.time() - t_cat
+        if os.environ.get("LS_STREAM_TIMING"):
+            import resource
+            print("[stream_count] busy seconds: " + ", ".join("%s %.2f" % kv for kv in sorted(busy.items())) +
+                  "; peak RSS of this process %.2f GB" % (resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6), file=sys.stderr)
         return n_sites
     finally:
         for path in parts.values():

@@ -19,22 +19,27 @@ print("reads %d, aligned bases %d, BAM %.1f MB (written in %.1f s), %d host core
 del d, b
 script = os.path.join(ROOT, "workflow", "scripts", "SNVCalling", "BaseCellCounter.py")
 res = {}
-for mode, env in (("stream", {}), ("whole", {"LONGSOM_STREAM": "0"})):
+for mode, env in (("stream", {}), ("whole", {"LONGSOM_STREAM": "0"})):  # streaming first: the smaller footprint
     e = dict(os.environ, **env)
     if len(sys.argv) > 2 and mode == "stream":
         e["LONGSOM_CHUNK_MB"] = sys.argv[2]
     out = tmp + "/out_" + mode
     os.makedirs(out, exist_ok=True)
     best = None
-    for rep in range(2):
+    e["LS_STREAM_TIMING"] = "1"
+    for rep in range(3):
         t0 = time.time()
-        r = subprocess.run(["/usr/bin/time", "-v", sys.executable, script, "--bam", tmp + "/x.bam", "--ref", tmp + "/ref.fa", "--chrom", "all",
+        rss0 = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+        r = subprocess.run([sys.executable, script, "--bam", tmp + "/x.bam", "--ref", tmp + "/ref.fa", "--chrom", "all",
                             "--out_folder", out, "--id", "x", "--min_bq", "20", "--min_mq", "60", "--tmp_dir", out + "/tmp"],
                            env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         dt = time.time() - t0
         assert r.returncode == 0, r.stderr[-2000:]
-        rss = [l for l in r.stderr.splitlines() if "Maximum resident set size" in l]
-        rss_gb = int(rss[0].split()[-1]) / 1e6 if rss else None
+        for l in r.stderr.splitlines():
+            if l.startswith("[stream_count]"):
+                print("   ", l, flush=True)
+        # ru_maxrss of the children is a running maximum: meaningful for the first (largest so far) run of each mode
+        rss_gb = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1e6
         best = dt if best is None or dt < best else best
     res[mode] = dict(seconds=best, bases_per_s=aligned / best, peak_rss_gb=rss_gb)
     print("%-6s %.2f s  %.3g aligned bases/s disk to disk, peak RSS %.2f GB" % (mode, best, aligned / best, rss_gb or -1), flush=True)
