@@ -62,8 +62,9 @@ static inline uint16_t rd16(const uint8_t *p) { return (uint16_t)(p[0] | (p[1] <
 // saves the ~40 KB state allocation that inflateInit2 / inflateEnd would do for every 64 KB member
 static bool inflate_block(z_stream &zs, const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
   // gzip member: 10-byte header + XLEN extra, deflate stream, CRC32, ISIZE
-  if (csize < 18) return false;
+  if (csize < 26) return false;
   uint32_t xlen = rd16(src + 10);
+  if (12u + xlen + 8u > csize) return false;  // the extra field must leave room for the CRC32 / ISIZE trailer
   const uint8_t *def = src + 12 + xlen;
   uint32_t dlen = csize - 12 - xlen - 8;
   if (inflateReset(&zs) != Z_OK) return false;
@@ -215,13 +216,26 @@ void *ls_bam_read(const char *path, int threads) {
     b->err = "bad BAM magic";
     return b;
   }
-  uint32_t l_text = rd32(p + 4);
+  // every length field is checked against the bytes that are there: a truncated or corrupt file is an error string
+  const uint64_t l_text = rd32(p + 4);
+  if (12 + l_text > raw_size) {
+    b->err = "truncated BAM header (l_text)";
+    return b;
+  }
   b->header_text.assign(reinterpret_cast<const char *>(p + 8), l_text);
   p += 8 + l_text;
   uint32_t n_ref = rd32(p);
   p += 4;
   for (uint32_t i = 0; i < n_ref; ++i) {
-    uint32_t l_name = rd32(p);
+    if (end - p < 4) {
+      b->err = "truncated BAM header (reference table)";
+      return b;
+    }
+    const uint64_t l_name = rd32(p);
+    if ((uint64_t)(end - p) < 8 + l_name) {
+      b->err = "truncated BAM header (reference name)";
+      return b;
+    }
     b->contig_names.emplace_back(reinterpret_cast<const char *>(p + 4), l_name ? l_name - 1 : 0);
     b->contig_lens.push_back((int32_t)rd32(p + 4 + l_name));
     p += 8 + l_name;
@@ -229,10 +243,18 @@ void *ls_bam_read(const char *path, int threads) {
   // pass 3: record offsets (sequential walk over block_size fields)
   std::vector<const uint8_t *> recs;
   while (p + 4 <= end) {
-    uint32_t bs = rd32(p);
-    if (p + 4 + bs > end) {
-      b->err = "truncated BAM record";
+    const uint64_t bs = rd32(p);
+    if (bs < 32 || (uint64_t)(end - p) < 4 + bs) {
+      b->err = "truncated or corrupt BAM record";
       return b;
+    }
+    {
+      const uint8_t *r = p + 4;
+      const uint64_t need = 32 + (uint64_t)r[8] + 4 * (uint64_t)rd16(r + 12) + ((uint64_t)rd32(r + 16) + 1) / 2 + rd32(r + 16);
+      if (need > bs) {
+        b->err = "corrupt BAM record (fields exceed block_size)";
+        return b;
+      }
     }
     recs.push_back(p + 4);
     p += 4 + bs;

@@ -108,6 +108,35 @@ __global__ void __launch_bounds__(256) nibble_swap_kernel(uint4 *p, size_t n16) 
   }
 }
 
+// Validation of an uploaded batch on the device (it used to be an O(n_reads) host loop inside every upload):
+// err bits: 1 = not sorted by (tid, pos), 2 = bad cigar_off, 4 = base_off not aligned, 8 = read bases exceed n_bases
+__global__ void __launch_bounds__(256) batch_check_kernel(int64_t n, const int32_t *__restrict__ tid, const int32_t *__restrict__ pos,
+                                                          const int32_t *__restrict__ cell, const uint32_t *__restrict__ cigar_off,
+                                                          const uint64_t *__restrict__ base_off, const int32_t *__restrict__ lq,
+                                                          int64_t n_cigar, int64_t n_bases, uint32_t *__restrict__ err,
+                                                          int32_t *__restrict__ max_cell) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t e = 0;
+  int32_t c = -1;
+  if (i < n) {
+    if (i > 0 && (tid[i] < tid[i - 1] || (tid[i] == tid[i - 1] && pos[i] < pos[i - 1]))) e |= 1u;
+    if (cigar_off[i + 1] < cigar_off[i] || (int64_t)cigar_off[i + 1] > n_cigar) e |= 2u;
+    if (base_off[i] % LS_BASE_ALIGN != 0) e |= 4u;
+    if (lq[i] < 0 || base_off[i] + (uint64_t)(lq[i] < 0 ? 0 : lq[i]) > (uint64_t)n_bases) e |= 8u;
+    c = cell[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    e |= __shfl_xor_sync(0xffffffffu, e, o);
+    const int32_t t = __shfl_xor_sync(0xffffffffu, c, o);
+    c = t > c ? t : c;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (e) atomicOr(err, e);
+    if (c >= 0) atomicMax(max_cell, c);
+  }
+}
+
 #define UP(buf, src, bytes)                                                                   \
   do {                                                                                        \
     LS_CK(ctx->buf.ensure((bytes) ? (bytes) : 16));                                           \
@@ -128,18 +157,6 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
     LS_FAIL(LS_E_ARG, "ls_pileup_upload: null per-read array");
   if (b->n_cigar > 0 && !b->cigar) LS_FAIL(LS_E_ARG, "ls_pileup_upload: null cigar");
   if (b->n_bases > 0 && (!b->seq4 || !b->qual)) LS_FAIL(LS_E_ARG, "ls_pileup_upload: null seq4/qual");
-  int32_t max_cell = -1;
-  for (int64_t i = 0; i < n; ++i) {
-    if (i > 0 && (b->tid[i] < b->tid[i - 1] || (b->tid[i] == b->tid[i - 1] && b->pos[i] < b->pos[i - 1])))
-      LS_FAIL(LS_E_ARG, "ls_pileup_upload: reads are not sorted by (tid, pos)");
-    if (b->cigar_off[i + 1] < b->cigar_off[i] || (int64_t)b->cigar_off[i + 1] > b->n_cigar)
-      LS_FAIL(LS_E_ARG, "ls_pileup_upload: bad cigar_off");
-    if (b->base_off[i] % LS_BASE_ALIGN != 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: base_off not aligned");
-    if (b->l_qseq[i] < 0 || b->base_off[i] + (uint64_t)b->l_qseq[i] > (uint64_t)b->n_bases)
-      LS_FAIL(LS_E_ARG, "ls_pileup_upload: read bases exceed n_bases");
-    if (b->cell[i] > max_cell) max_cell = b->cell[i];
-  }
-  if (max_cell >= 0x7ffffffe) LS_FAIL(LS_E_ARG, "ls_pileup_upload: cell id too large");
   const int64_t nw = w ? w->n_windows : 0;
   if (nw < 0) LS_FAIL(LS_E_ARG, "ls_pileup_upload: negative n_windows");
   if (nw > 0 && (!w->tid || !w->start || !w->end || !w->ref_off || !w->ref))
@@ -193,7 +210,24 @@ extern "C" int ls_pileup_upload(ls_ctx *ctx, const ls_read_batch *b, const ls_wi
   UP(wref_off, w ? w->ref_off : nullptr, (size_t)(nw > 0 ? (nw + 1) * 8 : 0));
   UP(ref, w ? w->ref : nullptr, (size_t)(nw ? w->ref_off[nw] : 0));
   UP(wtile_base, ctx->h_wtile_base.data(), (size_t)(nw + 1) * 8);
+  // batch validation + largest cell id, on the device, behind the copies
+  LS_CK(ctx->counters.ensure(128));
+  int32_t h_chk[2] = {0, -1};
+  LS_CK(cudaMemcpyAsync(ctx->counters.p, h_chk, 8, cudaMemcpyHostToDevice, st));
+  if (n > 0)
+    batch_check_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        n, ctx->tid.as<int32_t>(), ctx->pos.as<int32_t>(), ctx->cell.as<int32_t>(), ctx->cigar_off.as<uint32_t>(),
+        ctx->base_off.as<uint64_t>(), ctx->lq.as<int32_t>(), b->n_cigar, b->n_bases, ctx->counters.as<uint32_t>(),
+        ctx->counters.as<int32_t>() + 1);
+  LS_CK(cudaGetLastError());
+  LS_CK(cudaMemcpyAsync(h_chk, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
   LS_CK(cudaStreamSynchronize(st));
+  if (h_chk[0] & 1) LS_FAIL(LS_E_ARG, "ls_pileup_upload: reads are not sorted by (tid, pos)");
+  if (h_chk[0] & 2) LS_FAIL(LS_E_ARG, "ls_pileup_upload: bad cigar_off");
+  if (h_chk[0] & 4) LS_FAIL(LS_E_ARG, "ls_pileup_upload: base_off not aligned");
+  if (h_chk[0] & 8) LS_FAIL(LS_E_ARG, "ls_pileup_upload: read bases exceed n_bases");
+  const int32_t max_cell = h_chk[1];
+  if (max_cell >= 0x7ffffffe) LS_FAIL(LS_E_ARG, "ls_pileup_upload: cell id too large");
   ctx->n_reads = n;
   ctx->n_cigar = b->n_cigar;
   ctx->n_bases = b->n_bases;

@@ -32,7 +32,7 @@
 // shared-memory state, no atomics and no warp-level serialisation per run.
 #pragma once
 
-constexpr int K1_WARPS = 8;
+constexpr int K1_WARPS = 8;              // default CTA shape (the kernel is templated on it: LS_K1_SHAPE)
 constexpr int K1_THREADS = K1_WARPS * 32;
 constexpr int K1_PART_SEGS = 2048;       // nominal segments per part
 constexpr int K1_MAX_RUN_PACKED = 2039;  // packed counters (12-bit) need: part segs + run extension <= 4095
@@ -42,7 +42,7 @@ constexpr uint32_t K1_ROW_BYTES = 4u * K1_ROWW;
 constexpr uint32_t K1_DUMP_OFF = 16u * K1_ROW_BYTES;
 constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
 
-static_assert(LS_TILE % K1_THREADS == 0 && LS_TILE == 512, "tile / block shape");
+static_assert(LS_TILE % 32 == 0 && LS_TILE == 512, "tile shape");
 
 // unit.x: low 32 bits of q = index in qual[] of the base at column lo (deletion-like: of the one quality byte)
 // unit.y: q >> 32: bits 0-3 | window: 4-7 | lo: 8-12 | hi: 13-18 | strand: 19 | deletion-like: 20 | ind: 21-22 |
@@ -604,8 +604,10 @@ __device__ __forceinline__ uint32_t run_start_at_or_after(const uint64_t *__rest
   }
 }
 
-template <bool PACKED, int MIN_CTAS>
-__global__ void __launch_bounds__(K1_THREADS, MIN_CTAS) pileup_count_kernel(CountArgs a) {
+template <bool PACKED, int MIN_CTAS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(CountArgs a) {
+  constexpr int K1_THREADS = WARPS * 32;  // shadows the default shape inside the kernel
+  constexpr int K1_WARPS = WARPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
   const uint32_t part = blockIdx.x;

@@ -426,32 +426,37 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ca.min_cc = params->min_cc;
     ca.min_ac = params->min_ac;
     {
-      // shared memory per CTA: the acx row sits last and is only allocated with --min_ac > 0; without it four packed
-      // CTAs would fit an SM, but the 64-register build they need spills and measured 9 % slower (LS_K1_CTAS=4 selects it)
+      // shared memory per CTA: the acx row sits last and is only allocated with --min_ac > 0 (without it four CTAs fit)
       const size_t sm_p = params->min_ac > 0 ? sizeof(TileSmemT<true>) : offsetof(TileSmemT<true>, acx);
       const size_t sm_u = params->min_ac > 0 ? sizeof(TileSmemT<false>) : offsetof(TileSmemT<false>, acx);
-      static int ctas = -1;
-      if (ctas < 0) {
-        const char *e = getenv("LS_K1_CTAS");
-        ctas = (e && atoi(e) == 4) ? 4 : 3;
+      // CTA shape of the packed kernel: 8 warps x 3 CTAs / SM (default), 6 warps x 4 CTAs (same warps per SM, more
+      // tiles in flight; needs the acx row absent), 8 warps x 4 CTAs (64 registers: spills, measured slower)
+      static int shape = -1;
+      if (shape < 0) {
+        const char *e = getenv("LS_K1_SHAPE");
+        shape = !e ? 0 : (!strcmp(e, "6x4") ? 1 : (!strcmp(e, "8x4") ? 2 : 0));
       }
       if (!ctx->k1_attr_set) {
-        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(TileSmemT<true>)));
-        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(TileSmemT<true>)));
-        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<true, 4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)sizeof(TileSmemT<true>)));
+        LS_CK(cudaFuncSetAttribute(pileup_count_kernel<false, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)sizeof(TileSmemT<false>)));
         ctx->k1_attr_set = true;
       }
       ca.cnt1 = packed ? (1u << K1_CNT_SHIFT) : 0u;
       // 12-bit packed counters unless some cell has > K1_MAX_RUN_PACKED reads in one tile
       if (!packed)
-        pileup_count_kernel<false, 1><<<(unsigned)max_parts, K1_THREADS, sm_u, st>>>(ca);
-      else if (ctas == 3)
-        pileup_count_kernel<true, 3><<<(unsigned)max_parts, K1_THREADS, sm_p, st>>>(ca);
+        pileup_count_kernel<false, 1, 8><<<(unsigned)max_parts, 256, sm_u, st>>>(ca);
+      else if (shape == 1)
+        pileup_count_kernel<true, 4, 6><<<(unsigned)max_parts, 192, sm_p, st>>>(ca);
+      else if (shape == 2)
+        pileup_count_kernel<true, 4, 8><<<(unsigned)max_parts, 256, sm_p, st>>>(ca);
       else
-        pileup_count_kernel<true, 4><<<(unsigned)max_parts, K1_THREADS, sm_p, st>>>(ca);
+        pileup_count_kernel<true, 3, 8><<<(unsigned)max_parts, 256, sm_p, st>>>(ca);
     }
     ++launches;
     LS_CK(cudaGetLastError());
