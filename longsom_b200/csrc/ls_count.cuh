@@ -57,20 +57,11 @@ __host__ __device__ __forceinline__ int k1_col(int s) { return s + (s >> 5); }  
 struct CountArgs {
   const uint8_t *seq4, *qual;                // device copies (padded, seq4 nibble-swapped; see ls_ctx)
   const uint2 *units;                        // S stream, then M, then U
-  const uint32_t *offs_s, *offs_m, *offs_u;  // [nseg + 1] first unit of sorted segment i in its stream (offs_u may be null)
   const uint64_t *tot_s, *tot_m;             // stream sizes (M starts at *tot_s, U at *tot_s + *tot_m)
-  const uint32_t *goffs;                     // [nseg + 1] first (cell, window) group of the runs starting at or after segment i
   const uint32_t *gdir;                      // [n_groups + 1] first unit (in M) of every group, in run / window order
-  const uint64_t *keys;
-  const int64_t *slot_tile;
-  const uint32_t *slot_lo;
-  const uint32_t *part_slot, *part_k, *slot_nparts;
+  int with_u;                                // a U stream exists (--min_ac > 0)
+  const struct PartDesc *parts;              // [grid] what every CTA of the count kernel works on (part_build_kernel)
   uint32_t *slot_done;
-  const uint32_t *n_parts;
-  int64_t n_windows;
-  const int32_t *wstart, *wend;
-  const int64_t *wtile_base;
-  const uint64_t *wref_off;
   const uint8_t *ref;
   uint32_t *out;    // [n_slots][LS_SITE_WORDS][LS_TILE]
   uint32_t *acbuf;  // [n_slots][LS_TILE], only when min_ac > 0
@@ -83,6 +74,21 @@ struct CountArgs {
   uint32_t cnt1;  // 1 << K1_CNT_SHIFT for the packed kernel, 0 for the unpacked one (a run-time value on purpose:
                   // as a compile-time constant it takes PRMT's immediate slot and the byte selectors need a MOV each)
 };
+
+// Everything a count CTA needs to start, in one 64-byte record: without it the CTA walks a chain of dependent loads
+// (part -> slot -> tile -> binary search over the windows -> stream offsets) before its first unit, and that chain was
+// an eighth of the kernel's warp time.
+struct alignas(16) PartDesc {
+  uint32_t slot;     // 0xffffffff: unused grid entry
+  uint32_t nparts;   // parts of this slot's tile
+  int32_t tile_start, tile_end;
+  uint64_t ref_base;  // index in ref[] of the tile's first column
+  uint32_t s_lo, s_n;  // the part's units in the S stream
+  uint32_t g_lo, g_n;  // its slice of the group directory (runs that START in the part)
+  uint32_t u_lo, u_n;  // its units in the U stream (relative to the stream's start)
+  uint32_t pad[4];
+};
+static_assert(sizeof(PartDesc) == 64, "PartDesc layout");
 
 template <bool PACKED>
 struct TileSmemT {
@@ -97,11 +103,11 @@ struct TileSmemT {
   uint32_t acx[K1_ROWW];                  // alt entries of visible-but-uncounted reads; LAST: only allocated with --min_ac > 0
 };
 
-__device__ __forceinline__ int64_t window_of_tile(const CountArgs &a, int64_t tile) {
-  int64_t lo = 0, hi = a.n_windows;  // last w with wtile_base[w] <= tile
+__device__ __forceinline__ int64_t window_of_tile(const int64_t *__restrict__ wtile_base, int64_t n_windows, int64_t tile) {
+  int64_t lo = 0, hi = n_windows;  // last w with wtile_base[w] <= tile
   while (hi - lo > 1) {
     int64_t m = (lo + hi) >> 1;
-    if (a.wtile_base[m] <= tile)
+    if (wtile_base[m] <= tile)
       lo = m;
     else
       hi = m;
@@ -590,41 +596,26 @@ __global__ void __launch_bounds__(256) expand_runs_kernel(ExpandArgs a) {
   });
 }
 
-// first sorted segment at or after i (inside the slot) that starts a run; warp-uniform
-__device__ __forceinline__ uint32_t run_start_at_or_after(const uint64_t *__restrict__ keys, uint32_t i, uint32_t slot_lo,
-                                                          uint32_t slot_hi, int lane) {
-  if (i <= slot_lo) return slot_lo;
-  for (;;) {
-    if (i >= slot_hi) return slot_hi;
-    const uint32_t idx = i + (uint32_t)lane;
-    const bool st = idx >= slot_hi || keys[idx] != keys[idx - 1];
-    const uint32_t m = __ballot_sync(0xffffffffu, st);
-    if (m) return i + (uint32_t)(__ffs(m) - 1);
-    i += 32u;
-  }
-}
-
 template <bool PACKED, int MIN_CTAS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(CountArgs a) {
   constexpr int K1_THREADS = WARPS * 32;  // shadows the default shape inside the kernel
   constexpr int K1_WARPS = WARPS;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TileSmemT<PACKED> &sm = *reinterpret_cast<TileSmemT<PACKED> *>(smem_raw);
-  const uint32_t part = blockIdx.x;
-  const uint32_t pslot = a.part_slot[part];
-  if (pslot == 0xffffffffu) return;  // unused entry between the heavy (front) and light (back) parts
+  PartDesc pd;
+  {
+    const uint4 *src = reinterpret_cast<const uint4 *>(a.parts + blockIdx.x);
+    uint4 *dst = reinterpret_cast<uint4 *>(&pd);
+    dst[0] = __ldg(src);
+    dst[1] = __ldg(src + 1);
+    dst[2] = __ldg(src + 2);
+  }
+  if (pd.slot == 0xffffffffu) return;  // unused entry between the heavy (front) and light (back) parts
   const int lane = threadIdx.x & 31;
-  const int64_t slot = pslot;
-  const uint32_t pk = a.part_k[part];
-  const uint32_t nparts = a.slot_nparts[slot];
-  const int64_t tile = a.slot_tile[slot];
-  const uint32_t slot_lo = a.slot_lo[slot], slot_hi = a.slot_lo[slot + 1];
-  const uint32_t my_lo = slot_lo + pk * K1_PART_SEGS;
-  const uint32_t my_hi = (my_lo + K1_PART_SEGS) < slot_hi ? (my_lo + K1_PART_SEGS) : slot_hi;
-  const int64_t w = window_of_tile(a, tile);
-  const int32_t tile_start = a.wstart[w] + (int32_t)(tile - a.wtile_base[w]) * LS_TILE;
-  const int32_t tile_end = (tile_start + LS_TILE) < a.wend[w] ? (tile_start + LS_TILE) : a.wend[w];
-  const uint64_t ref_base = a.wref_off[w] + (uint64_t)(tile_start - a.wstart[w]);
+  const int64_t slot = pd.slot;
+  const uint32_t nparts = pd.nparts;
+  const int32_t tile_start = pd.tile_start, tile_end = pd.tile_end;
+  const uint64_t ref_base = pd.ref_base;
 
   {  // zero the accumulators, stage the reference bases, build the nibble tables
     uint4 *z = reinterpret_cast<uint4 *>(&sm);
@@ -665,54 +656,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(Coun
 #pragma unroll
   for (int i = 0; i < 8; ++i) seen[i] = 0u;
 
-  // ---- phase 1: the part's single-segment units, one unit per lane and step ------------------------------------
-  {
-    const uint32_t u_lo = a.offs_s[my_lo];
-    const uint32_t nun = a.offs_s[my_hi] - u_lo;
-    const uint2 *us = a.units + u_lo;
-    for (;;) {
-      // guided self-scheduling: a grab is G batches of 32 units, G shrinking towards the end of the stream so that
-      // the warps of the CTA finish together
-      uint32_t g = 0, G = 0;
-      if (lane == 0) {
-        const uint32_t seen_next = *(volatile uint32_t *)&sm.next1;
-        const uint32_t left = seen_next < nun ? nun - seen_next : 0u;
-        G = left / (64u * K1_WARPS);
-        G = G < 1u ? 1u : (G > 8u ? 8u : G);
-        g = atomicAdd(&sm.next1, 32u * G);
-      }
-      g = __shfl_sync(0xffffffffu, g, 0);
-      G = __shfl_sync(0xffffffffu, G, 0);
-      if (g >= nun) break;
-      // descriptors run two steps ahead of the counting, the unit's loads one step ahead
-      uint32_t k = g + (uint32_t)lane;
-      uint2 u0 = k < nun ? __ldg(us + k) : make_uint2(0u, 0u);
-      uint2 u1 = (G > 1u && k + 32u < nun) ? __ldg(us + k + 32u) : make_uint2(0u, 0u);
-      URaw r0 = issue_unit(a, u0);
-      for (uint32_t b = 0; b < G; ++b) {
-        uint2 u2 = make_uint2(0u, 0u);
-        if (b + 2u < G && k + 64u < nun) u2 = __ldg(us + k + 64u);
-        const URaw r1 = issue_unit(a, u1);
-        const UData d0 = align_unit(r0, u0);
-        count_unit<PACKED, false>(c, u0.y, d0, lane, seen);
-        u0 = u1;
-        u1 = u2;
-        r0 = r1;
-        k += 32u;
-      }
-    }
-  }
-
-  // ---- phase 2: the same-cell runs that start in the part.  Every lane works through whole (cell, window) groups,
+  // ---- phase 1: the same-cell runs that start in the part.  Every lane works through whole (cell, window) groups,
   // which it claims one ahead from the part's slice of the group directory ---------------------------------------
   {
-    uint32_t r_lo = my_lo, r_hi = my_hi;
-    if (nparts > 1) {
-      r_lo = run_start_at_or_after(a.keys, my_lo, slot_lo, slot_hi, lane);
-      r_hi = run_start_at_or_after(a.keys, my_hi, slot_lo, slot_hi, lane);
-    }
-    const uint32_t g_lo = a.goffs[r_lo];
-    const uint32_t ngr = a.goffs[r_hi] - g_lo;
+    const uint32_t g_lo = pd.g_lo, ngr = pd.g_n;
     const uint32_t *gd = a.gdir + g_lo;
     const uint2 *um = a.units + *a.tot_s;
     const uint32_t lt = (1u << lane) - 1u;
@@ -789,11 +736,41 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(Coun
     }
   }
 
+  // ---- phase 2: the part's single-segment units, one unit per lane and step.  It runs AFTER the same-cell runs:
+  // its guided grabs are fine-grained (one 32-unit batch at the end), so the warps that leave phase 1 early absorb
+  // the time other warps still spend on their last long groups and the CTA reaches the barrier together ----------
+  {
+    const uint32_t nun = pd.s_n;
+    const uint2 *us = a.units + pd.s_lo;
+    // one 32-unit batch per grab; the warp claims its batches two steps ahead, so that the unit descriptors (two
+    // ahead) and the units' bases (one ahead) are in flight while it counts -- the pipeline never drains between grabs
+    auto grab = [&]() -> uint32_t {
+      uint32_t g = 0;
+      if (lane == 0) g = atomicAdd(&sm.next1, 32u);
+      return __shfl_sync(0xffffffffu, g, 0) + (uint32_t)lane;
+    };
+    uint32_t k0 = grab(), k1 = grab();
+    uint2 u0 = k0 < nun ? __ldg(us + k0) : make_uint2(0u, 0u);
+    uint2 u1 = k1 < nun ? __ldg(us + k1) : make_uint2(0u, 0u);
+    URaw r0 = issue_unit(a, u0);
+    while (k0 - (uint32_t)lane < nun) {
+      const uint32_t k2 = grab();
+      const uint2 u2 = k2 < nun ? __ldg(us + k2) : make_uint2(0u, 0u);
+      const URaw r1 = issue_unit(a, u1);
+      const UData d0 = align_unit(r0, u0);
+      count_unit<PACKED, false>(c, u0.y, d0, lane, seen);
+      u0 = u1;
+      u1 = u2;
+      r0 = r1;
+      k0 = k1;
+      k1 = k2;
+    }
+  }
+
   // ---- phase 3: visible-but-uncounted reads (only emitted when --min_ac > 0) ---------------------------------
-  if (a.offs_u) {
-    const uint32_t u_lo = a.offs_u[my_lo], u_hi = a.offs_u[my_hi];
-    const uint2 *uu = a.units + *a.tot_s + *a.tot_m + u_lo;
-    const uint32_t nun = u_hi - u_lo;
+  if (a.with_u) {
+    const uint2 *uu = a.units + *a.tot_s + *a.tot_m + pd.u_lo;
+    const uint32_t nun = pd.u_n;
     for (;;) {
       uint32_t g = 0;
       if (lane == 0) g = atomicAdd(&sm.next3, 32u);
@@ -902,38 +879,86 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(Coun
   if (last_part && threadIdx.x == 0) a.npass[slot] = sm.npass;
 }
 
-// One CTA per slot: split the slot into parts, register them (part_slot[] pre-set to 0xffffffff), zero the HBM slot of
+// One CTA per slot: split the slot into parts, write their descriptors (parts[] pre-set to 0xff), zero the HBM slot of
 // multi-part tiles (their parts merge with atomics).
-__global__ void __launch_bounds__(128) part_build_kernel(const uint32_t *__restrict__ slot_lo, int64_t n_slots,
-                                                         uint32_t *__restrict__ part_slot, uint32_t *__restrict__ part_k,
-                                                         uint32_t *__restrict__ slot_nparts, uint32_t *__restrict__ slot_done,
-                                                         uint32_t *__restrict__ n_parts, uint32_t *__restrict__ n_light,
-                                                         uint32_t max_parts, uint32_t *__restrict__ out,
-                                                         uint32_t *__restrict__ acbuf) {
+struct PartBuildArgs {
+  const uint32_t *slot_lo;
+  const int64_t *slot_tile;
+  int64_t n_slots;
+  const uint64_t *keys;
+  const uint32_t *offs_s, *offs_u, *goffs;
+  int64_t n_windows;
+  const int32_t *wstart, *wend;
+  const int64_t *wtile_base;
+  const uint64_t *wref_off;
+  PartDesc *parts;
+  uint32_t *slot_done;
+  uint32_t *n_parts, *n_light;
+  uint32_t max_parts;
+  uint32_t *out, *acbuf;
+};
+
+// first sorted segment at or after i (inside the slot) that starts a same-cell run or a single
+__device__ __forceinline__ uint32_t run_start_at_or_after(const uint64_t *__restrict__ keys, uint32_t i, uint32_t slot_lo,
+                                                          uint32_t slot_hi) {
+  if (i <= slot_lo) return slot_lo;
+  while (i < slot_hi && keys[i] == keys[i - 1]) ++i;
+  return i < slot_hi ? i : slot_hi;
+}
+
+__global__ void __launch_bounds__(128) part_build_kernel(PartBuildArgs a) {
   const int64_t slot = blockIdx.x;
-  if (slot >= n_slots) return;
-  const uint32_t n = slot_lo[slot + 1] - slot_lo[slot];
+  if (slot >= a.n_slots) return;
+  const uint32_t slot_lo = a.slot_lo[slot], slot_hi = a.slot_lo[slot + 1];
+  const uint32_t n = slot_hi - slot_lo;
   const uint32_t np = n == 0 ? 1u : (n + K1_PART_SEGS - 1) / K1_PART_SEGS;
   __shared__ uint32_t base;
+  __shared__ int32_t sh_start, sh_end;
+  __shared__ uint64_t sh_ref;
   if (threadIdx.x == 0) {
     // deep tiles first: their parts sit at the front of the grid, shallow tiles fill in behind (no long tail)
     if (n >= (uint32_t)K1_PART_SEGS / 2)
-      base = atomicAdd(n_parts, np);
+      base = atomicAdd(a.n_parts, np);
     else
-      base = max_parts - np - atomicAdd(n_light, np);
-    slot_nparts[slot] = np;
-    slot_done[slot] = 0;
+      base = a.max_parts - np - atomicAdd(a.n_light, np);
+    a.slot_done[slot] = 0;
+    const int64_t tile = a.slot_tile[slot];
+    const int64_t w = window_of_tile(a.wtile_base, a.n_windows, tile);
+    const int32_t ts = a.wstart[w] + (int32_t)(tile - a.wtile_base[w]) * LS_TILE;
+    sh_start = ts;
+    sh_end = (ts + LS_TILE) < a.wend[w] ? (ts + LS_TILE) : a.wend[w];
+    sh_ref = a.wref_off[w] + (uint64_t)(ts - a.wstart[w]);
   }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < np; k += blockDim.x) {
-    part_slot[base + k] = (uint32_t)slot;
-    part_k[base + k] = k;
+    const uint32_t my_lo = slot_lo + k * K1_PART_SEGS;
+    const uint32_t my_hi = (my_lo + K1_PART_SEGS) < slot_hi ? (my_lo + K1_PART_SEGS) : slot_hi;
+    // same-cell runs never straddle parts: a run belongs to the part that holds its first segment
+    uint32_t r_lo = my_lo, r_hi = my_hi;
+    if (np > 1) {
+      r_lo = run_start_at_or_after(a.keys, my_lo, slot_lo, slot_hi);
+      r_hi = run_start_at_or_after(a.keys, my_hi, slot_lo, slot_hi);
+    }
+    PartDesc d;
+    d.slot = (uint32_t)slot;
+    d.nparts = np;
+    d.tile_start = sh_start;
+    d.tile_end = sh_end;
+    d.ref_base = sh_ref;
+    d.s_lo = a.offs_s[my_lo];
+    d.s_n = a.offs_s[my_hi] - d.s_lo;
+    d.g_lo = a.goffs[r_lo];
+    d.g_n = a.goffs[r_hi] - d.g_lo;
+    d.u_lo = a.offs_u ? a.offs_u[my_lo] : 0u;
+    d.u_n = a.offs_u ? a.offs_u[my_hi] - d.u_lo : 0u;
+    d.pad[0] = d.pad[1] = d.pad[2] = d.pad[3] = 0u;
+    a.parts[base + k] = d;
   }
   if (np > 1) {
-    uint32_t *o = out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
+    uint32_t *o = a.out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
     for (int i = threadIdx.x; i < LS_SITE_WORDS * LS_TILE; i += blockDim.x) o[i] = 0u;
-    if (acbuf)
-      for (int i = threadIdx.x; i < LS_TILE; i += blockDim.x) acbuf[(size_t)slot * LS_TILE + i] = 0u;
+    if (a.acbuf)
+      for (int i = threadIdx.x; i < LS_TILE; i += blockDim.x) a.acbuf[(size_t)slot * LS_TILE + i] = 0u;
   }
 }
 

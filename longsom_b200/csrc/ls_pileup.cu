@@ -377,43 +377,45 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     LS_CK(ctx->slot_npass.ensure((size_t)n_slots * 4));
     LS_CK(ctx->slot_off.ensure((size_t)n_slots * 4));
     const int64_t max_parts = n_slots + nseg / K1_PART_SEGS + 1;
-    LS_CK(ctx->part_slot.ensure((size_t)max_parts * 4));
-    LS_CK(ctx->part_k.ensure((size_t)max_parts * 4));
-    LS_CK(ctx->slot_nparts.ensure((size_t)n_slots * 4));
+    LS_CK(ctx->part_slot.ensure((size_t)max_parts * sizeof(PartDesc)));
     LS_CK(ctx->slot_done.ensure((size_t)n_slots * 4));
     if (params->min_ac > 0) LS_CK(ctx->acbuf.ensure((size_t)n_slots * LS_TILE * 4));
-    LS_CK(cudaMemsetAsync(ctx->part_slot.p, 0xff, (size_t)max_parts * 4, st));
-    part_build_kernel<<<(unsigned)n_slots, 128, 0, st>>>(
-        ctx->slot_lo.as<uint32_t>(), n_slots, ctx->part_slot.as<uint32_t>(), ctx->part_k.as<uint32_t>(),
-        ctx->slot_nparts.as<uint32_t>(), ctx->slot_done.as<uint32_t>(), d_nparts, d_nlight, (uint32_t)max_parts,
-        ctx->slot_out.as<uint32_t>(),
-        params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr);
+    LS_CK(cudaMemsetAsync(ctx->part_slot.p, 0xff, (size_t)max_parts * sizeof(PartDesc), st));
+    {
+      PartBuildArgs pb;
+      pb.slot_lo = ctx->slot_lo.as<uint32_t>();
+      pb.slot_tile = ctx->slot_tile.as<int64_t>();
+      pb.n_slots = n_slots;
+      pb.keys = ctx->sorted_keys;
+      pb.offs_s = ctx->offs_s.as<uint32_t>();
+      pb.offs_u = params->min_ac > 0 ? ctx->offs_u.as<uint32_t>() : nullptr;
+      pb.goffs = ctx->goffs.as<uint32_t>();
+      pb.n_windows = ctx->n_windows;
+      pb.wstart = ctx->wstart.as<int32_t>();
+      pb.wend = ctx->wend.as<int32_t>();
+      pb.wtile_base = ctx->wtile_base.as<int64_t>();
+      pb.wref_off = ctx->wref_off.as<uint64_t>();
+      pb.parts = ctx->part_slot.as<PartDesc>();
+      pb.slot_done = ctx->slot_done.as<uint32_t>();
+      pb.n_parts = d_nparts;
+      pb.n_light = d_nlight;
+      pb.max_parts = (uint32_t)max_parts;
+      pb.out = ctx->slot_out.as<uint32_t>();
+      pb.acbuf = params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr;
+      part_build_kernel<<<(unsigned)n_slots, 128, 0, st>>>(pb);
+    }
     ++launches;
     CountArgs ca;
-    ca.part_slot = ctx->part_slot.as<uint32_t>();
-    ca.part_k = ctx->part_k.as<uint32_t>();
-    ca.slot_nparts = ctx->slot_nparts.as<uint32_t>();
+    ca.parts = ctx->part_slot.as<PartDesc>();
     ca.slot_done = ctx->slot_done.as<uint32_t>();
-    ca.n_parts = d_nparts;
     ca.acbuf = params->min_ac > 0 ? ctx->acbuf.as<uint32_t>() : nullptr;
     ca.units = ctx->units.as<uint2>();
-    ca.offs_s = ctx->offs_s.as<uint32_t>();
-    ca.offs_m = ctx->offs_m.as<uint32_t>();
-    ca.offs_u = params->min_ac > 0 ? ctx->offs_u.as<uint32_t>() : nullptr;
+    ca.with_u = params->min_ac > 0 ? 1 : 0;
     ca.tot_s = d_tot_s;
     ca.tot_m = d_tot_m;
-    ca.goffs = ctx->goffs.as<uint32_t>();
     ca.gdir = ctx->gdir.as<uint32_t>();
     ca.seq4 = ctx->seq4_d();
     ca.qual = ctx->qual_d();
-    ca.keys = ctx->sorted_keys;
-    ca.slot_tile = ctx->slot_tile.as<int64_t>();
-    ca.slot_lo = ctx->slot_lo.as<uint32_t>();
-    ca.n_windows = ctx->n_windows;
-    ca.wstart = ctx->wstart.as<int32_t>();
-    ca.wend = ctx->wend.as<int32_t>();
-    ca.wtile_base = ctx->wtile_base.as<int64_t>();
-    ca.wref_off = ctx->wref_off.as<uint64_t>();
     ca.ref = ctx->ref.as<uint8_t>();
     ca.out = ctx->slot_out.as<uint32_t>();
     ca.mask = ctx->slot_mask.as<uint32_t>();
