@@ -83,7 +83,7 @@ class _BamHandle:
 def read_bam(path, threads=None):
     lib = _load_host()
     if threads is None:
-        threads = min(32, os.cpu_count() or 1)
+        threads = min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     owner = _BamHandle(lib, lib.ls_bam_read(os.fsencode(path), int(threads)))
     h = owner.h
     err = lib.ls_bam_error(h)

@@ -1,9 +1,8 @@
 """Drop-in MergeBaseCellCounts (reference: workflow/scripts/SNVCalling/MergeBaseCellCounts.py).
 
 Host glue between the per-cell-type BaseCellCounter tables and BaseCellCalling.step1: a positional
-merge on (chrom, pos).  The reference advances N file cursors in lock-step (:116-204); here every
-table is indexed by (chrom, pos) and the union is emitted in the reference's order
-(chrom lexicographic, pos ascending), with 'NA' where a cell type lacks the site."""
+merge on (chrom, pos): N file cursors advanced in lock-step (:116-204), one row per table in memory,
+chromosomes in lexicographic order, positions ascending, 'NA' where a cell type lacks the site."""
 import argparse
 import collections
 import glob
@@ -27,46 +26,75 @@ def _most_common_join(values):
     return '|'.join(k for k, _ in sorted(counter.items(), key=lambda kv: kv[1], reverse=True))
 
 
+class _Cursor:
+    """One input table: the row its cursor points at.  A row whose position does not increase inside its chromosome
+    is skipped, like updatefields of the reference (:8-23); past the last row chrom is '' (:177-180)."""
+    __slots__ = ("f", "chrom", "pos", "ref", "info", "bc", "done")
+
+    def __init__(self, path):
+        self.f = open(path)
+        for _ in range(HEADER_LINES):
+            self.f.readline()
+        self.chrom, self.pos, self.ref, self.info, self.bc, self.done = 'x', 0, 0, 0, 0, False
+        first = self.f.readline()
+        if first.strip() == "":
+            self.done = True   # (the reference cannot parse a table without rows; here it contributes 'NA' everywhere)
+            self.chrom, self.pos = '', -1
+        else:
+            self._take(first.strip())
+
+    def _take(self, line):
+        chrom, pos, ref, info, bc = line.split('\t')
+        pos = int(pos)
+        if chrom == self.chrom and self.pos >= pos:
+            return
+        self.chrom, self.pos, self.ref, self.info, self.bc = chrom, pos, ref, info, bc
+
+    def advance(self):
+        line = self.f.readline().strip()
+        if line == "":   # end of file or a blank line: the table ends here
+            self.done = True
+            self.chrom, self.pos = '', -1
+            return False
+        self._take(line)
+        return True
+
+
 def merge_cell_types_files(infiles, outfile):
-    tables, header = [], ['#CHROM', 'Start', 'End', 'REF', 'INFO']
-    info_fmt = []  # last INFO format string seen per file (the reference passes this whole list to sort_set)
+    """N file cursors advanced in lock-step over the (chrom, pos)-sorted tables, one row per file in memory
+    (MergeBaseCellCounts.py:116-204): chromosomes in lexicographic order, positions ascending, 'NA' where a cell type
+    lacks the site."""
+    header = ['#CHROM', 'Start', 'End', 'REF', 'INFO']
+    cursors = []
     for path in infiles:
         header.append(os.path.basename(path).split('.')[-2])
-        rows = {}
-        fmt = None
-        with open(path) as f:
-            for i, line in enumerate(f):
-                if i < HEADER_LINES:
-                    continue
-                line = line.strip()
-                if line == "":
-                    break
-                p = line.split('\t')
-                rows[(p[0], int(p[1]))] = (p[2], p[3], p[4])
-        tables.append(rows)
-    keys = sorted(set().union(*[t.keys() for t in tables])) if tables else []
-    # the reference keeps, per file, the fields of the line its cursor currently points at; the INFO
-    # format column is the same constant on every line, so its joined set is that constant
+        cursors.append(_Cursor(path))
+    cur_chr, cur_pos = 1, 0
     with open(outfile, 'w') as out:
         out.write("##fileDate=%s\n" % time.strftime("%d/%m/%Y"))
         out.write(COUNTER_CONCEPTS + '\n')
         out.write('\t'.join(header) + '\n')
-        for t in tables:
-            first = next(iter(t.values()), None)
-            info_fmt.append(first[1] if first else 'NA')
-        fmt_joined = _most_common_join(info_fmt)
-        for chrom, pos in keys:
-            refs, cells = [], []
-            for t in tables:
-                r = t.get((chrom, pos))
-                if r is None:
-                    refs.append('NA')
-                    cells.append('NA')
-                else:
-                    refs.append(r[0])
-                    cells.append(r[2])
-            out.write('\t'.join([chrom, str(pos), str(pos), _most_common_join(refs), fmt_joined]) + '\t' +
-                      '\t'.join(cells) + '\n')
+        while not all(c.done for c in cursors):
+            for c in cursors:
+                while c.chrom == cur_chr and c.pos <= cur_pos:
+                    if not c.advance():
+                        break
+            go = not all(c.done for c in cursors)
+            if any(c.chrom == cur_chr for c in cursors):
+                if go:
+                    cur_pos = min(c.pos for c in cursors if c.chrom == cur_chr and c.pos > cur_pos)
+                    here = [c.chrom == cur_chr and c.pos == cur_pos for c in cursors]
+                    refs = [str(c.ref) if h else 'NA' for c, h in zip(cursors, here)]
+                    cells = [str(c.bc) if h else 'NA' for c, h in zip(cursors, here)]
+                    # the INFO column joins the format strings of ALL cursors, on this site or not (:80)
+                    fmt = _most_common_join([str(c.info) if c.info != 0 else 'NA' for c in cursors])
+                    out.write('\t'.join([str(cur_chr), str(cur_pos), str(cur_pos), _most_common_join(refs), fmt]) + '\t' +
+                              '\t'.join(cells) + '\n')
+            elif go:
+                cur_chr = sorted(c.chrom for c in cursors if c.chrom)[0]
+                cur_pos = 0
+    for c in cursors:
+        c.f.close()
 
 
 def initialize_parser():

@@ -59,7 +59,7 @@ def split_bam(bam, txt, outdir, donor, tissue, max_NM, max_NH, min_MAPQ, n_trim)
     rc = host.ls_bam_split(os.fsencode(bam), C.c_int(len(out_paths)), paths, blob, off, types, C.c_int64(len(barcodes)),
                            C.c_int(int(min_MAPQ)), C.c_int(-1 if max_NM is None else int(max_NM)),
                            C.c_int(-1 if max_NH is None else int(max_NH)), C.c_int(int(n_trim)),
-                           C.c_int(min(32, os.cpu_count() or 1)), C.c_int(int(os.environ.get("LONGSOM_BAM_LEVEL", "6"))), counters,
+                           C.c_int(min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))), C.c_int(int(os.environ.get("LONGSOM_BAM_LEVEL", "6"))), counters,
                            first_seen, err, C.c_int(512))
     if rc != 0:
         raise RuntimeError("ls_bam_split(%s): %s" % (bam, err.value.decode(errors="replace")))

@@ -83,6 +83,52 @@ class _Params:
         self.min_cell_types, self.max_cell_types, self.fisher_cutoff = min_cell_types, max_cell_types, fisher_cutoff
 
 
+def _text_lines(data):
+    """bytes -> lines the way the reference's text-mode `for line in f` sees them (:32-33): universal newlines
+    ('\\r\\n' and a lone '\\r' both end a line and read as '\\n'), nothing else splits a line."""
+    text = data.decode()
+    if '\r' in text:
+        text = text.replace('\r\n', '\n').replace('\r', '\n')
+    parts = text.split('\n')
+    lines = [x + '\n' for x in parts[:-1]]
+    if parts[-1]:
+        lines.append(parts[-1])
+    return lines
+
+
+def _header_lines(path):
+    """(byte offset, line) for the leading lines of the file, line ends normalised to '\\n'; (offset of EOF, None) at
+    the end.  The caller stops at the first line that is not header, whose offset is where the body starts."""
+    import re
+    size = os.path.getsize(path)
+    want = 1 << 16
+    while True:
+        with open(path, 'rb') as f:
+            data = f.read(want)
+        complete = len(data) >= size
+        out, pos = [], 0
+        for m in re.finditer(rb'([^\r\n]*)(\r\n|\n|\r)', data):
+            if not complete and m.end() == len(data):
+                break   # a '\r' at the end of the chunk may be half of a '\r\n'
+            out.append((m.start(), m.group(1).decode() + '\n'))
+            pos = m.end()
+        if complete and pos < len(data):
+            out.append((pos, data[pos:].decode()))
+            pos = len(data)
+        # enough if the chunk holds a line that is not header (the caller stops there) or the whole file
+        if complete or any(not ln.startswith('#') for _, ln in out):
+            for item in out:
+                yield item
+            yield (pos, None)
+            return
+        want *= 4
+
+
+def _available_cpus():
+    """CPUs this process may run on (the cgroup / affinity of a `threads: 1` Snakemake rule), not the machine's."""
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
 def _parse_rows(lines, cell_types_idx, fa, P):
     """Pass 1 over data lines: per row the parsed pieces, plus the beta-binomial queries of the rows
     (q1: read counts with alpha1/beta1, q2: cell counts with alpha2/beta2); row indices into the query arrays are
@@ -91,6 +137,9 @@ def _parse_rows(lines, cell_types_idx, fa, P):
     rows = []
     q1k, q1n, q2k, q2n = [], [], [], []
     for line in lines:
+            if line.startswith('##'):   # a '##' line anywhere in the file is copied through where it stands (:34-35)
+                rows.append({"verbatim": line})
+                continue
             elements = line.rstrip('\n').split('\t')
             CHROM, POS, REF = str(elements[0]), int(elements[1]), elements[3]
             up_context = down_context = '.'
@@ -160,6 +209,9 @@ def _format_rows(rows, r1, r2, P):
     max_cell_types, fisher_cutoff = P.max_cell_types, P.fisher_cutoff
     lines = []
     for row in rows:
+        if "verbatim" in row:
+            lines.append(row["verbatim"])
+            continue
         elements, calls = row["elements"], row["calls"]
         Sum_alts_bc, Sum_alts_cc, Sum_dp, Sum_nc = row["sums"]
         if row["rest"] is not None:
@@ -250,7 +302,7 @@ def _worker(conn, infile, lo, hi, cell_types_idx, fasta, P):
         fa = bamio.Fasta(fasta) if fasta is not None else None
         with open(infile, 'rb') as f:
             f.seek(lo)
-            lines = f.read(hi - lo).decode().splitlines(True)
+            lines = _text_lines(f.read(hi - lo))
         rows, q = _parse_rows(lines, cell_types_idx, fa, P)
         conn.send(("queries", q))
         r1, r2 = conn.recv()
@@ -281,32 +333,28 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
     out_lines = []          # header lines written verbatim
     cell_types_idx = None
     body_start = 0
-    with open(infile, 'rb') as f:   # header: '##' lines and the first '#CHROM' line
-        while True:
-            pos = f.tell()
-            raw = f.readline()
-            if not raw:
-                body_start = pos
-                break
-            line = raw.decode()
-            if line.startswith('##'):
-                out_lines.append(line)
-                continue
-            if line.startswith('#CHROM') and cell_types_idx is None:
-                elements = line.rstrip('\n').split('\t')
-                cell_types_idx = {x: elements[x] for x in range(len(elements)) if x > 4}
-                for _, text in INFO_HEADER:
-                    out_lines.append(text + '\n')
-                elements.insert(4, "\t".join(k for k, _ in INFO_HEADER))
-                out_lines.append('\t'.join(elements) + '\n')
-                continue
-            body_start = pos
+    # header: '##' lines and the first '#CHROM' line, split the way text mode splits them (see _text_lines)
+    for pos, line in _header_lines(infile):
+        body_start = pos
+        if line is None:
             break
+        if line.startswith('##'):
+            out_lines.append(line)
+            continue
+        if line.startswith('#CHROM') and cell_types_idx is None:
+            elements = line.rstrip('\n').split('\t')
+            cell_types_idx = {x: elements[x] for x in range(len(elements)) if x > 4}
+            for _, text in INFO_HEADER:
+                out_lines.append(text + '\n')
+            elements.insert(4, "\t".join(k for k, _ in INFO_HEADER))
+            out_lines.append('\t'.join(elements) + '\n')
+            continue
+        break
     body_bytes = os.path.getsize(infile) - body_start
     if procs is None:
         procs = int(os.environ.get("LONGSOM_PROCS", "0") or 0)   # an explicit setting is honoured as is
         if procs <= 0:
-            procs = 1 if body_bytes < (8 << 20) else min(16, os.cpu_count() or 1)   # small tables: not worth forking
+            procs = 1 if body_bytes < (8 << 20) else min(16, _available_cpus())   # small tables: not worth forking
 
     warm = {}
 
@@ -332,7 +380,7 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
         fa = bamio.Fasta(fasta) if fasta is not None else None
         with open(infile, 'rb') as f:
             f.seek(body_start)
-            data_lines = f.read().decode().splitlines(True)
+            data_lines = _text_lines(f.read())
         if cell_types_idx is None and data_lines:
             raise TypeError("'NoneType' object is not iterable")  # data before any #CHROM line: the reference fails here too
         rows, q = _parse_rows(data_lines, cell_types_idx, fa, P)

@@ -498,7 +498,7 @@ def write_counter_tsv(out_file, ID, sites: SiteCounts, bam_names):
         ref = np.ascontiguousarray(sites.ref[lo:hi])
         cnt = np.ascontiguousarray(sites.counts[lo:hi])
         rc = host.ls_write_counter_rows(os.fsencode(out_file), bam_names[t].encode(), pos.ctypes.data, ref.ctypes.data,
-                                        cnt.ctypes.data, hi - lo, min(16, os.cpu_count() or 1), 1)
+                                        cnt.ctypes.data, hi - lo, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)), 1)
         if rc != 0:
             raise IOError("ls_write_counter_rows(%s) failed: %d" % (out_file, rc))
     return True

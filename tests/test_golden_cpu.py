@@ -224,6 +224,38 @@ def test_merge_matches_reference(work):
     assert_same(file_lines(out), want, "MergeBaseCellCounts")
 
 
+def test_merge_cursor_quirks(tmp_path):
+    """The lock-step cursors of MergeBaseCellCounts.py:8-23,116-204 on crafted tables: a repeated position and a
+    position that goes backwards are skipped, a blank line ends its table, chromosomes come in lexicographic order
+    (chr10 before chr2), absent cell types read 'NA'.  The expected rows are the reference's own output on these
+    inputs (generated once with the reference script in the build container)."""
+    from longsom_b200.cli.merge import merge_cell_types_files
+    fmt = "DP|NC|CC|BC|BQ|BCf|BCr"
+    hdr = "##fileDate=x\n" + "\n".join("##INFO=%d" % i for i in range(7)) + "\n#CHROM\tStart\tREF\tINFO\tX\n"
+    a = [("chr1", 5, "A", "a5"), ("chr1", 9, "C", "a9"), ("chr1", 9, "C", "a9dup"), ("chr1", 7, "G", "a7back"),
+         ("chr10", 3, "T", "a10_3"), ("chr2", 1, "G", "a2_1")]
+    b = [("chr1", 9, "c", "b9"), ("chr2", 1, "G", "b2_1"), ("chr2", 8, ".", "b2_8")]
+    c = [("chr10", 3, "T", "c10_3")]
+    files = []
+    for name, rows, tail in (("s.A.tsv", a, ""), ("s.B.tsv", b, "\nchr3\t1\tA\t%s\tafter_blank\n" % fmt), ("s.C.tsv", c, "")):
+        fp = str(tmp_path / name)
+        with open(fp, "w") as f:
+            f.write(hdr)
+            for ch, pos, ref, bc in rows:
+                f.write("%s\t%d\t%s\t%s\t%s\n" % (ch, pos, ref, fmt, bc))
+            f.write(tail)
+        files.append(fp)
+    out = str(tmp_path / "merged.tsv")
+    merge_cell_types_files(files, out)
+    got = open(out).read().splitlines()
+    assert got[8] == "#CHROM\tStart\tEnd\tREF\tINFO\tA\tB\tC"
+    assert got[9:] == ["chr1\t5\t5\tA\t%s\ta5\tNA\tNA" % fmt,
+                       "chr1\t9\t9\tC|c\t%s\ta9\tb9\tNA" % fmt,
+                       "chr10\t3\t3\tT\t%s\ta10_3\tNA\tc10_3" % fmt,
+                       "chr2\t1\t1\tG\t%s\ta2_1\tb2_1\tNA" % fmt,
+                       "chr2\t8\t8\t.\t%s\tNA\tb2_8\tNA" % fmt]
+
+
 def test_step1_host_logic_matches_reference(work):
     import pipeline_inputs as pi
     from longsom_b200.cli.step1 import variant_calling_step1
@@ -232,6 +264,30 @@ def test_step1_host_logic_matches_reference(work):
     variant_calling_step1(os.path.join(d, "merged.tsv"), out, p["ref"], pi.ALPHA1, pi.BETA1, pi.ALPHA2, pi.BETA2, 2, 3, 5, 5,
                           2, 1, 1, OracleEngine())
     assert_same(file_lines(out), gold_lines(case, "step1.tsv"), "BaseCellCalling.step1")
+
+
+def test_step1_line_handling_follows_text_mode(work):
+    """The reference reads its table in text mode (BaseCellCalling.step1.py:32-35): '\\r\\n' ends a line like '\\n', and
+    a '##' line in the BODY is copied through where it stands.  Same table with CRLF line ends and a comment in the
+    middle -> the golden output plus that comment, in the single-process and in the forked-workers path."""
+    import pipeline_inputs as pi
+    from longsom_b200.cli.step1 import variant_calling_step1
+    case, d, p, data = work
+    src = open(os.path.join(d, "merged.tsv")).read().split("\n")
+    n_head = next(i for i, x in enumerate(src) if x.startswith("#CHROM")) + 1
+    body = [x for x in src[n_head:] if x]
+    k = len(body) // 2
+    crlf = os.path.join(d, "merged_crlf.tsv")
+    with open(crlf, "w", newline="") as f:
+        f.write("\r\n".join(src[:n_head] + body[:k] + ["##a comment in the body"] + body[k:]) + "\r\n")
+    want = gold_lines(case, "step1.tsv")
+    w_head = next(i for i, x in enumerate(want) if x.startswith("#CHROM")) + 1
+    want = want[:w_head + k] + ["##a comment in the body\n"] + want[w_head + k:]
+    for procs in (1, 3):
+        out = os.path.join(d, "step1_crlf_%d.tsv" % procs)
+        variant_calling_step1(crlf, out, p["ref"], pi.ALPHA1, pi.BETA1, pi.ALPHA2, pi.BETA2, 2, 3, 5, 5, 2, 1, 1,
+                              OracleEngine(), procs=procs)
+        assert_same(file_lines(out), want, "BaseCellCalling.step1 (CRLF, procs=%d)" % procs)
 
 
 def test_step2_host_logic_matches_reference(work):
