@@ -453,6 +453,42 @@ def run_ours(args, rank, world, local_rank):
                                             "achieved": g_alg / (gk_ms * 1e-3) / 1e9 if gk_ms else None, "peak": peak,
                                             "unit": "GB/s", "frac": g_alg / (gk_ms * 1e-3) / 1e9 / peak if gk_ms else None,
                                             "algorithmic_bytes": g_alg}}}
+        if world == 1:
+            # K2 and K3 on their own (the step1 / step2 kernels of the path), host arrays in and out like their callers
+            rng = np.random.default_rng(11)
+            m2 = int(2_000_000 * min(1.0, args.scale))
+            n2 = np.minimum(2 + rng.geometric(0.01, m2), 200000).astype(np.int32)
+            k2 = np.minimum(1 + rng.geometric(0.25, m2), n2).astype(np.int32)
+            big = rng.random(m2) < 0.002   # a few deep sites with long tails (k > 128: the staged path)
+            k2[big] = np.minimum(n2[big], 129 + rng.integers(0, 2000, int(big.sum()))).astype(np.int32)
+            eng.betabinom_sf(k2[:1000], n2[:1000], 0.26, 173.9)
+            t0 = time.perf_counter()
+            eng.betabinom_sf(k2, n2, 0.26, 173.9)
+            k2_wall = time.perf_counter() - t0
+            st2 = eng.last_stats
+            m3, nk3 = int(2_000_000 * min(1.0, args.scale)), int(4_000_000 * min(1.0, args.scale))
+            tab = (rng.integers(0, 25, nk3).astype(np.uint64) << np.uint64(32)) | rng.integers(0, 250_000_000, nk3).astype(np.uint64)
+            q3 = np.concatenate([tab[rng.integers(0, nk3, m3 // 2)],
+                                 (rng.integers(0, 25, m3 - m3 // 2).astype(np.uint64) << np.uint64(32)) |
+                                 rng.integers(0, 250_000_000, m3 - m3 // 2).astype(np.uint64)])
+            eng.site_table_load(0, tab)
+            st3a = eng.last_stats
+            eng.site_table_lookup(0, q3[:1000])
+            t0 = time.perf_counter()
+            eng.site_table_lookup(0, q3)
+            k3_wall = time.perf_counter() - t0
+            st3b = eng.last_stats
+            secondary["k2"] = {"kernel": "bb_small_kernel (k <= 128, terms in registers) + staged terms for longer tails",
+                               "queries": m2, "pmf_terms": int(st2["n_events"]), "kernel_ms": st2["ms_count"],
+                               "fp64_pmf_terms_per_s": st2["n_events"] / (st2["ms_count"] * 1e-3) if st2["ms_count"] else None,
+                               "queries_per_s_host_to_host": m2 / k2_wall}
+            secondary["k3"] = {"kernel": "mask_lookup_kernel against a resident sorted table", "table_keys": nk3, "queries": m3,
+                               "table_sort_ms": st3a["ms_sort"], "lookup_ms": st3b["ms_count"],
+                               "lookups_per_s": m3 / (st3b["ms_count"] * 1e-3) if st3b["ms_count"] else None,
+                               "GB_per_s": (9.0 * m3 + 8.0 * nk3) / (st3b["ms_count"] * 1e-3) / 1e9 if st3b["ms_count"] else None,
+                               "bytes_note": "8 B query + 1 B hit per lookup + one pass over the table",
+                               "queries_per_s_host_to_host": m3 / k3_wall}
+            del tab, q3, k2, n2
         del got
     # ---- BASELINE.json configs[3] (hotspot stress: 20 genes at > 1e5 reads / locus, 10k cells), N = 1 only --------
     c4 = None

@@ -219,6 +219,15 @@ int ls_betabinom_sf(ls_ctx *ctx, const int32_t *k, const int32_t *n, double a, d
  * or unique; hit[i] = 1 iff query[i] is in keys. */
 int ls_site_mask(ls_ctx *ctx, const uint64_t *keys, int64_t n_keys, const uint64_t *query,
                  int64_t m, uint8_t *hit, ls_run_stats *stats);
+/* The same in two steps, for a site list that is looked up more than once (step2 holds the
+ * editing list and the two panels of normals for the whole run, :197-221): the table is
+ * sorted once and stays resident in HBM in slot `table` (0 .. LS_SITE_TABLES-1) until that
+ * slot is loaded again.  A lookup in an empty slot is LS_E_STATE. */
+#define LS_SITE_TABLES 4
+int ls_site_table_load(ls_ctx *ctx, int table, const uint64_t *keys, int64_t n_keys,
+                       ls_run_stats *stats);
+int ls_site_table_lookup(ls_ctx *ctx, int table, const uint64_t *query, int64_t m, uint8_t *hit,
+                         ls_run_stats *stats);
 
 /* ---- device-resident handles for benchmarking (inputs already in HBM) ----------------------- */
 int ls_device_synchronize(ls_ctx *ctx);

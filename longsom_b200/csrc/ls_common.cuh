@@ -114,7 +114,7 @@ struct ls_ctx {
   ls_count_params params = {};
   DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;
-  DBuf drop_keys, rend, wcount, part_slot, part_k, slot_nparts, slot_done, acbuf;
+  DBuf drop_keys, rend, wcount, part_slot, slot_done, acbuf;  // part_slot: PartDesc records
   DBuf offs_s, offs_m, offs_u, units, goffs, gdir, mrank, mlist;
   int64_t n_drop = 0;
   bool k1_attr_set = false;
@@ -128,6 +128,10 @@ struct ls_ctx {
   DBuf out_tid, out_pos, out_ref, out_counts;
   DBuf l2_scratch;
   DBuf g_a, g_b, g_c, g_d, g_e;  // genotype / betabinom / mask scratch
+  // K3: resident sorted site tables (slot LS_SITE_TABLES is the scratch table of the one-shot ls_site_mask)
+  DBuf site_tab[LS_SITE_TABLES + 1];
+  int64_t site_tab_n[LS_SITE_TABLES + 1] = {};
+  bool site_tab_ok[LS_SITE_TABLES + 1] = {};
   DBuf gs_cnt, gs_hits_a, gs_hits_b, gs_flag, gs_tup, gs_p, gs_skip;  // sparse genotyping
   int64_t n_tuples = 0;
   bool have_tuples = false;

@@ -175,6 +175,24 @@ class Engine:
         self.last_stats = st.as_dict()
         return hit
 
+    def site_table_load(self, table, keys):
+        """Sort a (tid<<32 | pos) key table into resident slot `table`; look it up with site_table_lookup."""
+        keys = np.ascontiguousarray(keys, np.uint64)
+        st = L.LsRunStats()
+        self._check(self._lib.ls_site_table_load(self._ctx, int(table), keys.ctypes.data_as(C.c_void_p) if keys.size else None,
+                                                 keys.shape[0], C.byref(st)), "ls_site_table_load")
+        self.last_stats = st.as_dict()
+
+    def site_table_lookup(self, table, query):
+        query = np.ascontiguousarray(query, np.uint64)
+        hit = np.zeros(query.shape[0], np.uint8)
+        st = L.LsRunStats()
+        vp = lambda x: x.ctypes.data_as(C.c_void_p) if x.size else None
+        self._check(self._lib.ls_site_table_lookup(self._ctx, int(table), vp(query), query.shape[0], vp(hit), C.byref(st)),
+                    "ls_site_table_lookup")
+        self.last_stats = st.as_dict()
+        return hit
+
     def flush_l2(self):
         self._check(self._lib.ls_flush_l2(self._ctx), "ls_flush_l2")
 

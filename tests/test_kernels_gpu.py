@@ -97,3 +97,30 @@ def test_site_mask(engine):
     assert np.array_equal(hit, want)
     assert hit[:5000].all()
     assert engine.site_mask(np.zeros(0, np.uint64), q).sum() == 0
+
+
+def test_site_tables_stay_resident(engine):
+    """K3 in two steps (step2 keeps its three site lists for the whole run, BaseCellCalling.step2.py:197-221): tables
+    sorted once into resident slots, several lookups against each, slots independent, reload replaces, an empty slot
+    is a state error."""
+    rng = np.random.default_rng(6)
+
+    def table(n, seed):
+        r = np.random.default_rng(seed)
+        return (r.integers(0, 90, n).astype(np.uint64) << np.uint64(32)) | r.integers(0, 250_000_000, n).astype(np.uint64)
+    t0, t1 = table(1_000_000, 1), table(30_000, 2)
+    engine.site_table_load(0, t0)
+    engine.site_table_load(1, t1)
+    for rep in range(3):
+        q = np.concatenate([t0[rng.integers(0, t0.shape[0], 20000)], t1[rng.integers(0, t1.shape[0], 20000)], table(20000, 10 + rep)])
+        assert np.array_equal(engine.site_table_lookup(0, q), np.isin(q, t0).astype(np.uint8))
+        assert np.array_equal(engine.site_table_lookup(1, q), np.isin(q, t1).astype(np.uint8))
+        # the one-shot call uses its own scratch slot: the resident tables survive it
+        assert np.array_equal(engine.site_mask(t1, q), np.isin(q, t1).astype(np.uint8))
+    engine.site_table_load(0, t1)
+    q = np.concatenate([t0[:1000], t1[:1000]])
+    assert np.array_equal(engine.site_table_lookup(0, q), np.isin(q, t1).astype(np.uint8))
+    engine.site_table_load(2, np.zeros(0, np.uint64))
+    assert engine.site_table_lookup(2, q).sum() == 0
+    with pytest.raises(RuntimeError):
+        engine.site_table_lookup(3, q)
