@@ -137,16 +137,31 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.proc = gpu, [], None
+        self.t_rows = []          # arrival time of every row
+        self.t_begin = None       # rows that arrive before mark_begin() are not "under load"
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
+                self.t_rows.append(time.perf_counter())
         except Exception:
             pass
+
+    def wait_ready(self, timeout=8.0):
+        """nvidia-smi takes a variable time to print its first row: the timed region starts after it."""
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def n_under_load(self):
+        return sum(1 for t in self.t_rows if self.t_begin is not None and t >= self.t_begin)
 
     def stop(self):
         if self.proc:
@@ -154,7 +169,8 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows = [r for r, t in zip(self.rows, self.t_rows) if self.t_begin is None or t >= self.t_begin]
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
@@ -265,6 +281,8 @@ def run_ours(args, rank, world, local_rank):
     from longsom_b200.batch import ReadBatch, SiteCounts
     from longsom_b200.engine import CountParams, Engine
     from longsom_b200 import _lib
+    from longsom_b200.pipeline import bind_near_gpu
+    numa_node = bind_near_gpu(local_rank)   # before the batch and the pinned buffers are allocated (first touch)
     scale = args.scale
     wl = build_workload(scale, rank, world)
     batch, windows, info = wl["batch"], wl["windows"], wl["info"]
@@ -303,8 +321,9 @@ def run_ours(args, rank, world, local_rank):
         eng.compact()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    sampler.wait_ready()
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     ms_count, ms_total, ms_compact, launches = [], [], [], 0
     for _ in range(args.steps):
@@ -318,7 +337,15 @@ def run_ours(args, rank, world, local_rank):
         launches += 1
     barrier()
     dt = time.perf_counter() - t0
+    # a short timed region can end between two nvidia-smi rows: keep the same load running (untimed) until the sampler
+    # has at least three rows taken under it
+    extra = 0
+    while sampler.n_under_load() < 3 and extra < 400 and sampler.proc is not None:
+        eng.run(prm)
+        eng.compact()
+        extra += 1
     clocks = sampler.stop()
+    clocks["untimed_steps_added_for_sampling"] = extra
     dt = reduce_max(dt)
     ms_per_step = 1e3 * dt / args.steps
     value = total_units / (dt / args.steps)
@@ -567,7 +594,7 @@ def run_ours(args, rank, world, local_rank):
             "config": workload_config(info, scale, l2="inputs (%.2f GB per GPU) exceed the 126 MB L2; no flush needed"
                                       % (batch.nbytes() / 1e9)),
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "secondary": secondary, "c4": c4, "e2e_cli": e2e_cli,
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "numa_node": numa_node,
             "stats": {"n_segments": st["n_segments"], "n_tiles": st["n_tiles"], "n_sites": int(n_sites),
                       "n_events": st["n_events"], "ms_segments": st["ms_segments"], "ms_sort": st["ms_sort"],
                       "ms_count": k_ms, "ms_compact": c_ms, "ms_device_total": float(np.mean(ms_total)) + c_ms, "tile": tile,

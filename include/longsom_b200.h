@@ -231,6 +231,8 @@ int ls_site_table_lookup(ls_ctx *ctx, int table, const uint64_t *query, int64_t 
 
 /* ---- device-resident handles for benchmarking (inputs already in HBM) ----------------------- */
 int ls_device_synchronize(ls_ctx *ctx);
+/* PCI address ("0000:1b:00.0") of a CUDA device ordinal, for NUMA placement of the host staging buffers; no context */
+int ls_device_pci_bus_id(int device, char *buf, int len);
 /* flush L2 by writing a scratch buffer larger than the 126 MB L2 */
 int ls_flush_l2(ls_ctx *ctx);
 

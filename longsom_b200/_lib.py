@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "ls_abi_version", "ls_ctx_create", "ls_ctx_destroy", "ls_last_error", "ls_host_alloc", "ls_host_free",
     "ls_pileup_upload", "ls_pileup_run", "ls_pileup_compact", "ls_pileup_fetch", "ls_pileup_count", "ls_genotype_count",
     "ls_genotype_sparse_run", "ls_genotype_sparse_fetch",
-    "ls_betabinom_sf", "ls_site_mask", "ls_site_table_load", "ls_site_table_lookup", "ls_device_synchronize", "ls_flush_l2",
+    "ls_betabinom_sf", "ls_site_mask", "ls_site_table_load", "ls_site_table_lookup", "ls_device_synchronize", "ls_device_pci_bus_id", "ls_flush_l2",
 ]
 
 
@@ -109,6 +109,7 @@ def load():
     lib.ls_genotype_sparse_fetch.argtypes = [C.c_void_p, P(LsGenoTuples)]
     lib.ls_betabinom_sf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                                     C.c_int64, P(LsRunStats)]
+    lib.ls_device_pci_bus_id.argtypes = [C.c_int, C.c_char_p, C.c_int]
     lib.ls_site_table_load.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
     lib.ls_site_table_lookup.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.ls_site_mask.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,

@@ -11,7 +11,7 @@ import timeit
 
 from .. import bamio
 from ..engine import CountParams
-from ..pipeline import (count_sites, devices_from_env, load_bam_for_counting, prewarm, prune_and_sort_windows, read_ends,
+from ..pipeline import (bind_near_gpu, count_sites, devices_from_env, load_bam_for_counting, prewarm, prune_and_sort_windows, read_ends,
                         stream_count, write_counter_tsv)
 from ..windows import make_windows
 
@@ -55,6 +55,8 @@ def run(args):
         print("Not temp directory specified, using working directory as temp")
     if args.min_dp < 1:
         raise SystemExit("longsom_b200 BaseCellCounter: --min_dp must be >= 1")
+    if len(devices_from_env()) == 1:
+        bind_near_gpu(devices_from_env()[0])  # host threads and pinned staging buffers on the GPU's NUMA node
     prewarm(devices_from_env())  # CUDA contexts come up while the BAM is decoded
     fa = bamio.Fasta(args.ref)
     named = make_windows(fa.references, fa.lengths, args.chrom, args.bin, args.bed, args.bed_out)

@@ -71,6 +71,11 @@ extern "C" int ls_host_free(void *ptr) {
   return cudaFreeHost(ptr) == cudaSuccess ? LS_OK : LS_E_CUDA;
 }
 
+extern "C" int ls_device_pci_bus_id(int device, char *buf, int len) {
+  if (!buf || len < 16) return LS_E_ARG;
+  return cudaDeviceGetPCIBusId(buf, len, device) == cudaSuccess ? LS_OK : LS_E_CUDA;
+}
+
 extern "C" int ls_device_synchronize(ls_ctx *ctx) {
   if (!ctx) return LS_E_ARG;
   LS_CK(cudaSetDevice(ctx->device));

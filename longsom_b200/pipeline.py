@@ -40,6 +40,46 @@ def devices_from_env():
     return list(range(n)) if n > 0 else [0]
 
 
+def _parse_cpulist(text):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_near_gpu(device):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned staging buffers it
+    allocates afterwards (first touch) and the threads that fill them sit next to the GPU's PCIe root.  One process
+    per GPU (the bench's ranks, a CLI run on one device); a no-op when the platform does not say where the GPU is
+    (numa_node = -1, no sysfs) or LONGSOM_NUMA=0.  Returns the node, or None."""
+    if os.environ.get("LONGSOM_NUMA", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import ctypes
+        from . import _lib
+        buf = ctypes.create_string_buffer(64)   # CUDA ordinal -> PCI address (honours CUDA_VISIBLE_DEVICES)
+        if _lib.load().ls_device_pci_bus_id(int(device), buf, 64) != 0:
+            return None
+        bus = buf.value.decode().strip().lower()
+        if len(bus.split(":")[0]) == 8:   # an 8-digit PCI domain; sysfs uses 4 digits
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ---- CUDA context pre-warm ---------------------------------------------------------------------------------
 # Creating a CUDA context on a 180 GB device takes about a second or more; the CLIs start it in a background
 # thread before they decode the BAM (the native decoder releases the GIL), so the two overlap.
