@@ -114,7 +114,7 @@ struct ls_ctx {
   ls_count_params params = {};
   DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;
-  DBuf drop_keys, rend, wcount, part_slot, slot_done, acbuf;  // part_slot: PartDesc records
+  DBuf drop_keys, rend, wcount, part_slot, slot_done, slot_desc, acbuf;  // part_slot: PartDesc records
   DBuf offs_s, offs_m, offs_u, units, goffs, gdir, mrank, mlist;
   int64_t n_drop = 0;
   bool k1_attr_set = false;

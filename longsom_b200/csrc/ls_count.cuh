@@ -43,6 +43,7 @@ constexpr uint32_t K1_DUMP_OFF = 16u * K1_ROW_BYTES;
 constexpr uint32_t K1_CNT_SHIFT = 20;    // packed word: count << 20 | base-quality sum (<= 4095 * 255 < 2^20)
 
 static_assert(LS_TILE % 32 == 0 && LS_TILE == 512, "tile shape");
+static_assert(K1_CROWS + 8 >= LS_SITE_WORDS, "the epilogue transposes through the warp's columns of hist + dup rows");
 
 // unit.x: low 32 bits of q = index in qual[] of the base at column lo (deletion-like: of the one quality byte)
 // unit.y: q >> 32: bits 0-3 | window: 4-7 | lo: 8-12 | hi: 13-18 | strand: 19 | deletion-like: 20 | ind: 21-22 |
@@ -63,7 +64,8 @@ struct CountArgs {
   const struct PartDesc *parts;              // [grid] what every CTA of the count kernel works on (part_build_kernel)
   uint32_t *slot_done;
   const uint8_t *ref;
-  uint32_t *out;    // [n_slots][LS_SITE_WORDS][LS_TILE]
+  uint32_t *out;    // [n_slots]: single-part tiles [16 windows][32 records][LS_SITE_WORDS], passing sites packed at the
+                    // front of each window block; multi-part tiles [LS_SITE_WORDS][LS_TILE] (their parts merge with atomics)
   uint32_t *acbuf;  // [n_slots][LS_TILE], only when min_ac > 0
   uint32_t *mask;   // [n_slots][LS_TILE/32]
   uint32_t *npass;  // [n_slots]
@@ -859,16 +861,33 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(Coun
         a.mask[(size_t)slot * (LS_TILE / 32) + (s >> 5)] = bal;
         if (bal) atomicAdd(&sm.npass, (uint32_t)__popc(bal));
       }
-      if (pass && pass_no == 0) {
-        out[LS_SITE_DP * LS_TILE + s] = dp;
-        out[LS_SITE_NC * LS_TILE + s] = nc;
+      if (pass_no == 0) {
+        // Single-part tile: the warp's 32 columns leave as finished 26-word site records, the passing ones packed
+        // at the front of the window's 32-record block of the slot.  They are transposed through the warp's own
+        // columns of the 26 accumulator rows, which nobody reads any more (every lane has its column in registers).
+        __syncwarp();
+        uint32_t *stg = &sm.hist[0][0] + (s >> 5) * 33;
+        if (pass) {
+          // record e0/26 occupies words e0 .. e0+25 of the transposed block: at most two 32-word row segments
+          const uint32_t e0 = (uint32_t)__popc(bal & ((1u << lane) - 1u)) * LS_SITE_WORDS;
+          uint32_t *p0 = stg + (e0 >> 5) * K1_ROWW + (e0 & 31u);
+          const int split = 32 - (int)(e0 & 31u);  // fields from `split` on continue in the next row segment
+          auto put = [&](int fld, uint32_t v) { p0[fld + (fld >= split ? K1_ROWW - 32 : 0)] = v; };
+          put(LS_SITE_DP, dp);
+          put(LS_SITE_NC, nc);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          out[(LS_SITE_CC + k) * LS_TILE + s] = cc[k];
-          out[(LS_SITE_BCF + k) * LS_TILE + s] = f[k];
-          out[(LS_SITE_BCR + k) * LS_TILE + s] = r[k];
-          out[(LS_SITE_BQ + k) * LS_TILE + s] = bq[k];
+          for (int k = 0; k < 6; ++k) {
+            put(LS_SITE_CC + k, cc[k]);
+            put(LS_SITE_BCF + k, f[k]);
+            put(LS_SITE_BCR + k, r[k]);
+            put(LS_SITE_BQ + k, bq[k]);
+          }
         }
+        __syncwarp();
+        uint32_t *dst = out + (s >> 5) * (32 * LS_SITE_WORDS) + lane;
+        const int nw = __popc(bal) * LS_SITE_WORDS;
+        const uint32_t *src = stg + lane;
+        for (int i = lane; i < nw; i += 32, dst += 32, src += K1_ROWW) __stcs(dst, *src);
       }
     }
   }
@@ -878,6 +897,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) pileup_count_kernel(Coun
   __syncthreads();
   if (last_part && threadIdx.x == 0) a.npass[slot] = sm.npass;
 }
+
+// Where a slot's tile lies (compaction reads it instead of searching the window table again)
+struct alignas(16) SlotDesc {
+  int32_t tile_start, tid;
+  uint64_t ref_base;
+};
 
 // One CTA per slot: split the slot into parts, write their descriptors (parts[] pre-set to 0xff), zero the HBM slot of
 // multi-part tiles (their parts merge with atomics).
@@ -892,6 +917,8 @@ struct PartBuildArgs {
   const int64_t *wtile_base;
   const uint64_t *wref_off;
   PartDesc *parts;
+  struct SlotDesc *slot_desc;
+  const int32_t *wtid;
   uint32_t *slot_done;
   uint32_t *n_parts, *n_light;
   uint32_t max_parts;
@@ -928,6 +955,11 @@ __global__ void __launch_bounds__(128) part_build_kernel(PartBuildArgs a) {
     sh_start = ts;
     sh_end = (ts + LS_TILE) < a.wend[w] ? (ts + LS_TILE) : a.wend[w];
     sh_ref = a.wref_off[w] + (uint64_t)(ts - a.wstart[w]);
+    SlotDesc sd;
+    sd.tile_start = ts;
+    sd.tid = a.wtid[w];
+    sd.ref_base = sh_ref;
+    a.slot_desc[slot] = sd;
   }
   __syncthreads();
   for (uint32_t k = threadIdx.x; k < np; k += blockDim.x) {

@@ -427,7 +427,7 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
   LS_CK(cudaStreamSynchronize(st));
   const int64_t nh = (int64_t)h[1];
   S.n_events = nh;
-  int launches = 4;
+  int launches = 2;
   int64_t nt = 0;
   if (nh >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: more than 2^32 hits; split the site list");
   if (nh > 0) {
@@ -456,7 +456,7 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
     hit_reduce_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
                                                                     skip_p ? ctx->gs_skip.as<uint8_t>() : nullptr, t_site, t_cell,
                                                                     t_dp, t_alt, t_k);
-    launches += 6;
+    launches += 4;
     LS_CK(cudaGetLastError());
     LS_CK(cudaEventRecord(ctx->ev[1], st));
     // K2 on the device: p = betabinom.sf(Alt - eps, Dp, alpha, beta) for the pairs with a query

@@ -57,66 +57,80 @@ __global__ void __launch_bounds__(256) slot_fill_kernel(const uint64_t *__restri
 
 // ---- compaction of passing sites (fetch path) -----------------------------------------------
 struct CompactArgs {
-  const int64_t *slot_tile;
-  const uint32_t *slot_off;
+  const SlotDesc *slot_desc;
+  const uint32_t *slot_off, *slot_lo;
   const uint32_t *out, *mask;
-  int64_t n_windows;
-  const int32_t *wtid, *wstart;
-  const int64_t *wtile_base;
-  const uint64_t *wref_off;
   const uint8_t *ref;
   int32_t *o_tid, *o_pos;
   uint8_t *o_ref;
   uint32_t *o_counts;
 };
 
+static_assert(LS_SITE_WORDS % 2 == 0, "records are copied as 8-byte pairs");
+
 __global__ void __launch_bounds__(256) compact_sites_kernel(CompactArgs a) {
   __shared__ uint16_t list[LS_TILE];
   __shared__ uint32_t words[LS_TILE / 32];
   __shared__ uint32_t wpre[LS_TILE / 32 + 1];
   const int64_t slot = blockIdx.x;
-  if (threadIdx.x < LS_TILE / 32) words[threadIdx.x] = a.mask[(size_t)slot * (LS_TILE / 32) + threadIdx.x];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < LS_TILE / 32; ++i) {
-      wpre[i] = run;
-      run += __popc(words[i]);
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x < 32) {  // pass mask of the tile's 16 windows -> exclusive prefix of their counts
+    const uint32_t wd = lane < LS_TILE / 32 ? a.mask[(size_t)slot * (LS_TILE / 32) + lane] : 0u;
+    uint32_t inc = (uint32_t)__popc(wd);
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
     }
-    wpre[LS_TILE / 32] = run;
+    if (lane < LS_TILE / 32) {
+      words[lane] = wd;
+      wpre[lane] = inc - (uint32_t)__popc(wd);
+    }
+    if (lane == LS_TILE / 32 - 1) wpre[LS_TILE / 32] = inc;
   }
   __syncthreads();
   const uint32_t np = wpre[LS_TILE / 32];
   if (np == 0) return;
-  const int64_t tile = a.slot_tile[slot];
-  int64_t lo = 0, hi = a.n_windows;
-  while (hi - lo > 1) {
-    int64_t m = (lo + hi) >> 1;
-    if (a.wtile_base[m] <= tile)
-      lo = m;
-    else
-      hi = m;
-  }
-  const int64_t w = lo;
-  const int32_t tile_start = a.wstart[w] + (int32_t)(tile - a.wtile_base[w]) * LS_TILE;
-  const uint64_t ref_base = a.wref_off[w] + (uint64_t)(tile_start - a.wstart[w]);
+  const SlotDesc sd = a.slot_desc[slot];
   const uint32_t off = a.slot_off[slot];
+  const bool multi = a.slot_lo[slot + 1] - a.slot_lo[slot] > (uint32_t)K1_PART_SEGS;
   for (int s = threadIdx.x; s < LS_TILE; s += blockDim.x) {
     uint32_t wd = words[s >> 5];
     if ((wd >> (s & 31)) & 1u) {
       uint32_t rk = wpre[s >> 5] + __popc(wd & ((1u << (s & 31)) - 1u));
-      list[rk] = (uint16_t)s;
-      a.o_tid[off + rk] = a.wtid[w];
-      a.o_pos[off + rk] = tile_start + s;
-      a.o_ref[off + rk] = upper_ascii(a.ref[ref_base + s]);
+      if (multi) list[rk] = (uint16_t)s;
+      a.o_tid[off + rk] = sd.tid;
+      a.o_pos[off + rk] = sd.tile_start + s;
+      a.o_ref[off + rk] = upper_ascii(a.ref[sd.ref_base + s]);
     }
   }
-  __syncthreads();
   const uint32_t *src = a.out + (size_t)slot * LS_SITE_WORDS * LS_TILE;
   uint32_t *dst = a.o_counts + (size_t)off * LS_SITE_WORDS;
-  for (uint32_t e = threadIdx.x; e < np * LS_SITE_WORDS; e += blockDim.x) {
-    uint32_t rk = e / LS_SITE_WORDS, f = e - rk * LS_SITE_WORDS;
-    dst[e] = src[f * LS_TILE + list[rk]];
+  if (multi) {
+    // multi-part tile: field-major words of every column
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < np * LS_SITE_WORDS; e += blockDim.x) {
+      uint32_t rk = e / LS_SITE_WORDS, f = e - rk * LS_SITE_WORDS;
+      dst[e] = src[f * LS_TILE + list[rk]];
+    }
+  } else {
+    // single-part tile: finished records, the passing ones packed at the front of each window's 32-record block
+    // -> one contiguous run of words per window, copied by one warp
+    for (int g = threadIdx.x >> 5; g < LS_TILE / 32; g += blockDim.x >> 5) {
+      // 26 words = 13 eight-byte pairs per record; four loads in flight per lane
+      const uint32_t n2 = (wpre[g + 1] - wpre[g]) * (LS_SITE_WORDS / 2);
+      const uint2 *sg = reinterpret_cast<const uint2 *>(src + g * (32 * LS_SITE_WORDS));
+      uint2 *dg = reinterpret_cast<uint2 *>(dst + wpre[g] * LS_SITE_WORDS);
+      for (uint32_t i = lane; i < n2; i += 128u) {
+        uint2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i + 32u * k < n2) v[k] = __ldcs(sg + i + 32u * k);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (i + 32u * k < n2) dg[i + 32u * k] = v[k];
+      }
+    }
   }
 }
 
@@ -278,7 +292,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     ++launches;
     LS_CK(ls_scan_exclusive_u32(ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), nseg, d_nslot_total,
                                 ctx->scan_tmp, st));
-    launches += 3;
+    launches += 1;
     {
       const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
       long_run_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, cmask,
@@ -309,13 +323,13 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       LS_CK(ls_scan_exclusive_u32(os, os, nseg + 1, d_tot_s, ctx->scan_tmp, st));
       LS_CK(ls_scan_exclusive_u32(om, om, nseg + 1, d_tot_m, ctx->scan_tmp, st));
       LS_CK(ls_scan_exclusive_u32(mr, mr, nseg + 1, d_tot_ms, ctx->scan_tmp, st));
-      launches += 9;
+      launches += 3;
       mlist_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, cmask, unc, mr,
                                                                    ctx->mlist.as<uint32_t>());
       ++launches;
       if (with_u) {
         LS_CK(ls_scan_exclusive_u32(ou, ou, nseg + 1, d_tot_u, ctx->scan_tmp, st));
-        launches += 3;
+        launches += 1;
       }
       ea.keys = ctx->sorted_keys;
       ea.vals = ctx->sorted_vals;
@@ -340,7 +354,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       rungroups_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ea);
       ++launches;
       LS_CK(ls_scan_exclusive_u32(og, og, nseg + 1, d_tot_g, ctx->scan_tmp, st));
-      launches += 3;
+      launches += 1;
       LS_CK(cudaGetLastError());
     }
     if (replay) {
@@ -379,6 +393,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     const int64_t max_parts = n_slots + nseg / K1_PART_SEGS + 1;
     LS_CK(ctx->part_slot.ensure((size_t)max_parts * sizeof(PartDesc)));
     LS_CK(ctx->slot_done.ensure((size_t)n_slots * 4));
+    LS_CK(ctx->slot_desc.ensure((size_t)n_slots * sizeof(SlotDesc)));
     if (params->min_ac > 0) LS_CK(ctx->acbuf.ensure((size_t)n_slots * LS_TILE * 4));
     LS_CK(cudaMemsetAsync(ctx->part_slot.p, 0xff, (size_t)max_parts * sizeof(PartDesc), st));
     {
@@ -396,6 +411,8 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       pb.wtile_base = ctx->wtile_base.as<int64_t>();
       pb.wref_off = ctx->wref_off.as<uint64_t>();
       pb.parts = ctx->part_slot.as<PartDesc>();
+      pb.slot_desc = ctx->slot_desc.as<SlotDesc>();
+      pb.wtid = ctx->wtid.as<int32_t>();
       pb.slot_done = ctx->slot_done.as<uint32_t>();
       pb.n_parts = d_nparts;
       pb.n_light = d_nlight;
@@ -466,7 +483,7 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     // the number of passing sites goes to counter 2: counter 3 keeps the number of slots for the replay check
     LS_CK(ls_scan_exclusive_u32(ctx->slot_npass.as<uint32_t>(), ctx->slot_off.as<uint32_t>(), n_slots, d_nseg_total,
                                 ctx->scan_tmp, st));
-    launches += 3;
+    launches += 1;
     LS_CK(cudaEventRecord(ctx->ev[4], st));
     LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 128, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
@@ -517,15 +534,11 @@ extern "C" int ls_pileup_compact(ls_ctx *ctx, ls_run_stats *stats) {
     LS_CK(ctx->out_ref.ensure((size_t)ns));
     LS_CK(ctx->out_counts.ensure((size_t)ns * LS_SITE_WORDS * 4));
     CompactArgs a;
-    a.slot_tile = ctx->slot_tile.as<int64_t>();
+    a.slot_desc = ctx->slot_desc.as<SlotDesc>();
     a.slot_off = ctx->slot_off.as<uint32_t>();
+    a.slot_lo = ctx->slot_lo.as<uint32_t>();
     a.out = ctx->slot_out.as<uint32_t>();
     a.mask = ctx->slot_mask.as<uint32_t>();
-    a.n_windows = ctx->n_windows;
-    a.wtid = ctx->wtid.as<int32_t>();
-    a.wstart = ctx->wstart.as<int32_t>();
-    a.wtile_base = ctx->wtile_base.as<int64_t>();
-    a.wref_off = ctx->wref_off.as<uint64_t>();
     a.ref = ctx->ref.as<uint8_t>();
     a.o_tid = ctx->out_tid.as<int32_t>();
     a.o_pos = ctx->out_pos.as<int32_t>();

@@ -38,60 +38,84 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total,
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_partials(const uint32_t *__restrict__ in, int64_t n,
-                                                              uint32_t *__restrict__ partial) {
-  __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
-  int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK;
-  uint32_t s = 0;
-#pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    int64_t idx = base + (int64_t)i * SCAN_THREADS + threadIdx.x;
-    if (idx < n) s += in[idx];
-  }
-  uint32_t tot;
-  block_excl_scan<SCAN_THREADS>(s, &tot, sm);
-  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-}
+// Single-pass exclusive scan with decoupled look-back: every CTA takes the next chunk in ticket order (so that the
+// chunks before it are always running or done), publishes its chunk total, then walks back over its predecessors'
+// records until it meets one that already carries an inclusive prefix.  One read and one write of the array.
+// state[j]: bits 62-63 = 0 not ready, 1 = chunk total, 2 = inclusive prefix up to and including chunk j; bits 0-61 value.
+constexpr uint64_t SCAN_AGG = 1ull << 62, SCAN_PFX = 2ull << 62, SCAN_VAL = (1ull << 62) - 1ull;
 
-__global__ void __launch_bounds__(1024) scan_of_partials(uint32_t *__restrict__ partial, int64_t nb,
-                                                         uint64_t *__restrict__ total) {
-  __shared__ uint32_t sm[1024 / 32 + 1];
-  __shared__ uint64_t carry_s;
-  if (threadIdx.x == 0) carry_s = 0;
+__global__ void __launch_bounds__(SCAN_THREADS) scan_chained(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
+                                                             int64_t n, unsigned long long *__restrict__ state,
+                                                             unsigned int *__restrict__ ticket, uint64_t *__restrict__ total) {
+  __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
+  __shared__ uint32_t bid_s;
+  __shared__ unsigned long long pfx_s;
+  if (threadIdx.x == 0) bid_s = atomicAdd(ticket, 1u);
   __syncthreads();
-  for (int64_t base = 0; base < nb; base += 1024) {
-    int64_t idx = base + threadIdx.x;
-    uint32_t v = idx < nb ? partial[idx] : 0u;
-    uint32_t tot;
-    uint32_t ex = block_excl_scan<1024>(v, &tot, sm);
-    uint64_t carry = carry_s;
-    if (idx < nb) partial[idx] = (uint32_t)(carry + ex);
-    __syncthreads();
-    if (threadIdx.x == 0) carry_s = carry + tot;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0 && total) *total = carry_s;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                                                           int64_t n, const uint32_t *__restrict__ partial) {
-  __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
-  int64_t base = (int64_t)blockIdx.x * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
+  const uint32_t bid = bid_s;
+  const int64_t base = (int64_t)bid * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
   uint32_t s = 0;
+  if (base + SCAN_ITEMS <= n) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(in + base), b = *reinterpret_cast<const uint4 *>(in + base + 4);
+    v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+  } else {
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    int64_t idx = base + i;
-    v[i] = idx < n ? in[idx] : 0u;
-    s += v[i];
+    for (int i = 0; i < SCAN_ITEMS; ++i) v[i] = base + i < n ? in[base + i] : 0u;
   }
-  uint32_t tot;
-  uint32_t ex = block_excl_scan<SCAN_THREADS>(s, &tot, sm) + partial[blockIdx.x];
 #pragma unroll
-  for (int i = 0; i < SCAN_ITEMS; ++i) {
-    int64_t idx = base + i;
-    if (idx < n) out[idx] = ex;
-    ex += v[i];
+  for (int i = 0; i < SCAN_ITEMS; ++i) s += v[i];
+  uint32_t tot;
+  uint32_t ex = block_excl_scan<SCAN_THREADS>(s, &tot, sm);
+  if (threadIdx.x < 32) {
+    // the first warp looks back 32 chunk records at a time
+    const int lane = threadIdx.x;
+    unsigned long long pfx = 0;
+    if (bid > 0) {
+      if (lane == 0) atomicExch(state + bid, SCAN_AGG | (unsigned long long)tot);
+      for (int64_t j = (int64_t)bid - 1 - lane;; j -= 32) {
+        unsigned long long st = SCAN_PFX;  // before the first chunk: an inclusive prefix of zero
+        if (j >= 0) {
+          do {
+            st = *((volatile unsigned long long *)(state + j));
+          } while ((st >> 62) == 0ull);
+        }
+        const uint32_t pm = __ballot_sync(0xffffffffu, (st >> 62) == 2ull);
+        const int first = pm ? __ffs(pm) - 1 : 32;  // nearest record that carries a prefix
+        unsigned long long val = lane <= first ? (st & SCAN_VAL) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        pfx += val;
+        if (pm) break;
+      }
+    }
+    if (lane == 0) {
+      __threadfence();
+      atomicExch(state + bid, SCAN_PFX | (pfx + (unsigned long long)tot));
+      pfx_s = pfx;
+      if (total && (int64_t)(bid + 1) * SCAN_CHUNK >= n) *total = pfx + (unsigned long long)tot;
+    }
+  }
+  __syncthreads();
+  ex += (uint32_t)pfx_s;
+  if (base + SCAN_ITEMS <= n) {
+    uint4 a, b;
+    a.x = ex, ex += v[0];
+    a.y = ex, ex += v[1];
+    a.z = ex, ex += v[2];
+    a.w = ex, ex += v[3];
+    b.x = ex, ex += v[4];
+    b.y = ex, ex += v[5];
+    b.z = ex, ex += v[6];
+    b.w = ex;
+    *reinterpret_cast<uint4 *>(out + base) = a;
+    *reinterpret_cast<uint4 *>(out + base + 4) = b;
+  } else {
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+      if (base + i < n) out[base + i] = ex;
+      ex += v[i];
+    }
   }
 }
 
@@ -276,12 +300,15 @@ cudaError_t ls_scan_exclusive_u32(const uint32_t *d_in, uint32_t *d_out, int64_t
     if (d_total) return cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
     return cudaSuccess;
   }
+  if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) return cudaErrorMisalignedAddress;
   int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
-  cudaError_t e = tmp.ensure((size_t)nb * sizeof(uint32_t));
+  // chunk records + the ticket counter behind them, cleared before every scan
+  cudaError_t e = tmp.ensure((size_t)(nb + 1) * sizeof(uint64_t));
   if (e != cudaSuccess) return e;
-  scan_partials<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, n, tmp.as<uint32_t>());
-  scan_of_partials<<<1, 1024, 0, st>>>(tmp.as<uint32_t>(), nb, d_total);
-  scan_apply<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, tmp.as<uint32_t>());
+  e = cudaMemsetAsync(tmp.p, 0, (size_t)(nb + 1) * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return e;
+  scan_chained<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, tmp.as<unsigned long long>(),
+                                                      reinterpret_cast<unsigned int *>(tmp.as<unsigned long long>() + nb), d_total);
   return cudaGetLastError();
 }
 
