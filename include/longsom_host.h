@@ -44,6 +44,28 @@ const void *ls_bam_array(void *h, int which);
 int ls_write_counter_rows(const char *path, const char *chrom, const int32_t *pos, const uint8_t *ref,
                           const uint32_t *counts, int64_t n, int threads, int append);
 
+/* ---- streaming BAM decoder (bounded memory) ---------------------------------------------------------- */
+/* The drop-in BaseCellCounter's reader (replaces the per-window pysam pileup fetches of BaseCellCounter.py:190-191,
+ * 344-409): ls_bams_next() hands out the next ~target_bytes of inflated records (a record cut by the chunk end is
+ * carried over) while a background thread already inflates and indexes the chunk after it; ls_bams_fill() copies the
+ * current chunk into caller buffers (pinned staging memory) in the layout of ls_read_batch.  Barcode ids are stable
+ * for the whole file; ls_bams_n_barcodes() is the table size when the CURRENT chunk was indexed.
+ * ls_bams_next: number of records, 0 at end of file, -1 on error (ls_bams_error has the text). */
+void *ls_bams_open(const char *path, int threads);
+const char *ls_bams_error(void *h);
+void ls_bams_close(void *h);
+int32_t ls_bams_n_contigs(void *h);
+const char *ls_bams_contig_name(void *h, int i);
+int32_t ls_bams_contig_len(void *h, int i);
+int32_t ls_bams_n_barcodes(void *h);
+const char *ls_bams_barcode(void *h, int i);
+int64_t ls_bams_next(void *h, int64_t target_bytes, int64_t *n_cigar, int64_t *n_bases);
+int ls_bams_fill(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *mapq, int32_t *cb, int32_t *l_qseq,
+                 uint32_t *cigar_off, uint64_t *base_off, uint32_t *cigar, uint8_t *seq4, uint8_t *qual);
+/* The decoders' own raw-DEFLATE inflater (RFC 1951, whole buffers, exact output size; ls_inflate.h): 1 if `in`
+ * inflates to exactly out_len bytes, 0 otherwise (the readers then hand the member to zlib).  Exposed for tests. */
+int ls_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
+
 /* ---- SplitBamCellTypes --------------------------------------------------------------------------- */
 /* Routes every placed record of the coordinate-sorted BAM in_path to out_paths[type of its barcode]
  * (+ ".bai" each).  Barcode table: n_bc keys, key i = bc_blob[bc_off[i] .. bc_off[i+1]), type bc_type[i];

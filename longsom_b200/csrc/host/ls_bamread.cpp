@@ -18,6 +18,8 @@
 #include <time.h>
 #include <zlib.h>
 
+#include "ls_inflate.h"
+
 #include <algorithm>
 #include <atomic>
 #include <memory>
@@ -67,6 +69,10 @@ static bool inflate_block(z_stream &zs, const uint8_t *src, uint32_t csize, uint
   if (12u + xlen + 8u > csize) return false;  // the extra field must leave room for the CRC32 / ISIZE trailer
   const uint8_t *def = src + 12 + xlen;
   uint32_t dlen = csize - 12 - xlen - 8;
+  {
+    static thread_local lsinf::Tables tabs;  // own decoder first; zlib judges whatever it does not accept
+    if (!getenv("LS_ZLIB_INFLATE") && lsinf::inflate_raw(def, dlen, dst, usize, tabs)) return true;
+  }
   if (inflateReset(&zs) != Z_OK) return false;
   zs.next_in = const_cast<Bytef *>(def);
   zs.avail_in = dlen;

@@ -5,7 +5,10 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <zlib.h>
+
+#include "ls_inflate.h"
 
 #include <atomic>
 #include <string>
@@ -99,10 +102,15 @@ static inline bool deflate_stream(const uint8_t *data, size_t n, int threads, in
 }
 
 static inline bool inflate_member(const uint8_t *src, uint32_t csize, uint8_t *dst, uint32_t usize) {
-  if (csize < 18) return false;
+  if (csize < 26) return false;
   const uint32_t xlen = rd16(src + 10);
+  if (12u + xlen + 8u > csize) return false;
   const uint8_t *def = src + 12 + xlen;
   const uint32_t dlen = csize - 12 - xlen - 8;
+  {
+    static thread_local lsinf::Tables tabs;  // own decoder first; zlib judges whatever it does not accept
+    if (!getenv("LS_ZLIB_INFLATE") && lsinf::inflate_raw(def, dlen, dst, usize, tabs)) return true;
+  }
   z_stream zs;
   memset(&zs, 0, sizeof zs);
   if (inflateInit2(&zs, -15) != Z_OK) return false;

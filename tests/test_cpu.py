@@ -123,3 +123,53 @@ def test_decoded_arrays_outlive_the_bam_object(built, tmp_path):
         assert not b.qual[bo[i] + lq[i]:bo[i + 1]].any()          # padding to 16 bases is zeroed
     b.qual[0] = 7   # writable view
     assert b.qual[0] == 7
+
+
+def test_own_inflater_matches_zlib(built):
+    """ls_inflate.h (the BGZF readers' DEFLATE decoder) against zlib on streams of every block type: random bytes
+    (stored blocks), quality-like and base-like text (dynamic codes, short and long matches, period < 8), fixed-code
+    streams, several blocks per stream; a wrong expected size, a truncated stream and garbage are refused."""
+    import ctypes as C
+    import zlib
+    from longsom_b200 import bamio
+    lib = bamio._load_host()
+    lib.ls_inflate_raw.restype = C.c_int
+    lib.ls_inflate_raw.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
+    rng = np.random.default_rng(3)
+
+    def inflate(comp, n):
+        out = np.full(n + 16, 0xEE, np.uint8)
+        ok = lib.ls_inflate_raw(comp, len(comp), out.ctypes.data, n)
+        assert (out[n:] == 0xEE).all(), "wrote past the end of the output"
+        return ok, out[:n].tobytes()
+    n_streams = 0
+    for it in range(400):
+        n = int(rng.integers(0, 65536)) if it % 25 else int(rng.integers(0, 50))
+        mode = it % 6
+        if mode == 0:
+            d = rng.integers(0, 256, n, dtype=np.uint8)
+        elif mode == 1:
+            d = rng.integers(33, 74, n).astype(np.uint8)
+        elif mode == 2:
+            d = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, n)]
+        elif mode == 3:
+            d = np.where(rng.random(n) < 0.93, 65, rng.integers(0, 256, n)).astype(np.uint8)
+        elif mode == 4:
+            d = np.tile(rng.integers(0, 256, int(rng.integers(1, 12)), dtype=np.uint8), n + 1)[:n]
+        else:
+            d = (np.arange(n) * 7 % 251).astype(np.uint8)
+        data = d.tobytes()
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED][(it // 6) % 4]
+        co = zlib.compressobj(it % 10, zlib.DEFLATED, -15, 8, strategy)
+        comp = co.compress(data[:n // 2]) + (co.flush(zlib.Z_FULL_FLUSH) if it % 3 == 0 else b"") + co.compress(data[n // 2:]) + co.flush()
+        ok, got = inflate(comp, n)
+        assert ok == 1 and got == data, (it, n, mode)
+        n_streams += 1
+        if n > 4:
+            assert inflate(comp, n - 1)[0] == 0
+            assert inflate(comp, n + 1)[0] == 0
+            assert inflate(comp[:-3], n)[0] == 0
+    for it in range(2000):
+        junk = rng.integers(0, 256, int(rng.integers(0, 200)), dtype=np.uint8).tobytes()
+        inflate(junk, int(rng.integers(0, 70000)))   # must not crash or write out of bounds
+    assert n_streams == 400
