@@ -85,6 +85,9 @@ def main(argv=None):
     run(args)
     stop = timeit.default_timer()
     print("Computation time: " + str(round(stop - start)) + ' seconds')
+    if os.environ.get("LS_STREAM_TIMING"):
+        from ..pipeline import _peak_rss_gb
+        print("[counter] peak RSS %.2f GB" % _peak_rss_gb(), file=sys.stderr)
 
 
 if __name__ == '__main__':

@@ -289,6 +289,20 @@ class PinnedSlot:
         self.arrays, self.ptrs, self.caps = {}, {}, {}
 
 
+def _peak_rss_gb():
+    """High-water mark of THIS process image (VmHWM).  ru_maxrss is no use here: it survives exec, so a child started
+    by a large parent reports the parent's resident set."""
+    try:
+        with open("/proc/self/status") as f:
+            for line in f:
+                if line.startswith("VmHWM:"):
+                    return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    import resource
+    return resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6
+
+
 def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, ID, devices=None, chunk_bytes=None,
                  stats_out=None):
     """BaseCellCounter over a BAM of any size with bounded host memory (reference: the per-window pool of
@@ -491,7 +505,21 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
         if os.environ.get("LS_STREAM_TIMING"):
             import resource
             print("[stream_count] busy seconds: " + ", ".join("%s %.2f" % kv for kv in sorted(busy.items())) +
-                  "; peak RSS of this process %.2f GB" % (resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6), file=sys.stderr)
+                  "; peak RSS of this process %.2f GB" % _peak_rss_gb(), file=sys.stderr)
+            if os.environ.get("LS_STREAM_TIMING") == "2":   # what the resident set is made of (largest mappings)
+                try:
+                    maps, cur = [], None
+                    with open("/proc/self/smaps") as f:
+                        for line in f:
+                            if "-" in line.split(" ", 1)[0] and ":" not in line.split(" ", 1)[0]:
+                                cur = line.split()
+                            elif line.startswith("Rss:") and cur is not None:
+                                maps.append((int(line.split()[1]), cur[5] if len(cur) > 5 else "[anon]", cur[0]))
+                    maps.sort(reverse=True)
+                    print("[stream_count] largest resident mappings (MB): " +
+                          "; ".join("%d %s" % (kb // 1024, name) for kb, name, _ in maps[:10]), file=sys.stderr)
+                except OSError:
+                    pass
         return n_sites
     finally:
         for path in parts.values():

@@ -35,11 +35,12 @@ for mode, env in (("stream", {}), ("whole", {"LONGSOM_STREAM": "0"})):  # stream
                            env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         dt = time.time() - t0
         assert r.returncode == 0, r.stderr[-2000:]
+        rss_gb = None
         for l in r.stderr.splitlines():
             if l.startswith("[stream_count]"):
                 print("   ", l, flush=True)
-        # ru_maxrss of the children is a running maximum: meaningful for the first (largest so far) run of each mode
-        rss_gb = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss / 1e6
+            if l.startswith("[counter] peak RSS"):   # VmHWM of the child (ru_maxrss would carry this parent's RSS over exec)
+                rss_gb = float(l.split()[3])
         best = dt if best is None or dt < best else best
     res[mode] = dict(seconds=best, bases_per_s=aligned / best, peak_rss_gb=rss_gb)
     print("%-6s %.2f s  %.3g aligned bases/s disk to disk, peak RSS %.2f GB" % (mode, best, aligned / best, rss_gb or -1), flush=True)
