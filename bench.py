@@ -397,7 +397,7 @@ def run_ours(args, rank, world, local_rank):
            "d2h_bytes_per_step": int(reduce_sum(float(d2h))), "steps": e2e_steps, "ms_per_step": single_ms,
            "api": "ls_pileup_count (C-ABI, pinned host buffers)"}
     # Pipelined variant (what the CLI-level pipeline offers for large inputs): the same batch cut into window shards,
-    # ls_pileup_count() per shard on `lanes` CUDA contexts of this GPU, so uploads, kernels and result copies of
+    # ls_pileup_count() per shard on `lanes` engine handles (ls_ctx: own stream and buffers, same CUDA context), so uploads, kernels and result copies of
     # different shards overlap.  Every step still moves every input byte H2D and every result byte D2H.
     if args.e2e_shards > 1:
         from longsom_b200.pipeline import count_shards_pipelined, window_shards
@@ -427,11 +427,36 @@ def run_ours(args, rank, world, local_rank):
         e2e = {"value": total_units / (dtp / e2e_steps), "unit": UNIT, "h2d_bytes_per_step": int(reduce_sum(float(h2d_p))),
                "d2h_bytes_per_step": int(reduce_sum(float(d2h))), "steps": e2e_steps, "ms_per_step": 1e3 * dtp / e2e_steps,
                "api": "longsom_b200.pipeline.count_shards_pipelined: ls_pileup_count (C-ABI, pinned host buffers) per "
-                      "window shard, %d shards on %d CUDA contexts of the GPU" % (len(shards), len(lanes)),
+                      "window shard, %d shards on %d engine handles (streams of the device's CUDA context)" % (len(shards), len(lanes)),
                "single_call_ms_per_step": single_ms, "single_call_value": total_units / (single_ms * 1e-3)}
         for l in lanes:
             l.close()
         del shards, outs
+
+    # ---- what the box's PCIe / host memory can do at this N: every rank copies 1 GiB of pinned memory to its GPU at
+    # the same time, three times (the ceiling the end-to-end number above is to be read against)
+    h2d_ceiling = None
+    try:
+        hbuf = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+        dbuf = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+        dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        dt_c = reduce_max(time.perf_counter() - t0)
+        h2d_ceiling = {"aggregate_GBps": world * 3 * (1 << 30) / dt_c / 1e9, "per_gpu_GBps": 3 * (1 << 30) / dt_c / 1e9,
+                       "how": "1 GiB pinned -> device, all ranks at once, 3 copies, max over ranks"}
+        del hbuf, dbuf
+    except Exception as ex:   # the number is an annotation, never a reason to fail the bench
+        h2d_ceiling = {"error": repr(ex)}
+    if isinstance(e2e, dict):
+        e2e["h2d_ceiling"] = h2d_ceiling
+        if h2d_ceiling and "aggregate_GBps" in h2d_ceiling and e2e.get("ms_per_step"):
+            e2e["h2d_GBps_achieved"] = e2e["h2d_bytes_per_step"] / (e2e["ms_per_step"] * 1e-3) / 1e9
 
     # ---- second half of BASELINE.json's metric: candidate sites genotyped / s (K1' + K2), every N -------------------
     # 200 000 candidate sites over the whole batch (each rank takes the ones inside its window shard), all cells of
@@ -616,7 +641,7 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("LS_BENCH_SCALE", "1.0")),
                     help="fraction of the C2 workload (1.0 = 5M reads); only for local debugging")
     ap.add_argument("--e2e-shards", type=int, default=8, help="window shards of the pipelined end-to-end leg (1 = off)")
-    ap.add_argument("--e2e-lanes", type=int, default=2, help="CUDA contexts the pipelined end-to-end leg alternates on")
+    ap.add_argument("--e2e-lanes", type=int, default=2, help="engine handles (streams) the pipelined end-to-end leg alternates on")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the genotyping metric and the C4 line")
     ap.add_argument("--cli-scale", type=float, default=0.2,

@@ -111,6 +111,7 @@ struct ls_ctx {
   bool cache_valid = false;
   ls_count_params cache_params = {};
   uint64_t cache_seg[3] = {0, 0, 0}, cache_tot[16] = {0};
+  int64_t cache_n_sites = 0;
   ls_count_params params = {};
   DBuf segs, pieces, keys_a, keys_b, vals_a, vals_b, rs_hist, scan_tmp, counters;
   DBuf tile_flag, tile_rank, slot_tile, slot_lo, slot_out, slot_mask, slot_npass, slot_off;

@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(256) compact_sites_kernel(CompactArgs a) {
   }
 }
 
+static int enqueue_compact(ls_ctx *ctx, int64_t ns);
+
 // ---- host-side orchestration ------------------------------------------------------------------
 static SegArgs make_seg_args(ls_ctx *ctx, const ls_count_params &p, bool emit_uncounted) {
   SegArgs a;
@@ -485,11 +487,21 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
                                 ctx->scan_tmp, st));
     launches += 1;
     LS_CK(cudaEventRecord(ctx->ev[4], st));
+    // a replayed run knows how many sites will pass: the compaction goes into the same submission, one synchronisation
+    // per step instead of two
+    bool pre_compacted = false;
+    if (replay && ctx->cache_n_sites > 0) {
+      ctx->n_slots = n_slots;
+      const int rc = enqueue_compact(ctx, ctx->cache_n_sites);
+      if (rc != LS_OK) return rc;
+      pre_compacted = true;
+    }
     LS_CK(cudaMemcpyAsync(h_tot, ctx->counters.p, 128, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
     if (replay) {
       // what the device actually produced against what the enqueued sizes assumed
       bool same = h_tot[0] == h_mid[0] && h_tot[3] == h_mid[3] && (h_tot[5] & 0xffffffffull) == (h_mid[5] & 0xffffffffull);
+      if (pre_compacted) same = same && (int64_t)h_tot[2] == ctx->cache_n_sites;
       for (int k = 8; k < 16; ++k) same = same && h_tot[k] == (k < 11 ? ctx->cache_seg[k - 8] : h_mid[k]);
       if (!same) {
         ctx->cache_valid = false;
@@ -500,8 +512,13 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       ctx->cache_params = *params;
       memcpy(ctx->cache_seg, h_seg, sizeof h_seg);
       memcpy(ctx->cache_tot, h_mid, sizeof h_mid);
+      ctx->cache_n_sites = (int64_t)h_tot[2];
     }
     ctx->n_sites = (int64_t)h_tot[2];
+    if (pre_compacted) {
+      ctx->compacted = true;
+      LS_CK(cudaEventElapsedTime(&S.ms_compact, ctx->ev[5], ctx->ev[6]));  // (the caller counts this launch)
+    }
     S.n_events = (int64_t)h_tot[1];
     LS_CK(cudaEventElapsedTime(&S.ms_segments, ctx->ev[0], ctx->ev[1]));
     LS_CK(cudaEventElapsedTime(&S.ms_sort, ctx->ev[1], ctx->ev[2]));
@@ -522,33 +539,38 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
 
 // Compaction of the passing sites into the reference's output order (window, position): device only.  The site table
 // of a run is tile-major with a pass bitmask; this is the step that turns it into the unit the reference emits.
+static int enqueue_compact(ls_ctx *ctx, int64_t ns) {
+  cudaStream_t st = ctx->stream;
+  LS_CK(ctx->out_tid.ensure((size_t)ns * 4));
+  LS_CK(ctx->out_pos.ensure((size_t)ns * 4));
+  LS_CK(ctx->out_ref.ensure((size_t)ns));
+  LS_CK(ctx->out_counts.ensure((size_t)ns * LS_SITE_WORDS * 4));
+  CompactArgs a;
+  a.slot_desc = ctx->slot_desc.as<SlotDesc>();
+  a.slot_off = ctx->slot_off.as<uint32_t>();
+  a.slot_lo = ctx->slot_lo.as<uint32_t>();
+  a.out = ctx->slot_out.as<uint32_t>();
+  a.mask = ctx->slot_mask.as<uint32_t>();
+  a.ref = ctx->ref.as<uint8_t>();
+  a.o_tid = ctx->out_tid.as<int32_t>();
+  a.o_pos = ctx->out_pos.as<int32_t>();
+  a.o_ref = ctx->out_ref.as<uint8_t>();
+  a.o_counts = ctx->out_counts.as<uint32_t>();
+  LS_CK(cudaEventRecord(ctx->ev[5], st));
+  compact_sites_kernel<<<(unsigned)ctx->n_slots, 256, 0, st>>>(a);
+  LS_CK(cudaGetLastError());
+  LS_CK(cudaEventRecord(ctx->ev[6], st));
+  return LS_OK;
+}
+
 extern "C" int ls_pileup_compact(ls_ctx *ctx, ls_run_stats *stats) {
   if (!ctx) return LS_E_ARG;
   if (!ctx->have_run) LS_FAIL(LS_E_STATE, "ls_pileup_compact: ls_pileup_run has not completed");
-  if (!ctx->compacted && ctx->n_sites > 0) {
+  if (!ctx->compacted && ctx->n_sites > 0) {  // (a replayed run has already done it: see ls_pileup_run)
     LS_CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const int64_t ns = ctx->n_sites;
-    LS_CK(ctx->out_tid.ensure((size_t)ns * 4));
-    LS_CK(ctx->out_pos.ensure((size_t)ns * 4));
-    LS_CK(ctx->out_ref.ensure((size_t)ns));
-    LS_CK(ctx->out_counts.ensure((size_t)ns * LS_SITE_WORDS * 4));
-    CompactArgs a;
-    a.slot_desc = ctx->slot_desc.as<SlotDesc>();
-    a.slot_off = ctx->slot_off.as<uint32_t>();
-    a.slot_lo = ctx->slot_lo.as<uint32_t>();
-    a.out = ctx->slot_out.as<uint32_t>();
-    a.mask = ctx->slot_mask.as<uint32_t>();
-    a.ref = ctx->ref.as<uint8_t>();
-    a.o_tid = ctx->out_tid.as<int32_t>();
-    a.o_pos = ctx->out_pos.as<int32_t>();
-    a.o_ref = ctx->out_ref.as<uint8_t>();
-    a.o_counts = ctx->out_counts.as<uint32_t>();
-    LS_CK(cudaEventRecord(ctx->ev[5], st));
-    compact_sites_kernel<<<(unsigned)ctx->n_slots, 256, 0, st>>>(a);
-    LS_CK(cudaGetLastError());
-    LS_CK(cudaEventRecord(ctx->ev[6], st));
-    LS_CK(cudaStreamSynchronize(st));
+    const int rc = enqueue_compact(ctx, ctx->n_sites);
+    if (rc != LS_OK) return rc;
+    LS_CK(cudaStreamSynchronize(ctx->stream));
     LS_CK(cudaEventElapsedTime(&ctx->stats.ms_compact, ctx->ev[5], ctx->ev[6]));
   }
   ctx->compacted = true;
