@@ -228,6 +228,15 @@ int ls_depth_cap_host(ls_ctx *ctx, int min_mq, int max_depth, const std::vector<
 int ls_tile_size(void);
 
 // ---- utilities implemented in ls_util.cu --------------------------------------------------
+// several independent exclusive scans in one launch (ls_util.cu)
+constexpr int LS_SCAN_MAX_JOBS = 6;
+struct LsScanJob {
+  const uint32_t *in;
+  uint32_t *out;
+  int64_t n;
+  uint64_t *total;  // may be null
+};
+cudaError_t ls_scan_exclusive_u32_multi(const LsScanJob *jobs, int n_jobs, DBuf &tmp, cudaStream_t st);
 cudaError_t ls_scan_exclusive_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total,
                                   DBuf &tmp, cudaStream_t st);
 cudaError_t ls_radix_sort_pairs(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b,

@@ -394,11 +394,15 @@ __device__ __forceinline__ int segment_class(const uint64_t *__restrict__ keys, 
   return 0;
 }
 
+// One pass over the sorted keys: stream class and unit count of every segment (inputs of the S / M / U offset scans and
+// of the run-member ranks), the first-segment-of-its-tile flags (input of the slot table scan), and the check for a
+// same-cell run too long for the packed counters.
 __global__ void __launch_bounds__(256) classify_kernel(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                        const Segment *__restrict__ segs, int64_t n, uint64_t cmask,
-                                                       uint64_t unc, uint32_t *__restrict__ nu_s,
+                                                       uint64_t unc, int cell_bits, uint32_t *__restrict__ nu_s,
                                                        uint32_t *__restrict__ nu_m, uint32_t *__restrict__ nu_u,
-                                                       uint32_t *__restrict__ is_m) {
+                                                       uint32_t *__restrict__ is_m, uint32_t *__restrict__ tile_flag,
+                                                       uint32_t *__restrict__ long_run) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   if (i == n) {  // the arrays have n + 1 entries: after the exclusive scans entry n holds the stream size
@@ -408,12 +412,16 @@ __global__ void __launch_bounds__(256) classify_kernel(const uint64_t *__restric
     if (nu_u) nu_u[n] = 0u;
     return;
   }
-  const int cls = segment_class(keys, i, n, cmask, unc);
+  const uint64_t k = keys[i];
+  const uint64_t kp = i > 0 ? keys[i - 1] : ~k, kn = i + 1 < n ? keys[i + 1] : ~k;
+  const int cls = (k & cmask) == unc ? 2 : ((kp == k || kn == k) ? 1 : 0);
   const uint32_t nu = segs[vals[i]].np_nu >> 16;
   nu_s[i] = cls == 0 ? nu : 0u;
   nu_m[i] = cls == 1 ? nu : 0u;
   is_m[i] = cls == 1 ? 1u : 0u;
   if (nu_u) nu_u[i] = cls == 2 ? nu : 0u;
+  tile_flag[i] = (i == 0 || (kp >> cell_bits) != (k >> cell_bits)) ? 1u : 0u;
+  if (cls == 1 && i >= K1_MAX_RUN_PACKED && keys[i - K1_MAX_RUN_PACKED] == k) *long_run = 1u;
 }
 
 // mlist[rank of i among the run members] = i
@@ -992,13 +1000,4 @@ __global__ void __launch_bounds__(128) part_build_kernel(PartBuildArgs a) {
     if (a.acbuf)
       for (int i = threadIdx.x; i < LS_TILE; i += blockDim.x) a.acbuf[(size_t)slot * LS_TILE + i] = 0u;
   }
-}
-
-// any same-(tile, cell) run longer than K1_MAX_RUN_PACKED segments? (then the 12-bit packed counters could overflow)
-__global__ void __launch_bounds__(256) long_run_kernel(const uint64_t *__restrict__ keys, int64_t n, uint64_t cmask,
-                                                       uint64_t unc, uint32_t *__restrict__ flag) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < K1_MAX_RUN_PACKED || i >= n) return;
-  const uint64_t k = keys[i];
-  if ((k & cmask) != unc && keys[i - K1_MAX_RUN_PACKED] == k) *flag = 1u;
 }

@@ -31,14 +31,6 @@
 #include "ls_segments.cuh"
 
 // tile boundaries in the sorted key array
-__global__ void __launch_bounds__(256) tile_flag_kernel(const uint64_t *__restrict__ keys, int64_t n, int cell_bits,
-                                                        uint32_t *__restrict__ flag) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint64_t t = keys[i] >> cell_bits;
-  flag[i] = (i == 0 || (keys[i - 1] >> cell_bits) != t) ? 1u : 0u;
-}
-
 __global__ void __launch_bounds__(256) slot_fill_kernel(const uint64_t *__restrict__ keys, int64_t n, int cell_bits,
                                                         const uint32_t *__restrict__ flag,
                                                         const uint32_t *__restrict__ rank, int64_t n_slots,
@@ -289,18 +281,6 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
     // non-empty tiles -> slots
     LS_CK(ctx->tile_flag.ensure((size_t)nseg * 4));
     LS_CK(ctx->tile_rank.ensure((size_t)nseg * 4));
-    tile_flag_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, ctx->cell_bits,
-                                                                     ctx->tile_flag.as<uint32_t>());
-    ++launches;
-    LS_CK(ls_scan_exclusive_u32(ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), nseg, d_nslot_total,
-                                ctx->scan_tmp, st));
-    launches += 1;
-    {
-      const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
-      long_run_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, cmask,
-                                                                      (uint64_t)(uint32_t)(ctx->max_cell + 1), d_longrun);
-      ++launches;
-    }
     const uint64_t cmask = (1ull << ctx->cell_bits) - 1ull;
     const uint64_t unc = (uint64_t)(uint32_t)(ctx->max_cell + 1);
     const bool with_u = params->min_ac > 0;
@@ -319,20 +299,25 @@ extern "C" int ls_pileup_run(ls_ctx *ctx, const ls_count_params *params, int64_t
       og = ctx->goffs.as<uint32_t>();
       ou = with_u ? ctx->offs_u.as<uint32_t>() : nullptr;
       uint32_t *mr = ctx->mrank.as<uint32_t>();
-      classify_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, ctx->sorted_vals,
-                                                                          ctx->segs.as<Segment>(), nseg, cmask, unc, os, om, ou, mr);
+      classify_kernel<<<(unsigned)((nseg + 1 + 255) / 256), 256, 0, st>>>(
+          ctx->sorted_keys, ctx->sorted_vals, ctx->segs.as<Segment>(), nseg, cmask, unc, ctx->cell_bits, os, om, ou, mr,
+          ctx->tile_flag.as<uint32_t>(), d_longrun);
       ++launches;
-      LS_CK(ls_scan_exclusive_u32(os, os, nseg + 1, d_tot_s, ctx->scan_tmp, st));
-      LS_CK(ls_scan_exclusive_u32(om, om, nseg + 1, d_tot_m, ctx->scan_tmp, st));
-      LS_CK(ls_scan_exclusive_u32(mr, mr, nseg + 1, d_tot_ms, ctx->scan_tmp, st));
-      launches += 3;
+      {
+        // slot ranks, S / M (/ U) stream offsets and run-member ranks: independent scans, one launch
+        LsScanJob jobs[5];
+        int nj = 0;
+        jobs[nj++] = LsScanJob{ctx->tile_flag.as<uint32_t>(), ctx->tile_rank.as<uint32_t>(), nseg, d_nslot_total};
+        jobs[nj++] = LsScanJob{os, os, nseg + 1, d_tot_s};
+        jobs[nj++] = LsScanJob{om, om, nseg + 1, d_tot_m};
+        jobs[nj++] = LsScanJob{mr, mr, nseg + 1, d_tot_ms};
+        if (with_u) jobs[nj++] = LsScanJob{ou, ou, nseg + 1, d_tot_u};
+        LS_CK(ls_scan_exclusive_u32_multi(jobs, nj, ctx->scan_tmp, st));
+        ++launches;
+      }
       mlist_kernel<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(ctx->sorted_keys, nseg, cmask, unc, mr,
                                                                    ctx->mlist.as<uint32_t>());
       ++launches;
-      if (with_u) {
-        LS_CK(ls_scan_exclusive_u32(ou, ou, nseg + 1, d_tot_u, ctx->scan_tmp, st));
-        launches += 1;
-      }
       ea.keys = ctx->sorted_keys;
       ea.vals = ctx->sorted_vals;
       ea.segs = ctx->segs.as<Segment>();

@@ -44,15 +44,28 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total,
 // state[j]: bits 62-63 = 0 not ready, 1 = chunk total, 2 = inclusive prefix up to and including chunk j; bits 0-61 value.
 constexpr uint64_t SCAN_AGG = 1ull << 62, SCAN_PFX = 2ull << 62, SCAN_VAL = (1ull << 62) - 1ull;
 
-__global__ void __launch_bounds__(SCAN_THREADS) scan_chained(const uint32_t *__restrict__ in, uint32_t *__restrict__ out,
-                                                             int64_t n, unsigned long long *__restrict__ state,
-                                                             unsigned int *__restrict__ ticket, uint64_t *__restrict__ total) {
+struct ScanJobs {
+  LsScanJob j[LS_SCAN_MAX_JOBS];
+  unsigned long long *state;  // [jobs][nb_max] chunk records
+  unsigned int *ticket;       // [jobs]
+  int64_t nb_max;
+};
+
+// blockIdx.y = the array (several independent scans share one launch)
+__global__ void __launch_bounds__(SCAN_THREADS) scan_chained(ScanJobs jobs) {
   __shared__ uint32_t sm[SCAN_THREADS / 32 + 1];
   __shared__ uint32_t bid_s;
   __shared__ unsigned long long pfx_s;
-  if (threadIdx.x == 0) bid_s = atomicAdd(ticket, 1u);
+  const LsScanJob job = jobs.j[blockIdx.y];
+  const uint32_t *__restrict__ in = job.in;
+  uint32_t *__restrict__ out = job.out;
+  const int64_t n = job.n;
+  uint64_t *__restrict__ total = job.total;
+  unsigned long long *__restrict__ state = jobs.state + (size_t)blockIdx.y * jobs.nb_max;
+  if (threadIdx.x == 0) bid_s = atomicAdd(jobs.ticket + blockIdx.y, 1u);
   __syncthreads();
   const uint32_t bid = bid_s;
+  if ((int64_t)bid * SCAN_CHUNK >= n) return;  // the launch covers the longest array of the batch
   const int64_t base = (int64_t)bid * SCAN_CHUNK + (int64_t)threadIdx.x * SCAN_ITEMS;
   uint32_t v[SCAN_ITEMS];
   uint32_t s = 0;
@@ -294,22 +307,46 @@ cudaError_t radix_sort_impl(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a
 
 }  // namespace
 
+cudaError_t ls_scan_exclusive_u32_multi(const LsScanJob *jobs, int n_jobs, DBuf &tmp, cudaStream_t st) {
+  if (n_jobs < 1 || n_jobs > LS_SCAN_MAX_JOBS) return cudaErrorInvalidValue;
+  ScanJobs a;
+  int64_t nb_max = 0;
+  int live = 0;
+  for (int k = 0; k < n_jobs; ++k) {
+    if (jobs[k].n <= 0) {
+      if (jobs[k].total) {
+        cudaError_t e = cudaMemsetAsync(jobs[k].total, 0, sizeof(uint64_t), st);
+        if (e != cudaSuccess) return e;
+      }
+      continue;
+    }
+    if ((reinterpret_cast<uintptr_t>(jobs[k].in) | reinterpret_cast<uintptr_t>(jobs[k].out)) & 15u) return cudaErrorMisalignedAddress;
+    a.j[live++] = jobs[k];
+    const int64_t nb = (jobs[k].n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    nb_max = nb > nb_max ? nb : nb_max;
+  }
+  if (!live) return cudaSuccess;
+  // chunk records of every array + the ticket counters behind them, cleared before every launch
+  const size_t words = (size_t)live * (size_t)nb_max + LS_SCAN_MAX_JOBS;
+  cudaError_t e = tmp.ensure(words * sizeof(uint64_t));
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(tmp.p, 0, words * sizeof(uint64_t), st);
+  if (e != cudaSuccess) return e;
+  a.state = tmp.as<unsigned long long>();
+  a.ticket = reinterpret_cast<unsigned int *>(tmp.as<unsigned long long>() + (size_t)live * (size_t)nb_max);
+  a.nb_max = nb_max;
+  scan_chained<<<dim3((unsigned)nb_max, (unsigned)live), SCAN_THREADS, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t ls_scan_exclusive_u32(const uint32_t *d_in, uint32_t *d_out, int64_t n, uint64_t *d_total, DBuf &tmp,
                                   cudaStream_t st) {
-  if (n <= 0) {
-    if (d_total) return cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st);
-    return cudaSuccess;
-  }
-  if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_out)) & 15u) return cudaErrorMisalignedAddress;
-  int64_t nb = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
-  // chunk records + the ticket counter behind them, cleared before every scan
-  cudaError_t e = tmp.ensure((size_t)(nb + 1) * sizeof(uint64_t));
-  if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(tmp.p, 0, (size_t)(nb + 1) * sizeof(uint64_t), st);
-  if (e != cudaSuccess) return e;
-  scan_chained<<<(unsigned)nb, SCAN_THREADS, 0, st>>>(d_in, d_out, n, tmp.as<unsigned long long>(),
-                                                      reinterpret_cast<unsigned int *>(tmp.as<unsigned long long>() + nb), d_total);
-  return cudaGetLastError();
+  LsScanJob j;
+  j.in = d_in;
+  j.out = d_out;
+  j.n = n;
+  j.total = d_total;
+  return ls_scan_exclusive_u32_multi(&j, 1, tmp, st);
 }
 
 cudaError_t ls_radix_sort_pairs(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n,
