@@ -62,6 +62,9 @@ const char *ls_bams_barcode(void *h, int i);
 int64_t ls_bams_next(void *h, int64_t target_bytes, int64_t *n_cigar, int64_t *n_bases);
 int ls_bams_fill(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *mapq, int32_t *cb, int32_t *l_qseq,
                  uint32_t *cigar_off, uint64_t *base_off, uint32_t *cigar, uint8_t *seq4, uint8_t *qual);
+/* the same, plus ref_end[i] = pos + M/D/N/=/X lengths of read i (exclusive reference end; may be NULL) */
+int ls_bams_fill2(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *mapq, int32_t *cb, int32_t *l_qseq,
+                  uint32_t *cigar_off, uint64_t *base_off, uint32_t *cigar, uint8_t *seq4, uint8_t *qual, int64_t *ref_end);
 /* The decoders' own raw-DEFLATE inflater (RFC 1951, whole buffers, exact output size; ls_inflate.h): 1 if `in`
  * inflates to exactly out_len bytes, 0 otherwise (the readers then hand the member to zlib).  Exposed for tests. */
 int ls_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);

@@ -133,6 +133,8 @@ class BamStream:
             lib.ls_bams_next.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
             lib.ls_bams_fill.restype = C.c_int
             lib.ls_bams_fill.argtypes = [C.c_void_p] + [C.c_void_p] * 11
+            lib.ls_bams_fill2.restype = C.c_int
+            lib.ls_bams_fill2.argtypes = [C.c_void_p] + [C.c_void_p] * 12
             for f in ("ls_bams_n_contigs", "ls_bams_n_barcodes"):
                 getattr(lib, f).restype = C.c_int32
                 getattr(lib, f).argtypes = [C.c_void_p]
@@ -166,7 +168,9 @@ class BamStream:
         except Exception:
             pass
 
-    def next_chunk(self, target_bytes, alloc, head=None):
+    def next_chunk(self, target_bytes, alloc, head=None, head_ends=None):
+        """-> (batch, n_new, ends) or None; ends = exclusive reference end of every read of the batch (head_ends: those of
+        the carried reads in `head`)."""
         nc, nb = C.c_int64(0), C.c_int64(0)
         n = self.lib.ls_bams_next(self.h, int(target_bytes), C.byref(nc), C.byref(nb))
         if n < 0:
@@ -187,9 +191,15 @@ class BamStream:
             a["seq4"][:h_b // 2] = head.seq4
             a["qual"][:h_b] = head.qual
         ptr = lambda arr, off: C.c_void_p(arr.ctypes.data + off * arr.itemsize)
-        rc = self.lib.ls_bams_fill(self.h, ptr(a["tid"], h_n), ptr(a["pos"], h_n), ptr(a["flag"], h_n), ptr(a["mapq"], h_n),
+        ends = np.empty(h_n + n, np.int64)
+        if h_n:
+            if head_ends is None:
+                raise ValueError("next_chunk: head given without head_ends")
+            ends[:h_n] = head_ends
+        rc = self.lib.ls_bams_fill2(self.h, ptr(a["tid"], h_n), ptr(a["pos"], h_n), ptr(a["flag"], h_n), ptr(a["mapq"], h_n),
                                    ptr(a["cell"], h_n), ptr(a["l_qseq"], h_n), ptr(a["cigar_off"], h_n),
-                                   ptr(a["base_off"], h_n), ptr(a["cigar"], h_c), ptr(a["seq4"], h_b // 2), ptr(a["qual"], h_b))
+                                   ptr(a["base_off"], h_n), ptr(a["cigar"], h_c), ptr(a["seq4"], h_b // 2), ptr(a["qual"], h_b),
+                                    ptr(ends, h_n))
         if rc != 0:
             self._check()
             raise IOError("BAM stream: fill failed")
@@ -201,7 +211,7 @@ class BamStream:
             self.barcodes.append(self.lib.ls_bams_barcode(self.h, i).decode())
         N, NC, NB = h_n + n, h_c + nc.value, h_b + nb.value
         return ReadBatch(a["tid"][:N], a["pos"][:N], a["flag"][:N], a["mapq"][:N], a["cell"][:N], a["cigar_off"][:N + 1],
-                         a["cigar"][:NC], a["base_off"][:N + 1], a["l_qseq"][:N], a["seq4"][:NB // 2], a["qual"][:NB]), n
+                         a["cigar"][:NC], a["base_off"][:N + 1], a["l_qseq"][:N], a["seq4"][:NB // 2], a["qual"][:NB]), n, ends
 
 
 def _bgzf_block(data, level):

@@ -559,8 +559,10 @@ int64_t ls_bams_next(void *h, int64_t target_bytes, int64_t *n_cigar, int64_t *n
 
 // Copy the current chunk into caller buffers: per-read arrays [n] (cigar_off / base_off: [n + 1]), cigar [n_cigar],
 // seq4 [n_bases / 2], qual [n_bases].  Reads start at multiples of 16 bases, the padding is zeroed.
-int ls_bams_fill(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *mapq, int32_t *cb, int32_t *lq,
-                 uint32_t *cigar_off, uint64_t *base_off, uint32_t *cigar, uint8_t *seq4, uint8_t *qual) {
+// ref_end (optional): exclusive reference end of every read, pos + its M/D/N/=/X lengths -- what the caller needs to
+// decide which windows are complete, computed here while the CIGAR is in cache.
+int ls_bams_fill2(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *mapq, int32_t *cb, int32_t *lq,
+                  uint32_t *cigar_off, uint64_t *base_off, uint32_t *cigar, uint8_t *seq4, uint8_t *qual, int64_t *ref_end) {
   Stream *s = (Stream *)h;
   if (!s->err.empty()) return -1;
   const Chunk &c = s->ch[s->cur];
@@ -584,6 +586,14 @@ int ls_bams_fill(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *m
         lq[i] = (int32_t)l_seq;
         const uint8_t *cg = r + 32 + l_name;
         memcpy(cigar + c.cig_off[(size_t)i], cg, 4 * (size_t)n_cig);
+        if (ref_end) {
+          int64_t span = 0;
+          for (uint32_t k = 0; k < n_cig; ++k) {
+            const uint32_t op = rd32(cg + 4 * k);
+            if ((0x18du >> (op & 15u)) & 1u) span += op >> 4;  // M, D, N, =, X consume the reference
+          }
+          ref_end[i] = (int64_t)(int32_t)rd32(r + 4) + span;
+        }
         const uint8_t *sq = cg + 4 * (size_t)n_cig;
         const uint64_t bo = c.base_off[(size_t)i], pad = c.base_off[(size_t)i + 1] - bo;
         const uint32_t sb = (l_seq + 1) / 2;
@@ -600,6 +610,11 @@ int ls_bams_fill(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *m
   for (auto &t : th) t.join();
   s->t_fill += now_s() - t_f0;
   return 0;
+}
+
+int ls_bams_fill(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *mapq, int32_t *cb, int32_t *lq,
+                 uint32_t *cigar_off, uint64_t *base_off, uint32_t *cigar, uint8_t *seq4, uint8_t *qual) {
+  return ls_bams_fill2(h, tid, pos, flag, mapq, cb, lq, cigar_off, base_off, cigar, seq4, qual, nullptr);
 }
 
 int ls_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len) {

@@ -356,33 +356,32 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
 
     def decoder():
         try:
-            wi, seq, carry = 0, 0, None
+            wi, seq, carry, carry_ends = 0, 0, None, None
             while True:
                 slot = free_slots.get()
                 t_a = time.time()
-                got = bs.next_chunk(chunk_bytes, slot, carry)
+                got = bs.next_chunk(chunk_bytes, slot, carry, carry_ends)
                 busy["decode"] += time.time() - t_a
                 t_a = time.time()
                 if got is None:
                     free_slots.put(slot)
-                    batch, last = carry, None
+                    batch, last, ends = carry, None, carry_ends
                     if batch is None or batch.n_reads == 0 or wi >= len(win):
                         break
                     slot = None
                 else:
-                    batch, _n_new = got
+                    batch, _n_new, ends = got
                     last = (int(batch.tid[-1]) << 32) | int(batch.pos[-1])
                 # windows no future read can overlap: every later read starts at or after `last`
                 wj = len(win) if last is None else int(np.searchsorted(wk_end, last, side="right"))
                 wj = max(wj, wi)
-                ends = read_ends(batch)
                 rk_end = (batch.tid.astype(np.int64) << 32) | np.maximum(ends, batch.pos.astype(np.int64) + 1)
                 if wj > wi:
                     iv = prune_and_sort_windows([(bs.contig_names[t], s, e) for t, s, e in win[wi:wj]], bs.contig_names, batch, ends)
                     if iv:
                         b2 = ReadBatch(batch.tid, batch.pos, batch.flag, batch.mapq, cell_ids(batch.cell, bs.barcodes),
                                        batch.cigar_off, batch.cigar, batch.base_off, batch.l_qseq, batch.seq4, batch.qual)
-                        todo.put((seq, b2, iv, slot))
+                        todo.put((seq, b2, iv, slot, win[wj][0] if wj < len(win) else (1 << 30)))
                         seq += 1
                         slot_in_use = True
                     else:
@@ -398,8 +397,9 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                 if wi < len(win):
                     keep = np.nonzero(rk_end > wk_start[wi])[0]
                     carry = batch.select(keep) if keep.shape[0] else None
+                    carry_ends = ends[keep] if keep.shape[0] else None
                 else:
-                    carry = None
+                    carry, carry_ends = None, None
                 if not slot_in_use:
                     free_slots.put(slot)
                 busy["host_glue"] += time.time() - t_a
@@ -419,7 +419,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                     item = todo.get()
                     if item is None:
                         break
-                    seq, batch, iv, slot = item
+                    seq, batch, iv, slot, complete_tid = item
                     t_a = time.time()
                     with fasta_lock:
                         contig_seq = {t: fasta.contig(bs.contig_names[t]) for t in sorted({w[0] for w in iv})}
@@ -430,7 +430,7 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                     if slot is not None:
                         free_slots.put(slot)
                     busy["device"] += time.time() - t_a
-                    done.put((seq, sites))
+                    done.put((seq, sites, complete_tid))
             finally:
                 eng.close()
         except Exception as ex:
@@ -449,15 +449,54 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
     host.ls_write_counter_rows.restype = C.c_int
     parts, pending, want, live, n_sites = {}, {}, 0, len(devices), 0
     nthreads = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    # The table lists the contigs in NAME order (collect_result sorts the window files by name), the BAM delivers them
+    # in header order: rows go to one part file per contig, and a part is appended to the output as soon as every
+    # contig before it in name order is complete -- at the end only the last few contigs are left to copy.
+    order = sorted({t for t, _s, _e in win}, key=lambda t: bs.contig_names[t])
+    state = {"out": None, "next": 0, "complete_tid": -1}
+    busy["concat"] = 0.0
+
+    def append_ready(everything=False):
+        t_cat = time.time()
+        while state["next"] < len(order) and (everything or order[state["next"]] < state["complete_tid"]):
+            t = order[state["next"]]
+            state["next"] += 1
+            path = parts.pop(t, None)
+            if path is None:
+                continue
+            if state["out"] is None:
+                state["out"] = open(out_file, "wb")
+                state["out"].write(("##fileDate=%s\n" % time.strftime("%d/%m/%Y")).encode())
+                state["out"].write((COUNTER_CONCEPTS + "\n").encode())
+                state["out"].write(("\t".join(["#CHROM", "POS", "REF", "INFO", str(ID)]) + "\n").encode())
+                state["out"].flush()
+            out = state["out"]
+            with open(path, "rb") as f:
+                left = os.fstat(f.fileno()).st_size
+                try:  # in-kernel copy
+                    while left > 0:
+                        k = os.sendfile(out.fileno(), f.fileno(), None, min(left, 1 << 30))
+                        if k <= 0:
+                            break
+                        left -= k
+                except OSError:
+                    pass
+                if left > 0:
+                    out.seek(0, os.SEEK_END)
+                    shutil.copyfileobj(f, out, 1 << 24)
+                    out.flush()
+            os.remove(path)
+        busy["concat"] += time.time() - t_cat
+
     while live:
         item = done.get()
         if item is None:
             live -= 1
             continue
-        pending[item[0]] = item[1]
+        pending[item[0]] = (item[1], item[2])
         t_w = time.time()
         while want in pending:
-            sites = pending.pop(want)
+            sites, complete_tid = pending.pop(want)
             want += 1
             n_sites += sites.n_sites
             for t in np.unique(sites.tid).tolist():
@@ -470,6 +509,9 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
                                                 cnt.ctypes.data, hi - lo, nthreads, 1)
                 if rc != 0:
                     errors.append(IOError("ls_write_counter_rows(%s) failed: %d" % (path, rc)))
+            state["complete_tid"] = max(state["complete_tid"], complete_tid)
+            if not errors:
+                append_ready()
         busy["writer"] += time.time() - t_w
     for t in threads:
         t.join()
@@ -482,26 +524,10 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
         if n_sites == 0:
             print("No temporary files found")
             return 0
-        with open(out_file, "wb") as out:
-            out.write(("##fileDate=%s\n" % time.strftime("%d/%m/%Y")).encode())
-            out.write((COUNTER_CONCEPTS + "\n").encode())
-            out.write(("\t".join(["#CHROM", "POS", "REF", "INFO", str(ID)]) + "\n").encode())
-            out.flush()
-            t_cat = time.time()
-            for t in sorted(parts, key=lambda t: bs.contig_names[t]):
-                with open(parts[t], "rb") as f:
-                    left = os.fstat(f.fileno()).st_size
-                    try:  # in-kernel copy
-                        while left > 0:
-                            k = os.sendfile(out.fileno(), f.fileno(), None, min(left, 1 << 30))
-                            if k <= 0:
-                                break
-                            left -= k
-                    except OSError:
-                        pass
-                    if left > 0:
-                        shutil.copyfileobj(f, out, 1 << 24)
-            busy["concat"] = time.time() - t_cat
+        append_ready(everything=True)
+        if state["out"] is not None:
+            state["out"].close()
+            state["out"] = None
         if os.environ.get("LS_STREAM_TIMING"):
             import resource
             print("[stream_count] busy seconds: " + ", ".join("%s %.2f" % kv for kv in sorted(busy.items())) +
@@ -525,6 +551,10 @@ def stream_count(bam_path, named_windows, fasta, params: CountParams, out_file, 
         for path in parts.values():
             if os.path.exists(path):
                 os.remove(path)
+        if state["out"] is not None:   # an error after the first contigs were appended: no partial table is left behind
+            state["out"].close()
+            if os.path.exists(out_file):
+                os.remove(out_file)
 
 
 def format_counter_lines(chrom, pos, ref, counts):
