@@ -595,7 +595,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_cli = {"value": al_cli / best, "unit": UNIT, "seconds": best, "reads": int(n_cli), "bam_mb": bam_mb,
                    "tsv_mb": os.path.getsize(tmp + "/x.tsv") / 1e6, "host_cores": os.cpu_count(),
                    "api": "workflow/scripts/SNVCalling/BaseCellCounter.py as a subprocess (process start, CUDA context, "
-                          "streaming BGZF decode -> pinned slots -> ls_pileup_count -> native TSV rows); decode-bound (zlib)"}
+                          "streaming BGZF decode (own DEFLATE decoder, prefetch thread) -> pinned slots -> ls_pileup_count -> native TSV rows, completed contigs appended as they finish)"}
         import shutil
         shutil.rmtree(tmp, ignore_errors=True)
 
