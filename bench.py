@@ -12,7 +12,7 @@ sort -> unit expansion -> pileup-count kernel -> compaction of the passing sites
 output order (the compacted site list in HBM is what BaseCellCounter emits).  `value` is device-resident
 throughput, `e2e` is the same metric from pinned HOST buffers (H2D of the batch and D2H of the compacted
 site table inside the timing): the batch cut into --e2e-shards window shards, the C-ABI call ls_pileup_count()
-per shard on --e2e-lanes CUDA contexts of the GPU (pipeline.count_shards_pipelined), so that transfers and
+per shard on --e2e-lanes engine handles of the GPU (own stream and buffers, one CUDA context; pipeline.count_shards_pipelined), so that transfers and
 kernels of different shards overlap; the one-call figure is reported next to it (e2e.single_call_*).
 One JSON line on stdout (rank 0).
 """

@@ -164,7 +164,7 @@ def prune_and_sort_windows(named_windows, bam_names, batch, ends):
 def count_sites(batch, windows_iv, contig_seq, params: CountParams, devices=None, stats_out=None):
     """Pileup counts for windows_iv = [(tid, start, end)] (sorted, disjoint).  The windows are cut into
     coverage-balanced shards (array slices of the batch, no copies): one per device, or
-    LONGSOM_SHARDS_PER_GPU per device, in which case each device runs two CUDA contexts so that uploads, kernels
+    LONGSOM_SHARDS_PER_GPU per device, in which case each device runs two engine handles (own stream and buffers in the device's one CUDA context) so that uploads, kernels
     and result copies of its shards overlap.  Results are concatenated in window order."""
     devices = devices or [0]
     if not windows_iv:
