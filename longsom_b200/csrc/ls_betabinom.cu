@@ -59,7 +59,8 @@ constexpr int BB_SMALL = 128;
 
 __global__ void __launch_bounds__(128) bb_small_kernel(const int32_t *__restrict__ k, const int32_t *__restrict__ n, int64_t m,
                                                        double a, double b, const double *__restrict__ lab_p,
-                                                       double *__restrict__ p, uint32_t *__restrict__ nbig, int no_query_nan) {
+                                                       double *__restrict__ p, uint32_t *__restrict__ nbig, int no_query_nan,
+                                                       const double *__restrict__ table, int table_n) {
   const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= m) return;
   const int kk = k[q], nn = n[q];
@@ -69,6 +70,10 @@ __global__ void __launch_bounds__(128) bb_small_kernel(const int32_t *__restrict
   }
   if (nn < 0 || kk <= 0 || kk > nn) {
     p[q] = ls_sf_finish(kk, nn, 0.0);
+    return;
+  }
+  if (table && nn <= table_n) {  // the tail is a function of (k, n) only: shallow pairs come from the table
+    p[q] = table[nn * (table_n + 1) + kk];
     return;
   }
   if (kk > BB_SMALL) {
@@ -82,14 +87,35 @@ __global__ void __launch_bounds__(128) bb_small_kernel(const int32_t *__restrict
   p[q] = ls_sf_finish(kk, nn, ls_pairwise_sum(t, kk));
 }
 
-// device arrays in, device array out (used by the sparse genotype path)
+// every (k, n) with 0 <= k, n <= BB_TABLE_N, as queries: entry n * (BB_TABLE_N + 1) + k
+constexpr int BB_TABLE_N = 64;
+__global__ void bb_table_queries_kernel(int32_t *__restrict__ k, int32_t *__restrict__ n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (BB_TABLE_N + 1) * (BB_TABLE_N + 1)) return;
+  k[i] = i % (BB_TABLE_N + 1);
+  n[i] = i / (BB_TABLE_N + 1);
+}
+
+// device arrays in, device array out (used by the sparse genotype path).  The depth of a (site, cell) pair is a
+// handful of reads, so almost every query repeats one of a few hundred (k, n) pairs: those tails are computed once per
+// call, by the same kernel (same arithmetic, same summation order), and looked up.
 int ls_betabinom_device(ls_ctx *ctx, const int32_t *d_k, const int32_t *d_n, double a, double b, double *d_p, int64_t m,
                         uint32_t *d_nbig) {
   if (m <= 0) return LS_OK;
   cudaStream_t st = ctx->stream;
-  LS_CK(ctx->g_c.ensure(64));
-  bb_const_kernel<<<1, 1, 0, st>>>(a, b, ctx->g_c.as<double>());
-  bb_small_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_k, d_n, m, a, b, ctx->g_c.as<double>(), d_p, d_nbig, 1);
+  constexpr int NT = (BB_TABLE_N + 1) * (BB_TABLE_N + 1);
+  LS_CK(ctx->g_c.ensure(64 + (size_t)NT * (4 + 4 + 8)));
+  double *d_lab = ctx->g_c.as<double>();
+  double *d_tab = d_lab + 8;
+  int32_t *d_tk = reinterpret_cast<int32_t *>(d_tab + NT), *d_tn = d_tk + NT;
+  bb_const_kernel<<<1, 1, 0, st>>>(a, b, d_lab);
+  const double *table = nullptr;
+  if (m > 4 * (int64_t)NT) {
+    bb_table_queries_kernel<<<(NT + 255) / 256, 256, 0, st>>>(d_tk, d_tn);
+    bb_small_kernel<<<(NT + 127) / 128, 128, 0, st>>>(d_tk, d_tn, NT, a, b, d_lab, d_tab, nullptr, 0, nullptr, 0);
+    table = d_tab;
+  }
+  bb_small_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_k, d_n, m, a, b, d_lab, d_p, d_nbig, 1, table, BB_TABLE_N);
   LS_CK(cudaGetLastError());
   return LS_OK;
 }
@@ -122,7 +148,7 @@ extern "C" int ls_betabinom_sf(ls_ctx *ctx, const int32_t *k, const int32_t *n, 
     LS_CK(cudaMemcpyAsync(ctx->g_b.p, n, (size_t)m * 4, cudaMemcpyHostToDevice, st));
     LS_CK(cudaEventRecord(ctx->ev[0], st));
     bb_small_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(ctx->g_a.as<int32_t>(), ctx->g_b.as<int32_t>(), m, a, b,
-                                                                 ctx->g_e.as<double>(), ctx->g_d.as<double>(), nullptr, 0);
+                                                                 ctx->g_e.as<double>(), ctx->g_d.as<double>(), nullptr, 0, nullptr, 0);
     ++launches;
     LS_CK(cudaGetLastError());
     LS_CK(cudaEventRecord(ctx->ev[1], st));

@@ -462,7 +462,7 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
     // K2 on the device: p = betabinom.sf(Alt - eps, Dp, alpha, beta) for the pairs with a query
     rc = ls_betabinom_device(ctx, t_k, t_dp, alpha, beta, ctx->gs_p.as<double>(), nt, d_nbig);
     if (rc != LS_OK) return rc;
-    launches += 2;
+    launches += nt > 4 * 65 * 65 ? 4 : 2;  // constants + tails (+ the (k, n) table and its queries)
   } else {
     LS_CK(cudaEventRecord(ctx->ev[1], st));
   }
