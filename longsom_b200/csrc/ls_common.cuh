@@ -242,5 +242,7 @@ cudaError_t ls_scan_exclusive_u32(const uint32_t *d_in, uint32_t *d_out, int64_t
 cudaError_t ls_radix_sort_pairs(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b,
                                 int64_t n, int key_bits, DBuf &hist, uint64_t **sorted_keys,
                                 uint32_t **sorted_vals, int num_sms, cudaStream_t st, int *launches);
+cudaError_t ls_radix_sort_keys32(uint32_t *keys_a, uint32_t *keys_b, int64_t n, int key_bits, DBuf &hist,
+                                 uint32_t **sorted_keys, int num_sms, cudaStream_t st, int *launches);
 cudaError_t ls_radix_sort_keys(uint64_t *keys_a, uint64_t *keys_b, int64_t n, int key_bits, DBuf &hist,
                                uint64_t **sorted_keys, int num_sms, cudaStream_t st, int *launches);

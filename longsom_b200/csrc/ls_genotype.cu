@@ -36,6 +36,7 @@ struct GenoArgs {
   uint32_t *hit_cnt;            // sparse pass 1: hits per read
   const uint32_t *hit_off;      // sparse pass 2: first hit slot of every read (exclusive scan of hit_cnt)
   uint64_t *hits;               // sparse pass 2: (site * n_cells + cell) << 1 | (class == ALT_expected)
+  uint32_t *hits32;             // the same as 32-bit keys (MODE 3: when n_sites * n_cells * 2 < 2^32 -- half the sort traffic)
   unsigned long long *n_events;
 };
 
@@ -65,13 +66,14 @@ __device__ __forceinline__ bool geno_dropped(const GenoArgs &a, uint32_t bin, ui
   return lo < a.n_drop && a.drop_keys[lo] == key;
 }
 
-// MODE 0: dense atomics, 1: count the read's hits, 2: write them at the read's slots
+// MODE 0: dense atomics, 1: count the read's hits, 2 / 3: write them at the read's slots as 64-bit / 32-bit keys
 template <int MODE>
 __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
   int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long nev = 0;
   if (r < a.n_reads) {
     uint64_t *hp = MODE == 2 ? a.hits + a.hit_off[r] : nullptr;
+    uint32_t *hp32 = MODE == 3 ? a.hits32 + a.hit_off[r] : nullptr;
     const uint32_t flag = a.flag[r];
     const int32_t cell = a.cell[r];
     const int32_t tid = a.tid[r];
@@ -120,6 +122,8 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
                   if (cls == ac) atomicAdd(&a.alt[(size_t)s * a.n_cells + cell], 1);
                 } else if (MODE == 2) {
                   *hp++ = (((uint64_t)s * (uint64_t)a.n_cells + (uint64_t)cell) << 1) | (cls == ac ? 1u : 0u);
+                } else if (MODE == 3) {
+                  *hp32++ = (((uint32_t)s * (uint32_t)a.n_cells + (uint32_t)cell) << 1) | (cls == ac ? 1u : 0u);
                 }
                 ++nev;
               }
@@ -145,23 +149,25 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
 }
 
 // ---- sparse output: sorted hits -> one (site, cell, Dp, Alt) tuple per touched pair ---------------------------
-__global__ void __launch_bounds__(256) hit_flag_kernel(const uint64_t *__restrict__ hits, int64_t n, uint32_t *__restrict__ flag) {
+template <typename K>
+__global__ void __launch_bounds__(256) hit_flag_kernel(const K *__restrict__ hits, int64_t n, uint32_t *__restrict__ flag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   flag[i] = (i < n && (i == 0 || (hits[i] >> 1) != (hits[i - 1] >> 1))) ? 1u : 0u;
 }
 
-__global__ void __launch_bounds__(256) hit_reduce_kernel(const uint64_t *__restrict__ hits, int64_t n,
+template <typename K>
+__global__ void __launch_bounds__(256) hit_reduce_kernel(const K *__restrict__ hits, int64_t n,
                                                          const uint32_t *__restrict__ rank, int32_t n_cells,
                                                          const uint8_t *__restrict__ skip_p, int32_t *__restrict__ t_site,
                                                          int32_t *__restrict__ t_cell, int32_t *__restrict__ t_dp,
                                                          int32_t *__restrict__ t_alt, int32_t *__restrict__ t_k) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint64_t key = hits[i] >> 1;
-  if (i > 0 && (hits[i - 1] >> 1) == key) return;  // not the first hit of its pair
+  const uint64_t key = (uint64_t)(hits[i] >> 1);
+  if (i > 0 && (uint64_t)(hits[i - 1] >> 1) == key) return;  // not the first hit of its pair
   int32_t dp = 0, alt = 0;
-  for (int64_t j = i; j < n && (hits[j] >> 1) == key; ++j) {  // the hits of a pair are adjacent; the alt ones last
+  for (int64_t j = i; j < n && (uint64_t)(hits[j] >> 1) == key; ++j) {  // the hits of a pair are adjacent; the alt ones last
     ++dp;
     alt += (int32_t)(hits[j] & 1u);
   }
@@ -360,6 +366,7 @@ static void geno_fill_args(ls_ctx *ctx, GenoArgs &a, int64_t n_sites, int32_t n_
   a.hit_cnt = nullptr;
   a.hit_off = nullptr;
   a.hits = nullptr;
+  a.hits32 = nullptr;
   a.n_events = ctx->counters.as<unsigned long long>();
 }
 
@@ -431,20 +438,33 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
   int64_t nt = 0;
   if (nh >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: more than 2^32 hits; split the site list");
   if (nh > 0) {
-    LS_CK(ctx->gs_hits_a.ensure((size_t)nh * 8));
-    LS_CK(ctx->gs_hits_b.ensure((size_t)nh * 8));
+    // keys that fit 32 bits are written, sorted and reduced as 32-bit words (half the traffic of the hit sort)
+    const uint64_t key_span = (uint64_t)n_sites * (uint64_t)n_cells * 2u;
+    const bool k32 = key_span < (1ull << 32) && !getenv("LS_GENO_KEYS64");
+    const size_t ksz = k32 ? 4 : 8;
+    LS_CK(ctx->gs_hits_a.ensure((size_t)nh * ksz));
+    LS_CK(ctx->gs_hits_b.ensure((size_t)nh * ksz));
     LS_CK(ctx->gs_flag.ensure((size_t)(nh + 1) * 4));
     // pass 2: the hits themselves
     a.hit_cnt = nullptr;
     a.hit_off = ctx->gs_cnt.as<uint32_t>();
     a.hits = ctx->gs_hits_a.as<uint64_t>();
+    a.hits32 = ctx->gs_hits_a.as<uint32_t>();
     LS_CK(cudaMemsetAsync(d_cnt, 0, 8, st));
-    genotype_kernel<2><<<grid, 256, 0, st>>>(a);
+    const int key_bits = ls_bits_for(key_span);
     uint64_t *sorted = nullptr;
-    const int key_bits = ls_bits_for((uint64_t)n_sites * (uint64_t)n_cells * 2u);
-    LS_CK(ls_radix_sort_keys(ctx->gs_hits_a.as<uint64_t>(), ctx->gs_hits_b.as<uint64_t>(), nh, key_bits, ctx->rs_hist, &sorted,
-                             ctx->num_sms, st, &launches));
-    hit_flag_kernel<<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>());
+    uint32_t *sorted32 = nullptr;
+    if (k32) {
+      genotype_kernel<3><<<grid, 256, 0, st>>>(a);
+      LS_CK(ls_radix_sort_keys32(ctx->gs_hits_a.as<uint32_t>(), ctx->gs_hits_b.as<uint32_t>(), nh, key_bits, ctx->rs_hist,
+                                 &sorted32, ctx->num_sms, st, &launches));
+      hit_flag_kernel<uint32_t><<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted32, nh, ctx->gs_flag.as<uint32_t>());
+    } else {
+      genotype_kernel<2><<<grid, 256, 0, st>>>(a);
+      LS_CK(ls_radix_sort_keys(ctx->gs_hits_a.as<uint64_t>(), ctx->gs_hits_b.as<uint64_t>(), nh, key_bits, ctx->rs_hist, &sorted,
+                               ctx->num_sms, st, &launches));
+      hit_flag_kernel<uint64_t><<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>());
+    }
     LS_CK(ls_scan_exclusive_u32(ctx->gs_flag.as<uint32_t>(), ctx->gs_flag.as<uint32_t>(), nh + 1, d_ntup, ctx->scan_tmp, st));
     LS_CK(cudaMemcpyAsync(h, d_cnt, 32, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
@@ -453,9 +473,13 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
     LS_CK(ctx->gs_p.ensure((size_t)nt * 8 + 16));
     int32_t *t_site = ctx->gs_tup.as<int32_t>(), *t_cell = t_site + nt, *t_dp = t_cell + nt, *t_alt = t_dp + nt,
             *t_k = t_alt + nt;
-    hit_reduce_kernel<<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
-                                                                    skip_p ? ctx->gs_skip.as<uint8_t>() : nullptr, t_site, t_cell,
-                                                                    t_dp, t_alt, t_k);
+    const uint8_t *d_skip = skip_p ? ctx->gs_skip.as<uint8_t>() : nullptr;
+    if (k32)
+      hit_reduce_kernel<uint32_t><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted32, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
+                                                                                d_skip, t_site, t_cell, t_dp, t_alt, t_k);
+    else
+      hit_reduce_kernel<uint64_t><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
+                                                                                d_skip, t_site, t_cell, t_dp, t_alt, t_k);
     launches += 4;
     LS_CK(cudaGetLastError());
     LS_CK(cudaEventRecord(ctx->ev[1], st));
@@ -598,6 +622,7 @@ extern "C" int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int
   a.hit_cnt = nullptr;
   a.hit_off = nullptr;
   a.hits = nullptr;
+  a.hits32 = nullptr;
   if (ctx->n_reads > 0) genotype_kernel<0><<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, st>>>(a);
   LS_CK(cudaGetLastError());
   LS_CK(cudaEventRecord(ctx->ev[2], st));

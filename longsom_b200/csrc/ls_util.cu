@@ -138,7 +138,8 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ROUNDS = 8;                       // items per thread per chunk
 constexpr int RS_CHUNK = RS_THREADS * RS_ROUNDS;   // 2048
 
-__global__ void __launch_bounds__(RS_THREADS) rs_hist(const uint64_t *__restrict__ keys, int64_t n, int64_t per_block,
+template <typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist(const K *__restrict__ keys, int64_t n, int64_t per_block,
                                                       int shift, uint32_t *__restrict__ hist, int G) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
@@ -156,17 +157,17 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist(const uint64_t *__restrict
 // One chunk (RS_CHUNK items) at a time: stable rank of every item inside its digit (match_any inside a warp,
 // per-warp digit counters across warps), then the chunk is laid out digit-major in shared memory and written
 // from there, so that each digit's items leave the CTA as one contiguous, coalesced run.
-template <bool HAS_VALS>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restrict__ keys_in,
+template <bool HAS_VALS, typename K>
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter(const K *__restrict__ keys_in,
                                                          const uint32_t *__restrict__ vals_in,
-                                                         uint64_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
+                                                         K *__restrict__ keys_out, uint32_t *__restrict__ vals_out,
                                                          int64_t n, int64_t per_block, int shift,
                                                          const uint32_t *__restrict__ hist_scanned, int G, int first_pass) {
   __shared__ uint32_t gbase[256];            // running global offset of each digit for this CTA
   __shared__ uint32_t lbase[256];            // offset of each digit inside the staged chunk
   __shared__ uint32_t wcnt[RS_WARPS][256];   // per-warp digit counts, then per-warp offsets inside the digit
   __shared__ uint32_t scan_sm[RS_THREADS / 32 + 1];
-  __shared__ uint64_t skey[RS_CHUNK];
+  __shared__ K skey[RS_CHUNK];
   __shared__ uint32_t sval[HAS_VALS ? RS_CHUNK : 1];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
   for (int64_t chunk = lo; chunk < hi; chunk += RS_CHUNK) {
     for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
     __syncthreads();
-    uint64_t key[RS_ROUNDS];
+    K key[RS_ROUNDS];
     uint32_t val[RS_ROUNDS];
     uint32_t rank[RS_ROUNDS];
     // all loads of the chunk first: the ranking below has warp barriers the loads could not be hoisted across
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
     for (int r = 0; r < RS_ROUNDS; ++r) {
       int64_t idx = chunk + (int64_t)w * (32 * RS_ROUNDS) + r * 32 + lane;
       bool valid = idx < hi;
-      key[r] = valid ? keys_in[idx] : 0ull;
+      key[r] = valid ? keys_in[idx] : (K)0;
       if (HAS_VALS) val[r] = valid ? (first_pass ? (uint32_t)idx : vals_in[idx]) : 0u;
     }
 #pragma unroll
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const uint64_t *__restr
     __syncthreads();
     const int cn = (int)((hi - chunk) < (int64_t)RS_CHUNK ? (hi - chunk) : (int64_t)RS_CHUNK);
     for (int i = threadIdx.x; i < cn; i += RS_THREADS) {
-      const uint64_t k = skey[i];
+      const K k = skey[i];
       const uint32_t d = (uint32_t)(k >> shift) & 255u;
       const uint32_t pos = gbase[d] + ((uint32_t)i - lbase[d]);
       keys_out[pos] = k;
@@ -269,9 +270,9 @@ __global__ void __launch_bounds__(256) rs_scan_totals(uint32_t *__restrict__ tot
   totals[threadIdx.x] = ex;
 }
 
-template <bool HAS_VALS>
-cudaError_t radix_sort_impl(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n,
-                            int key_bits, DBuf &hist, uint64_t **sorted_keys, uint32_t **sorted_vals, int num_sms,
+template <bool HAS_VALS, typename K>
+cudaError_t radix_sort_impl(K *keys_a, K *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n,
+                            int key_bits, DBuf &hist, K **sorted_keys, uint32_t **sorted_vals, int num_sms,
                             cudaStream_t st, int *launches) {
   *sorted_keys = keys_a;
   if (sorted_vals) *sorted_vals = vals_a;
@@ -283,17 +284,17 @@ cudaError_t radix_sort_impl(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a
   int64_t per_block = ((nchunks + G - 1) / G) * RS_CHUNK;
   cudaError_t e = hist.ensure(((size_t)256 * G + 256) * sizeof(uint32_t));
   if (e != cudaSuccess) return e;
-  uint64_t *kin = keys_a, *kout = keys_b;
+  K *kin = keys_a, *kout = keys_b;
   uint32_t *vin = vals_a, *vout = vals_b;
   for (int p = 0; p < passes; ++p) {
     int shift = p * 8;
-    rs_hist<<<G, RS_THREADS, 0, st>>>(kin, n, per_block, shift, hist.as<uint32_t>(), G);
+    rs_hist<K><<<G, RS_THREADS, 0, st>>>(kin, n, per_block, shift, hist.as<uint32_t>(), G);
     rs_scan_digit<<<256, 256, 0, st>>>(hist.as<uint32_t>(), G, hist.as<uint32_t>() + (size_t)256 * G);
     rs_scan_totals<<<1, 256, 0, st>>>(hist.as<uint32_t>() + (size_t)256 * G);
-    rs_scatter<HAS_VALS><<<G, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, per_block, shift, hist.as<uint32_t>(), G,
+    rs_scatter<HAS_VALS, K><<<G, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, per_block, shift, hist.as<uint32_t>(), G,
                                                    p == 0 ? 1 : 0);
     if (launches) *launches += 4;
-    uint64_t *tk = kin;
+    K *tk = kin;
     kin = kout;
     kout = tk;
     uint32_t *tv = vin;
@@ -352,7 +353,7 @@ cudaError_t ls_scan_exclusive_u32(const uint32_t *d_in, uint32_t *d_out, int64_t
 cudaError_t ls_radix_sort_pairs(uint64_t *keys_a, uint64_t *keys_b, uint32_t *vals_a, uint32_t *vals_b, int64_t n,
                                 int key_bits, DBuf &hist, uint64_t **sorted_keys, uint32_t **sorted_vals, int num_sms,
                                 cudaStream_t st, int *launches) {
-  return radix_sort_impl<true>(keys_a, keys_b, vals_a, vals_b, n, key_bits, hist, sorted_keys, sorted_vals, num_sms,
+  return radix_sort_impl<true, uint64_t>(keys_a, keys_b, vals_a, vals_b, n, key_bits, hist, sorted_keys, sorted_vals, num_sms,
                                st, launches);
 }
 
