@@ -362,3 +362,9 @@ cudaError_t ls_radix_sort_keys(uint64_t *keys_a, uint64_t *keys_b, int64_t n, in
   return radix_sort_impl<false>(keys_a, keys_b, nullptr, nullptr, n, key_bits, hist, sorted_keys, nullptr, num_sms,
                                 st, launches);
 }
+
+cudaError_t ls_radix_sort_keys32(uint32_t *keys_a, uint32_t *keys_b, int64_t n, int key_bits, DBuf &hist,
+                                 uint32_t **sorted_keys, int num_sms, cudaStream_t st, int *launches) {
+  return radix_sort_impl<false>(keys_a, keys_b, nullptr, nullptr, n, key_bits, hist, sorted_keys, nullptr, num_sms,
+                                st, launches);
+}
