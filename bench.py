@@ -501,7 +501,7 @@ def run_ours(args, rank, world, local_rank):
                              "note": "host site table in, touched (site, cell, Dp, Alt, p) tuples out"},
                      "rank0": {"sites": int(n_cand), "touched_pairs": int(n_tup), "pileup_hits": int(hits),
                                "k1p_ms": gk_ms, "k2_ms": bb_ms,
-                               "roofline": {"bound": "hbm", "kernel": "genotype_kernel x2 + hit sort + reduce",
+                               "roofline": {"bound": "hbm", "kernel": "slot count (CIGAR walk) + genotype_kernel + hit sort + reduce",
                                             "achieved": g_alg / (gk_ms * 1e-3) / 1e9 if gk_ms else None, "peak": peak,
                                             "unit": "GB/s", "frac": g_alg / (gk_ms * 1e-3) / 1e9 / peak if gk_ms else None,
                                             "algorithmic_bytes": g_alg}}}

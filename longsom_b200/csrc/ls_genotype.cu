@@ -36,6 +36,7 @@ struct GenoArgs {
   uint32_t *hit_cnt;            // sparse pass 1: hits per read
   const uint32_t *hit_off;      // sparse pass 2: first hit slot of every read (exclusive scan of hit_cnt)
   uint64_t *hits;               // sparse pass 2: (site * n_cells + cell) << 1 | (class == ALT_expected)
+  uint64_t sentinel;            // key of an unused slot (n_sites * n_cells * 2: behind every real key)
   uint32_t *hits32;             // the same as 32-bit keys (MODE 3: when n_sites * n_cells * 2 < 2^32 -- half the sort traffic)
   unsigned long long *n_events;
 };
@@ -142,6 +143,10 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
       }
     }
     if (MODE == 1) a.hit_cnt[r] = (uint32_t)nev;
+    if (MODE == 2)
+      for (uint64_t *e = a.hits + a.hit_off[r + 1]; hp < e; ++hp) *hp = a.sentinel;
+    if (MODE == 3)
+      for (uint32_t *e = a.hits32 + a.hit_off[r + 1]; hp32 < e; ++hp32) *hp32 = (uint32_t)a.sentinel;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nev += __shfl_xor_sync(0xffffffffu, nev, o);
@@ -150,24 +155,26 @@ __global__ void __launch_bounds__(256) genotype_kernel(GenoArgs a) {
 
 // ---- sparse output: sorted hits -> one (site, cell, Dp, Alt) tuple per touched pair ---------------------------
 template <typename K>
-__global__ void __launch_bounds__(256) hit_flag_kernel(const K *__restrict__ hits, int64_t n, uint32_t *__restrict__ flag) {
+__global__ void __launch_bounds__(256) hit_flag_kernel(const K *__restrict__ hits, int64_t n, K sentinel, uint32_t *__restrict__ flag) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  flag[i] = (i < n && (i == 0 || (hits[i] >> 1) != (hits[i - 1] >> 1))) ? 1u : 0u;
+  // unused slots carry the sentinel and sort behind every real key
+  flag[i] = (i < n && hits[i] != sentinel && (i == 0 || (hits[i] >> 1) != (hits[i - 1] >> 1))) ? 1u : 0u;
 }
 
 template <typename K>
-__global__ void __launch_bounds__(256) hit_reduce_kernel(const K *__restrict__ hits, int64_t n,
+__global__ void __launch_bounds__(256) hit_reduce_kernel(const K *__restrict__ hits, int64_t n, K sentinel,
                                                          const uint32_t *__restrict__ rank, int32_t n_cells,
                                                          const uint8_t *__restrict__ skip_p, int32_t *__restrict__ t_site,
                                                          int32_t *__restrict__ t_cell, int32_t *__restrict__ t_dp,
                                                          int32_t *__restrict__ t_alt, int32_t *__restrict__ t_k) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  if (hits[i] == sentinel) return;  // an unused slot
   const uint64_t key = (uint64_t)(hits[i] >> 1);
   if (i > 0 && (uint64_t)(hits[i - 1] >> 1) == key) return;  // not the first hit of its pair
   int32_t dp = 0, alt = 0;
-  for (int64_t j = i; j < n && (uint64_t)(hits[j] >> 1) == key; ++j) {  // the hits of a pair are adjacent; the alt ones last
+  for (int64_t j = i; j < n && hits[j] != sentinel && (uint64_t)(hits[j] >> 1) == key; ++j) {  // the hits of a pair are adjacent; the alt ones last
     ++dp;
     alt += (int32_t)(hits[j] & 1u);
   }
@@ -198,6 +205,26 @@ __global__ void __launch_bounds__(256) read_end_kernel(int64_t n, const int32_t 
 // Records each pileup() call (bin) would fetch.  Bins are disjoint and sorted by (tid, start).  A read can only be
 // dropped in a bin that fetches more than max_depth records (the rule needs max_depth accepted reads alive), so
 // the host pre-pass below is skipped unless the add that crosses the cap raises *over.
+struct CandArgs {          // sparse path: slots per read = candidate sites inside [pos, reference end)
+  const uint64_t *site_key;
+  int64_t n_sites;
+  const int32_t *cell;
+  int32_t n_cells;
+  uint32_t *cand_cnt;      // null: bin counts only
+};
+
+__device__ __forceinline__ int64_t lower_key(const uint64_t *__restrict__ keys, int64_t n, uint64_t key) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    const int64_t m = (lo + hi) >> 1;
+    if (keys[m] < key)
+      lo = m + 1;
+    else
+      hi = m;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256) bin_fetch_count_kernel(int64_t n, const int32_t *__restrict__ tid,
                                                               const int32_t *__restrict__ pos,
                                                               const uint16_t *__restrict__ flag,
@@ -208,44 +235,60 @@ __global__ void __launch_bounds__(256) bin_fetch_count_kernel(int64_t n, const i
                                                               const int32_t *__restrict__ bstart,
                                                               const int32_t *__restrict__ bend, int min_mq,
                                                               uint32_t max_depth, uint32_t *__restrict__ bincount,
-                                                              uint32_t *__restrict__ over) {
+                                                              uint32_t *__restrict__ over, CandArgs ca) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int32_t t = tid[r];
-  if (t < 0 || !read_passes_engine(flag[r], mapq[r], min_mq)) return;
-  const int32_t p = pos[r];
-  int64_t lo = 0, hi = n_bins;  // first bin with (btid, bend) > (t, p)
-  while (lo < hi) {
-    const int64_t m = (lo + hi) >> 1;
-    const int32_t bt = btid[m];
-    if (bt < t || (bt == t && bend[m] <= p))
-      lo = m + 1;
-    else
-      hi = m;
+  uint32_t cand = 0;
+  if (t >= 0 && read_passes_engine(flag[r], mapq[r], min_mq)) {
+    const int32_t p = pos[r];
+    int64_t lo = n_bins;
+    if (n_bins > 0) {  // first bin with (btid, bend) > (t, p)
+      int64_t hi = n_bins;
+      lo = 0;
+      while (lo < hi) {
+        const int64_t m = (lo + hi) >> 1;
+        const int32_t bt = btid[m];
+        if (bt < t || (bt == t && bend[m] <= p))
+          lo = m + 1;
+        else
+          hi = m;
+      }
+      if (lo < n_bins && btid[lo] != t) lo = n_bins;
+    }
+    const bool want_cand = ca.cand_cnt && !(flag[r] & LS_FLAG_SUPPL) && ca.cell[r] >= 0 && ca.cell[r] < ca.n_cells;
+    if (lo < n_bins || want_cand) {
+      int32_t x = p;
+      for (uint32_t k = cigar_off[r]; k < cigar_off[r + 1]; ++k) {
+        const uint32_t c = cigar[k];
+        if (op_consumes_ref(c & 15u)) x += (int32_t)(c >> 4);
+      }
+      const int32_t e = x > p ? x : p + 1;
+      for (int64_t b = lo; b < n_bins && btid[b] == t && bstart[b] < e; ++b) {
+        const uint32_t old = atomicAdd(&bincount[b], 1u);
+        if (old == max_depth) *over = 1u;
+      }
+      if (want_cand && x > p) {
+        const uint64_t kt = (uint64_t)(uint32_t)t << 32;
+        cand = (uint32_t)(lower_key(ca.site_key, ca.n_sites, kt | (uint32_t)x) - lower_key(ca.site_key, ca.n_sites, kt | (uint32_t)p));
+      }
+    }
   }
-  if (lo >= n_bins || btid[lo] != t) return;
-  int32_t x = p;
-  for (uint32_t k = cigar_off[r]; k < cigar_off[r + 1]; ++k) {
-    const uint32_t c = cigar[k];
-    if (op_consumes_ref(c & 15u)) x += (int32_t)(c >> 4);
-  }
-  const int32_t e = x > p ? x : p + 1;
-  for (int64_t b = lo; b < n_bins && btid[b] == t && bstart[b] < e; ++b) {
-    const uint32_t old = atomicAdd(&bincount[b], 1u);
-    if (old == max_depth) *over = 1u;
-  }
+  if (ca.cand_cnt) ca.cand_cnt[r] = cand;
 }
 
 // Depth cap per pileup() call of the genotype scripts: one call per 50 kb bin of candidate sites
 // over [min-1, max+1) (SingleCellGenotype.py:110-124).  Same rule as ls_depth_cap_host.
 static int geno_depth_cap(ls_ctx *ctx, const std::vector<int32_t> &btid, const std::vector<int32_t> &bstart,
-                          const std::vector<int32_t> &bend, int min_mq, int max_depth) {
+                          const std::vector<int32_t> &bend, int min_mq, int max_depth, CandArgs ca = CandArgs{}) {
   const int64_t n = ctx->n_reads;
   ctx->n_drop = 0;
-  if (max_depth <= 0 || n <= (int64_t)max_depth) return LS_OK;
+  const bool cap_possible = max_depth > 0 && n > (int64_t)max_depth;
+  if (!cap_possible && !ca.cand_cnt) return LS_OK;
   cudaStream_t st = ctx->stream;
-  {  // device pre-count: does any bin fetch more than max_depth records at all?
-    const size_t nb = btid.size();
+  {  // device pre-count: does any bin fetch more than max_depth records at all?  (The same walk over the CIGARs gives
+     // the sparse path its per-read slot counts.)
+    const size_t nb = cap_possible ? btid.size() : 0;
     LS_CK(ctx->wcount.ensure(nb * 4 * 4 + 16));
     int32_t *d_bt = ctx->wcount.as<int32_t>(), *d_bs = d_bt + nb, *d_be = d_bs + nb;
     uint32_t *d_cnt = reinterpret_cast<uint32_t *>(d_be + nb);  // [nb] counts + 1 flag word
@@ -256,8 +299,9 @@ static int geno_depth_cap(ls_ctx *ctx, const std::vector<int32_t> &btid, const s
     bin_fetch_count_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
         n, ctx->tid.as<int32_t>(), ctx->pos.as<int32_t>(), ctx->flag.as<uint16_t>(), ctx->mapq.as<uint8_t>(),
         ctx->cigar_off.as<uint32_t>(), ctx->cigar.as<uint32_t>(), (int64_t)nb, d_bt, d_bs, d_be, min_mq,
-        (uint32_t)max_depth, d_cnt, d_cnt + nb);
+        (uint32_t)max_depth, d_cnt, d_cnt + nb, ca);
     LS_CK(cudaGetLastError());
+    if (!cap_possible) return LS_OK;
     uint32_t over = 0;
     LS_CK(cudaMemcpyAsync(&over, d_cnt + nb, 4, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
@@ -367,6 +411,7 @@ static void geno_fill_args(ls_ctx *ctx, GenoArgs &a, int64_t n_sites, int32_t n_
   a.hit_off = nullptr;
   a.hits = nullptr;
   a.hits32 = nullptr;
+  a.sentinel = 0;
   a.n_events = ctx->counters.as<unsigned long long>();
 }
 
@@ -403,8 +448,6 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
   if (rc != LS_OK) return rc;
   LS_CK(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  rc = geno_depth_cap(ctx, g.btid, g.bstart, g.bend, params->min_mq, params->max_depth);
-  if (rc != LS_OK) return rc;
   const int64_t n = ctx->n_reads;
   LS_CK(ctx->g_a.ensure((size_t)n_sites * 8));
   LS_CK(ctx->g_b.ensure((size_t)n_sites));
@@ -419,21 +462,28 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
   LS_CK(cudaMemsetAsync(ctx->counters.p, 0, 128, st));
   LS_CK(cudaMemsetAsync((uint32_t *)ctx->gs_cnt.p + n, 0, 4, st));
   LS_CK(cudaEventRecord(ctx->ev[0], st));
+  // One walk over the CIGARs: per-bin fetch counts for the depth cap and, per read, how many candidate sites lie
+  // inside [pos, reference end) -- an upper bound of its hits, which sizes its slots (the slots a read does not use
+  // are filled with a key that sorts behind every real one).  No separate counting pass over the bases.
+  CandArgs ca;
+  ca.site_key = ctx->g_a.as<uint64_t>();
+  ca.n_sites = n_sites;
+  ca.cell = ctx->cell.as<int32_t>();
+  ca.n_cells = n_cells;
+  ca.cand_cnt = ctx->gs_cnt.as<uint32_t>();
+  rc = geno_depth_cap(ctx, g.btid, g.bstart, g.bend, params->min_mq, params->max_depth, ca);
+  if (rc != LS_OK) return rc;
   GenoArgs a;
   geno_fill_args(ctx, a, n_sites, n_cells, params);
   unsigned long long *d_cnt = ctx->counters.as<unsigned long long>();
   uint64_t *d_nhits = reinterpret_cast<uint64_t *>(d_cnt + 1), *d_ntup = reinterpret_cast<uint64_t *>(d_cnt + 2);
   uint32_t *d_nbig = reinterpret_cast<uint32_t *>(d_cnt + 3);
   const unsigned grid = (unsigned)((n + 255) / 256);
-  // pass 1: hits per read, their exclusive scan places every read's hits
-  a.hit_cnt = ctx->gs_cnt.as<uint32_t>();
-  genotype_kernel<1><<<grid, 256, 0, st>>>(a);
   LS_CK(ls_scan_exclusive_u32(ctx->gs_cnt.as<uint32_t>(), ctx->gs_cnt.as<uint32_t>(), n + 1, d_nhits, ctx->scan_tmp, st));
   uint64_t h[4] = {0, 0, 0, 0};
   LS_CK(cudaMemcpyAsync(h, d_cnt, 32, cudaMemcpyDeviceToHost, st));
   LS_CK(cudaStreamSynchronize(st));
-  const int64_t nh = (int64_t)h[1];
-  S.n_events = nh;
+  const int64_t nh = (int64_t)h[1];  // slots (>= hits)
   int launches = 2;
   int64_t nt = 0;
   if (nh >= (int64_t)0xffffffffll) LS_FAIL(LS_E_ARG, "ls_genotype_sparse_run: more than 2^32 hits; split the site list");
@@ -454,31 +504,33 @@ extern "C" int ls_genotype_sparse_run(ls_ctx *ctx, const int32_t *site_tid, cons
     const int key_bits = ls_bits_for(key_span);
     uint64_t *sorted = nullptr;
     uint32_t *sorted32 = nullptr;
+    a.sentinel = key_span;
     if (k32) {
       genotype_kernel<3><<<grid, 256, 0, st>>>(a);
       LS_CK(ls_radix_sort_keys32(ctx->gs_hits_a.as<uint32_t>(), ctx->gs_hits_b.as<uint32_t>(), nh, key_bits, ctx->rs_hist,
                                  &sorted32, ctx->num_sms, st, &launches));
-      hit_flag_kernel<uint32_t><<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted32, nh, ctx->gs_flag.as<uint32_t>());
+      hit_flag_kernel<uint32_t><<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted32, nh, (uint32_t)key_span, ctx->gs_flag.as<uint32_t>());
     } else {
       genotype_kernel<2><<<grid, 256, 0, st>>>(a);
       LS_CK(ls_radix_sort_keys(ctx->gs_hits_a.as<uint64_t>(), ctx->gs_hits_b.as<uint64_t>(), nh, key_bits, ctx->rs_hist, &sorted,
                                ctx->num_sms, st, &launches));
-      hit_flag_kernel<uint64_t><<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>());
+      hit_flag_kernel<uint64_t><<<(unsigned)((nh + 1 + 255) / 256), 256, 0, st>>>(sorted, nh, key_span, ctx->gs_flag.as<uint32_t>());
     }
     LS_CK(ls_scan_exclusive_u32(ctx->gs_flag.as<uint32_t>(), ctx->gs_flag.as<uint32_t>(), nh + 1, d_ntup, ctx->scan_tmp, st));
     LS_CK(cudaMemcpyAsync(h, d_cnt, 32, cudaMemcpyDeviceToHost, st));
     LS_CK(cudaStreamSynchronize(st));
     nt = (int64_t)h[2];
+    S.n_events = (int64_t)h[0];  // real hits
     LS_CK(ctx->gs_tup.ensure((size_t)nt * 5 * 4 + 16));
     LS_CK(ctx->gs_p.ensure((size_t)nt * 8 + 16));
     int32_t *t_site = ctx->gs_tup.as<int32_t>(), *t_cell = t_site + nt, *t_dp = t_cell + nt, *t_alt = t_dp + nt,
             *t_k = t_alt + nt;
     const uint8_t *d_skip = skip_p ? ctx->gs_skip.as<uint8_t>() : nullptr;
     if (k32)
-      hit_reduce_kernel<uint32_t><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted32, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
+      hit_reduce_kernel<uint32_t><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted32, nh, (uint32_t)key_span, ctx->gs_flag.as<uint32_t>(), n_cells,
                                                                                 d_skip, t_site, t_cell, t_dp, t_alt, t_k);
     else
-      hit_reduce_kernel<uint64_t><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted, nh, ctx->gs_flag.as<uint32_t>(), n_cells,
+      hit_reduce_kernel<uint64_t><<<(unsigned)((nh + 255) / 256), 256, 0, st>>>(sorted, nh, key_span, ctx->gs_flag.as<uint32_t>(), n_cells,
                                                                                 d_skip, t_site, t_cell, t_dp, t_alt, t_k);
     launches += 4;
     LS_CK(cudaGetLastError());
@@ -623,6 +675,7 @@ extern "C" int ls_genotype_count(ls_ctx *ctx, const int32_t *site_tid, const int
   a.hit_off = nullptr;
   a.hits = nullptr;
   a.hits32 = nullptr;
+  a.sentinel = 0;
   if (ctx->n_reads > 0) genotype_kernel<0><<<(unsigned)((ctx->n_reads + 255) / 256), 256, 0, st>>>(a);
   LS_CK(cudaGetLastError());
   LS_CK(cudaEventRecord(ctx->ev[2], st));
