@@ -69,6 +69,31 @@ int ls_bams_fill2(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *
  * inflates to exactly out_len bytes, 0 otherwise (the readers then hand the member to zlib).  Exposed for tests. */
 int ls_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
 
+/* ---- BaseCellCalling.step1: the per-row work ----------------------------------------------------------- */
+/* Replaces the row loop of BaseCellCalling.step1.py:78-467 around the beta-binomial calls (which stay on the GPU, K2).
+ * ls_s1_parse reads a byte range of the merged table (whole lines; "\n", "\r\n" and "\r" end a line; "##" lines are
+ * copied through): ct_cols = the columns of the cell types.  It returns NULL with a message in err for any row the
+ * reference would fail on -- the caller then runs its Python restatement on the range, whose exceptions are the
+ * reference's.  Queries: q1 = (alt reads, depth) with alpha1/beta1, q2 = (alt cells, cells) with alpha2/beta2, in the
+ * order the handle expects their ROUNDED tails back in ls_s1_format.  ls_s1_sites gives (contig id, POS) per row
+ * (id -1 for a "##" line) for the reference-context lookup: ctx[row][11] = fetch(CHROM, POS-6, POS+5) upper-cased,
+ * ctx_len[row] = bytes that exist, -1 = no context ('.').  --fisher_cutoff != 1 is not handled here.
+ * `data` must stay valid until ls_s1_free; the text of ls_s1_format belongs to the handle. */
+void *ls_s1_parse(const char *data, int64_t len, const int32_t *ct_cols, int32_t n_ct, int32_t min_reads,
+                  int32_t min_cells, char *err, int32_t errlen);
+void ls_s1_free(void *h);
+int64_t ls_s1_n_rows(void *h);
+int64_t ls_s1_n_data_rows(void *h);
+int64_t ls_s1_n_q1(void *h);
+int64_t ls_s1_n_q2(void *h);
+void ls_s1_queries(void *h, int32_t *q1k, int32_t *q1n, int32_t *q2k, int32_t *q2n);
+int32_t ls_s1_n_chroms(void *h);
+const char *ls_s1_chrom(void *h, int32_t i);
+void ls_s1_sites(void *h, int32_t *chrom, int64_t *pos);
+int64_t ls_s1_format(void *h, const double *r1, const double *r2, const uint8_t *ctx, const int8_t *ctx_len,
+                     const char *const *ct_names, int32_t min_ac_cells, int32_t min_ac_reads, int32_t min_cell_types,
+                     int32_t max_cell_types, const char **text);
+
 /* ---- SplitBamCellTypes --------------------------------------------------------------------------- */
 /* Routes every placed record of the coordinate-sorted BAM in_path to out_paths[type of its barcode]
  * (+ ".bai" each).  Barcode table: n_bc keys, key i = bc_blob[bc_off[i] .. bc_off[i+1]), type bc_type[i];

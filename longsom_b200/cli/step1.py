@@ -294,6 +294,112 @@ def _format_rows(rows, r1, r2, P):
     return lines
 
 
+# ---- native row passes (liblongsom_host.so, csrc/host/ls_step1.cpp) -------------------------------------------
+# The two per-row passes above restated in C++: a byte range of the table in, queries out; rounded tails in, output
+# text out.  Anything the strict native parser refuses (a row the reference itself would fail on) and the strand-bias
+# column (--fisher_cutoff != 1) go through the Python passes above, which stay the statement of the reference's
+# behaviour; LONGSOM_STEP1_NATIVE=0 switches the native path off.
+def _s1_lib():
+    import ctypes as C
+    lib = bamio._load_host()
+    if not getattr(lib, "_s1_ready", False):
+        lib.ls_s1_parse.restype = C.c_void_p
+        lib.ls_s1_parse.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_char_p, C.c_int32]
+        lib.ls_s1_free.argtypes = [C.c_void_p]
+        for f in ("ls_s1_n_rows", "ls_s1_n_data_rows", "ls_s1_n_q1", "ls_s1_n_q2"):
+            getattr(lib, f).restype = C.c_int64
+            getattr(lib, f).argtypes = [C.c_void_p]
+        lib.ls_s1_queries.argtypes = [C.c_void_p] * 5
+        lib.ls_s1_n_chroms.restype = C.c_int32
+        lib.ls_s1_n_chroms.argtypes = [C.c_void_p]
+        lib.ls_s1_chrom.restype = C.c_char_p
+        lib.ls_s1_chrom.argtypes = [C.c_void_p, C.c_int32]
+        lib.ls_s1_sites.argtypes = [C.c_void_p] * 3
+        lib.ls_s1_format.restype = C.c_int64
+        lib.ls_s1_format.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        lib._s1_ready = True
+    return lib
+
+
+class _NativeRange:
+    """One byte range of the table held by the native parser."""
+
+    def __init__(self, data, cell_types_idx, P):
+        import ctypes as C
+        self.C, self.lib = C, _s1_lib()
+        self.data = data                      # keeps the bytes alive: the handle points into them
+        self.cols = np.array(sorted(cell_types_idx), np.int32)
+        self.names = [cell_types_idx[int(c)].encode() for c in self.cols]
+        err = C.create_string_buffer(256)
+        self.h = self.lib.ls_s1_parse(C.c_char_p(data), len(data), self.cols.ctypes.data, len(self.cols), int(P.min_reads),
+                                      int(P.min_cells), err, 256)
+        if not self.h:
+            raise ValueError(err.value.decode())
+        n1, n2 = self.lib.ls_s1_n_q1(self.h), self.lib.ls_s1_n_q2(self.h)
+        self.q = tuple(np.zeros(n, np.int32) for n in (n1, n1, n2, n2))
+        self.lib.ls_s1_queries(self.h, *[a.ctypes.data for a in self.q])
+        self.n_rows = self.lib.ls_s1_n_rows(self.h)
+        self.n_data = self.lib.ls_s1_n_data_rows(self.h)
+
+    def contexts(self, fa):
+        """ctx[row][11], ctx_len[row] = fa.fetch(CHROM, POS - 6, POS + 5).upper() of every row; -1 where the reference
+        prints '.' (no FASTA, unknown contig, POS < 6: the bare except at step1.py:97-104)."""
+        n = self.n_rows
+        ctx, clen = np.zeros((n, 11), np.uint8), np.full(n, -1, np.int8)
+        if fa is None or n == 0:
+            return ctx, clen
+        chrom, pos = np.zeros(n, np.int32), np.zeros(n, np.int64)
+        self.lib.ls_s1_sites(self.h, chrom.ctypes.data, pos.ctypes.data)
+        offs = np.arange(11, dtype=np.int64)
+        for ci in range(self.lib.ls_s1_n_chroms(self.h)):
+            name = self.lib.ls_s1_chrom(self.h, ci).decode()
+            try:
+                seq = fa.contig(name)
+            except Exception:
+                continue
+            rows = np.nonzero((chrom == ci) & (pos >= 6))[0]
+            if rows.shape[0] == 0:
+                continue
+            start = pos[rows] - 6
+            L = np.clip(seq.shape[0] - start, 0, 11)
+            idx = np.minimum(start[:, None] + offs[None, :], max(seq.shape[0] - 1, 0))
+            block = seq[idx] if seq.shape[0] else np.zeros((rows.shape[0], 11), np.uint8)
+            lower = (block >= 97) & (block <= 122)
+            block = np.where(lower, block - 32, block).astype(np.uint8)
+            block[offs[None, :] >= L[:, None]] = 0
+            ctx[rows] = block
+            clen[rows] = L.astype(np.int8)
+        return ctx, clen
+
+    def format(self, r1, r2, fa, P):
+        """Output text of the range as a buffer that lives in the native handle (valid until close())."""
+        C = self.C
+        ctx_p = clen_p = None
+        if fa is not None:
+            ctx, clen = self.contexts(fa)
+            ctx_p, clen_p = ctx.ctypes.data, clen.ctypes.data
+        r1 = np.ascontiguousarray(r1, np.float64)
+        r2 = np.ascontiguousarray(r2, np.float64)
+        names = (C.c_char_p * max(1, len(self.names)))(*self.names)
+        text = C.c_void_p()
+        n = self.lib.ls_s1_format(self.h, r1.ctypes.data, r2.ctypes.data, ctx_p, clen_p, names,
+                                  int(P.min_ac_cells), int(P.min_ac_reads), int(P.min_cell_types), int(P.max_cell_types),
+                                  C.byref(text))
+        if n < 0:   # a NaN among the per-allele tails (min() over NaNs is order dependent), or > 64 calls in a row
+            raise ValueError("ls_s1_format: left to the Python passes")
+        return (C.c_char * n).from_address(text.value) if n else b""
+
+    def close(self):
+        if self.h:
+            self.lib.ls_s1_free(self.h)
+            self.h = None
+
+
+def _native_ok(P):
+    return P.fisher_cutoff == 1 and os.environ.get("LONGSOM_STEP1_NATIVE", "1") != "0"
+
+
 # ---- worker processes: the per-row Python of both passes is the cost of this step (tens of microseconds per row, the
 # GPU tails are milliseconds), so large tables are cut into byte ranges handled by forked workers; each parses its
 # range, sends its queries, receives its tails, formats its lines.  The order of the output is the order of the ranges.
@@ -351,6 +457,19 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
             continue
         break
     body_bytes = os.path.getsize(infile) - body_start
+    native = None
+    if _native_ok(P) and cell_types_idx is not None and body_bytes > 0:
+        from concurrent.futures import ThreadPoolExecutor
+        nthr = 1 if body_bytes < (4 << 20) else min(16, _available_cpus())
+        try:
+            def parse(rng):
+                with open(infile, 'rb') as f:
+                    f.seek(rng[0])
+                    return _NativeRange(f.read(rng[1] - rng[0]), cell_types_idx, P)
+            with ThreadPoolExecutor(nthr) as ex:
+                native = list(ex.map(parse, _line_aligned_ranges(infile, body_start, nthr)))
+        except ValueError:
+            native = None    # a row the native parser refuses: the Python passes (and their exceptions) take the table
     if procs is None:
         procs = int(os.environ.get("LONGSOM_PROCS", "0") or 0)   # an explicit setting is honoured as is
         if procs <= 0:
@@ -375,6 +494,40 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
         p2 = eng.betabinom_sf(q[2], q[3], alpha2, beta2)
         # == round(np.float64, 4) of the reference, element-wise
         return np.round(p1, 4), np.round(p2, 4)
+
+    if native is not None:
+        # native row passes: parse the ranges on threads (the library releases the GIL), one K2 call for all their
+        # queries, format on threads, write in order
+        from concurrent.futures import ThreadPoolExecutor
+        fa = bamio.Fasta(fasta) if fasta is not None else None
+        try:
+            qs = [r.q for r in native]
+            r1, r2 = tails(tuple(np.concatenate([q[j] for q in qs]) if qs else np.zeros(0, np.int32) for j in range(4)))
+            o1 = np.concatenate([[0], np.cumsum([len(q[0]) for q in qs])]).astype(np.int64)
+            o2 = np.concatenate([[0], np.cumsum([len(q[2]) for q in qs])]).astype(np.int64)
+            if fa is not None:     # contigs are loaded once, before the threads share the reader
+                for r in native:
+                    for ci in range(r.lib.ls_s1_n_chroms(r.h)):
+                        try:
+                            fa.contig(r.lib.ls_s1_chrom(r.h, ci).decode())
+                        except Exception:
+                            pass
+            with ThreadPoolExecutor(max(1, len(native))) as ex:
+                texts = list(ex.map(lambda kr: kr[1].format(r1[o1[kr[0]]:o1[kr[0] + 1]], r2[o2[kr[0]]:o2[kr[0] + 1]], fa, P),
+                                    enumerate(native)))
+            with open(outfile, 'wb') as out:
+                out.write("".join(out_lines).encode())
+                for t in texts:
+                    out.write(t)
+            return sum(r.n_rows for r in native), len(r1) + len(r2)
+        except ValueError:
+            pass   # fall through to the Python passes
+        finally:
+            for r in native:
+                r.close()
+            if fa is not None:
+                fa.close()
+        procs = 1 if procs is None or procs <= 1 else procs
 
     if procs <= 1:
         fa = bamio.Fasta(fasta) if fasta is not None else None
