@@ -94,6 +94,18 @@ int64_t ls_s1_format(void *h, const double *r1, const double *r2, const uint8_t 
                      const char *const *ct_names, int32_t min_ac_cells, int32_t min_ac_reads, int32_t min_cell_types,
                      int32_t max_cell_types, const char **text);
 
+/* ---- SingleCellGenotype / HCCVSingleCellGenotype: the dense long table ------------------------------------ */
+/* Expands the touched (site, cell) tuples of ls_genotype_sparse_* into the reference's rows, one per (site, barcode of
+ * the metadata) -- SingleCellGenotype.py:128-214, HCCVSingleCellGenotype.py:126-212.  prefix[s]: the seven leading
+ * columns of site s, tab-joined; index[s]: its INDEX column (NULL array when hccv); chrm[s]: the chrM shortcut applies;
+ * the site's tuples are [hit_lo[s], hit_hi[s]) of the arrays, sorted by cell, p rounded to four places;
+ * cell_text[c] = "barcode<tab>cell type".  Returns the text length (>= 0) and a malloc'd text (ls_geno_rows_free). */
+int64_t ls_geno_rows(int32_t n_sites, const char *const *prefix, const char *const *index, const uint8_t *chrm,
+                     const int64_t *hit_lo, const int64_t *hit_hi, const int32_t *t_cell, const int32_t *t_dp,
+                     const int32_t *t_alt, const double *t_p, int32_t n_cells, const char *const *cell_text, int32_t hccv,
+                     double pvalue, char **text);
+void ls_geno_rows_free(char *text);
+
 /* ---- SplitBamCellTypes --------------------------------------------------------------------------- */
 /* Routes every placed record of the coordinate-sorted BAM in_path to out_paths[type of its barcode]
  * (+ ".bai" each).  Barcode table: n_bc keys, key i = bc_blob[bc_off[i] .. bc_off[i+1]), type bc_type[i];

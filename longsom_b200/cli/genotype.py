@@ -124,20 +124,63 @@ def genotype(args, hccv):
             site_tid, site_pos, alt_cls, n_cells, args.alpha2, args.beta2, skip_p=skip, min_bq=args.min_bq,
             min_mq=args.min_mq, max_depth=200000, alt_only=(args.alt_flag != 'All'), bin_size=args.bin)
     t_p = np.round(t_p, 4)
-    # per site: {cell: (Dp, Alt, BetaBin)}
-    touched = [None] * len(keys)
     bounds = np.searchsorted(t_site, np.arange(len(keys) + 1))
-    tc, td, ta, tp = t_cell.tolist(), t_dp.tolist(), t_alt.tolist(), t_p.tolist()
-    for r in range(len(keys)):
-        lo_, hi_ = int(bounds[r]), int(bounds[r + 1])
-        if hi_ > lo_:
-            touched[r] = {tc[i]: (td[i], ta[i], tp[i]) for i in range(lo_, hi_)}
+    native = os.environ.get("LONGSOM_GENO_NATIVE", "1") != "0"
+    touched = [None] * len(keys)
+    if not native:
+        # per site: {cell: (Dp, Alt, BetaBin)}
+        tc, td, ta, tp = t_cell.tolist(), t_dp.tolist(), t_alt.tolist(), t_p.tolist()
+        for r in range(len(keys)):
+            lo_, hi_ = int(bounds[r]), int(bounds[r + 1])
+            if hi_ > lo_:
+                touched[r] = {tc[i]: (td[i], ta[i], tp[i]) for i in range(lo_, hi_)}
+    else:
+        import ctypes as C
+        host = bamio._load_host()
+        host.ls_geno_rows.restype = C.c_int64
+        host.ls_geno_rows.argtypes = [C.c_int32] + [C.c_void_p] * 9 + [C.c_int32, C.c_void_p, C.c_int32, C.c_double, C.c_void_p]
+        host.ls_geno_rows_free.argtypes = [C.c_void_p]
+        t_cell = np.ascontiguousarray(t_cell, np.int32)
+        t_dp = np.ascontiguousarray(t_dp, np.int32)
+        t_alt = np.ascontiguousarray(t_alt, np.int32)
+        t_p = np.ascontiguousarray(t_p, np.float64)
+        cell_text = (C.c_char_p * max(1, n_cells))(*[(bc + '\t' + meta_dict[bc]).encode() for bc in barcodes])
 
     # ---- rows, in the reference's order ------------------------------------------------------------
     blocks = {}
     for chrom, target in bin_info:
         sites = set(target.keys())  # same construction as the reference => same iteration order
         lo, hi = min(sites), max(sites)
+        if native:
+            # the dense rows are expanded from the touched pairs by the native writer (csrc/host/ls_genorows.cpp)
+            order = list(sites)  # CELLS dict comprehension iterates the set (:130)
+            ns = len(order)
+            prefix, index = [], []
+            chrm = np.zeros(ns, np.uint8)
+            hlo, hhi = np.zeros(ns, np.int64), np.zeros(ns, np.int64)
+            for j, POS in enumerate(order):
+                Ref_exp, Alt_exp, Cell_type_exp, Num_cells_exp = target[POS]
+                prefix.append('\t'.join([str(chrom), str(POS + 1), str(POS + 1), Ref_exp, Alt_exp, str(Cell_type_exp),
+                                         str(Num_cells_exp)]).encode())
+                index.append((str(chrom) + ':' + str(POS + 1) + ':' + Alt_exp.split(',')[0]).encode())
+                chrm[j] = 1 if (args.chrM_contaminant == 'True' and str(chrom) == 'chrM') else 0
+                r = row_of.get((tid_of.get(chrom, -1), POS))
+                if r is not None:
+                    hlo[j], hhi[j] = bounds[r], bounds[r + 1]
+            pre_a = (C.c_char_p * max(1, ns))(*prefix)
+            idx_a = None if hccv else (C.c_char_p * max(1, ns))(*index)
+            text = C.c_void_p()
+            n = host.ls_geno_rows(ns, pre_a, idx_a, chrm.ctypes.data, hlo.ctypes.data, hhi.ctypes.data, t_cell.ctypes.data,
+                                  t_dp.ctypes.data, t_alt.ctypes.data, t_p.ctypes.data, n_cells, cell_text, 1 if hccv else 0,
+                                  float(args.pvalue), C.byref(text))
+            if n < 0:
+                raise RuntimeError("ls_geno_rows failed (%d)" % n)
+            try:
+                blocks[(str(chrom), lo)] = [C.string_at(text.value, n)] if n else []
+            finally:
+                if n >= 0 and text.value:
+                    host.ls_geno_rows_free(text)
+            continue
         rows = []
         for POS in sites:  # CELLS dict comprehension iterates the set (:130)
             Ref_exp, Alt_exp, Cell_type_exp, Num_cells_exp = target[POS]
@@ -167,7 +210,7 @@ def genotype(args, hccv):
                 if not hccv:
                     BIN = 1 if MUTATED == "PASS" else (3 if MUTATED == "NoCoverage" else 0)
                     group += [str(BIN), str(chrom) + ':' + str(POS + 1) + ':' + Alt_exp.split(',')[0]]
-                rows.append('\t'.join(group) + '\n')
+                rows.append(('\t'.join(group) + '\n').encode())
         # temp file CHROM_min_max; a later bin with the same name overwrites an earlier one (:117-120)
         blocks[(str(chrom), lo)] = rows
     header = ['#CHROM', 'Start', 'End', 'REF', 'ALT_expected', 'Cell_type_expected', 'Num_cells_expected', 'CB',
@@ -176,8 +219,8 @@ def genotype(args, hccv):
         header += ['BinMutationStatus', 'INDEX']
     long_path = args.outfile if hccv else args.outfile + '.SingleCellGenotype.tsv'
     if blocks:
-        with open(long_path, 'w') as out:
-            out.write('\t'.join(header) + '\n')
+        with open(long_path, 'wb') as out:
+            out.write(('\t'.join(header) + '\n').encode())
             for chrom in sorted({k[0] for k in blocks}):
                 for start in sorted(k[1] for k in blocks if k[0] == chrom):
                     out.writelines(blocks[(chrom, start)])
