@@ -69,6 +69,14 @@ int ls_bams_fill2(void *h, int32_t *tid, int32_t *pos, uint16_t *flag, uint8_t *
  * inflates to exactly out_len bytes, 0 otherwise (the readers then hand the member to zlib).  Exposed for tests. */
 int ls_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
 
+/* ---- MergeBaseCellCounts ------------------------------------------------------------------------------------ */
+/* The lock-step cursor merge of MergeBaseCellCounts.py:116-204 over n (chrom, pos)-sorted BaseCellCounter tables: `header`
+ * (date line, ##INFO lines, column names) is written first, n_header_lines (9) lines are skipped at the top of every
+ * input.  Returns 0; 1 when a row is not "chrom<tab>integer<tab>ref<tab>info<tab>counts" (the caller then runs its Python
+ * restatement, whose exceptions are the reference's); -1 on an I/O error (err). */
+int ls_merge_tables(int32_t n, const char *const *paths, const char *out_path, const char *header, int32_t n_header_lines,
+                    char *err, int32_t errlen);
+
 /* ---- BaseCellCalling.step1: the per-row work ----------------------------------------------------------- */
 /* Replaces the row loop of BaseCellCalling.step1.py:78-467 around the beta-binomial calls (which stay on the GPU, K2).
  * ls_s1_parse reads a byte range of the merged table (whole lines; "\n", "\r\n" and "\r" end a line; "##" lines are

@@ -65,15 +65,28 @@ def merge_cell_types_files(infiles, outfile):
     (MergeBaseCellCounts.py:116-204): chromosomes in lexicographic order, positions ascending, 'NA' where a cell type
     lacks the site."""
     header = ['#CHROM', 'Start', 'End', 'REF', 'INFO']
-    cursors = []
     for path in infiles:
         header.append(os.path.basename(path).split('.')[-2])
-        cursors.append(_Cursor(path))
+    head_text = "##fileDate=%s\n" % time.strftime("%d/%m/%Y") + COUNTER_CONCEPTS + '\n' + '\t'.join(header) + '\n'
+    if os.environ.get("LONGSOM_MERGE_NATIVE", "1") != "0":
+        # the same cursor loop in native code (csrc/host/ls_merge.cpp); rows its strict parser refuses leave the table to
+        # the Python loop below, whose exceptions are the reference's
+        import ctypes as C
+        from .. import bamio
+        host = bamio._load_host()
+        host.ls_merge_tables.restype = C.c_int
+        host.ls_merge_tables.argtypes = [C.c_int32, C.c_void_p, C.c_char_p, C.c_char_p, C.c_int32, C.c_char_p, C.c_int32]
+        paths = (C.c_char_p * max(1, len(infiles)))(*[os.fsencode(p) for p in infiles])
+        err = C.create_string_buffer(256)
+        rc = host.ls_merge_tables(len(infiles), paths, os.fsencode(outfile), head_text.encode(), HEADER_LINES, err, 256)
+        if rc == 0:
+            return
+        if rc < 0:
+            raise IOError("MergeBaseCellCounts: " + err.value.decode())
+    cursors = [_Cursor(path) for path in infiles]
     cur_chr, cur_pos = 1, 0
     with open(outfile, 'w') as out:
-        out.write("##fileDate=%s\n" % time.strftime("%d/%m/%Y"))
-        out.write(COUNTER_CONCEPTS + '\n')
-        out.write('\t'.join(header) + '\n')
+        out.write(head_text)
         while not all(c.done for c in cursors):
             for c in cursors:
                 while c.chrom == cur_chr and c.pos <= cur_pos:
