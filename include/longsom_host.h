@@ -114,6 +114,18 @@ int64_t ls_geno_rows(int32_t n_sites, const char *const *prefix, const char *con
                      double pvalue, char **text);
 void ls_geno_rows_free(char *text);
 
+/* ---- BaseCellCalling.step2: site lists ------------------------------------------------------------------------ */
+/* The editing / panel-of-normals lists of build_dict (BaseCellCalling.step2.py:197-221): tab separated, '#' comments,
+ * columns chrom, pos.  ls_sitelist_read: 0 = parsed (handle in *h), 1 = a line the reference's loop would treat
+ * differently (the caller runs its Python loop, which empties the list on any failure), -1 = unreadable file.
+ * ls_sitelist_fill: per row the index of its chromosome name (ls_sitelist_chrom) and its position. */
+int ls_sitelist_read(const char *path, void **h);
+int64_t ls_sitelist_n(void *h);
+int32_t ls_sitelist_n_chroms(void *h);
+const char *ls_sitelist_chrom(void *h, int32_t i);
+void ls_sitelist_fill(void *h, int32_t *chrom, int64_t *pos);
+void ls_sitelist_free(void *h);
+
 /* ---- SplitBamCellTypes --------------------------------------------------------------------------- */
 /* Routes every placed record of the coordinate-sorted BAM in_path to out_paths[type of its barcode]
  * (+ ".bai" each).  Barcode table: n_bc keys, key i = bc_blob[bc_off[i] .. bc_off[i+1]), type bc_type[i];

@@ -35,6 +35,49 @@ def read_site_list(path):
     return out
 
 
+def site_list_keys(path, key_ids):
+    """uint64 keys (contig id << 32 | pos) of an editing / PoN list, read by the native parser
+    (csrc/host/ls_sitelist.cpp); key_ids(names) -> contig ids shared with the candidates.  Lines the native parser
+    refuses go through read_site_list, so that the reference's failure rule (Q9) decides."""
+    import ctypes as C
+    from .. import bamio
+    if os.environ.get("LONGSOM_STEP2_NATIVE", "1") != "0":
+        host = bamio._load_host()
+        host.ls_sitelist_read.restype = C.c_int
+        host.ls_sitelist_read.argtypes = [C.c_char_p, C.c_void_p]
+        host.ls_sitelist_n.restype = C.c_int64
+        host.ls_sitelist_n.argtypes = [C.c_void_p]
+        host.ls_sitelist_n_chroms.restype = C.c_int32
+        host.ls_sitelist_n_chroms.argtypes = [C.c_void_p]
+        host.ls_sitelist_chrom.restype = C.c_char_p
+        host.ls_sitelist_chrom.argtypes = [C.c_void_p, C.c_int32]
+        host.ls_sitelist_fill.argtypes = [C.c_void_p] * 3
+        host.ls_sitelist_free.argtypes = [C.c_void_p]
+        h = C.c_void_p()
+        rc = host.ls_sitelist_read(os.fsencode(path) if path else b"", C.byref(h))
+        if rc == 0:
+            try:
+                n = host.ls_sitelist_n(h)
+                chrom, pos = np.zeros(n, np.int32), np.zeros(n, np.int64)
+                host.ls_sitelist_fill(h, chrom.ctypes.data, pos.ctypes.data)
+                names = [host.ls_sitelist_chrom(h, i).decode() for i in range(host.ls_sitelist_n_chroms(h))]
+            finally:
+                host.ls_sitelist_free(h)
+            gid = np.array(key_ids(names), np.uint64) if names else np.zeros(0, np.uint64)
+            ok = (pos >= 0) & (pos < (1 << 32))
+            return (gid[chrom[ok]] << np.uint64(32)) | pos[ok].astype(np.uint64)
+        if rc < 0:
+            return np.zeros(0, np.uint64)   # unreadable: the reference's bare except leaves the filter empty
+    sites = read_site_list(path)
+    ids = {}
+    for c, _p in sites:
+        if c not in ids:
+            ids[c] = None
+    names = list(ids)
+    gid = dict(zip(names, key_ids(names)))
+    return np.array([(gid[c] << 32) | p for c, p in sites if 0 <= p < (1 << 32)], np.uint64)
+
+
 class GnomadTable:
     """Stand-in provider for gnomad_db.database.gnomAD_DB (step2.py:100-108) when that package is
     not installed: a TSV of chrom, pos, ref, alt, AF.  Unknown variants -> NaN (then 0)."""
@@ -79,10 +122,11 @@ def variant_calling_step2(infile, distance, editing, pon_SR, pon_LR, gnomAD_db, 
                 else:
                     comments.append(line)
                 continue
-            elements = line.rstrip('\n').split('\t')
-            # awk prefilter of the reference: keep rows with $5 != "." and $6 != "."
-            if len(elements) > 5 and elements[4] != "." and elements[5] != ".":
-                cands.append(elements)
+            # awk prefilter of the reference: keep rows with $5 != "." and $6 != ".".  Almost every row of a step1
+            # table fails it, so only the first six columns are cut out before the row is split in full.
+            head = line.rstrip('\n').split('\t', 6)
+            if len(head) > 5 and head[4] != "." and head[5] != ".":
+                cands.append(line.rstrip('\n').split('\t'))
 
     # ---- K3: membership of every candidate in the three site lists, on the GPU -----------------
     chrom_id = {}
@@ -93,8 +137,7 @@ def variant_calling_step2(infile, distance, editing, pon_SR, pon_LR, gnomAD_db, 
     qkeys = np.array([key_of(c[0], int(c[1])) for c in cands], np.uint64)
     hits = []
     for path in (editing, pon_SR, pon_LR):
-        sites = read_site_list(path)
-        keys = np.array([key_of(c, p) for c, p in sites if 0 <= p < (1 << 32)], np.uint64)
+        keys = site_list_keys(path, lambda names: [chrom_id.setdefault(n, len(chrom_id)) for n in names])
         hits.append(engine.site_mask(keys, qkeys) if len(cands) else np.zeros(0, np.uint8))
     EDIT, PSR, PLR = hits
 

@@ -76,3 +76,34 @@ def test_malformed_rows_are_left_to_the_python_loop(tmp_path):
         assert _native(files, str(tmp_path / "o.tsv")) == 1, name
         with pytest.raises(ValueError):
             merge.merge_cell_types_files(files, str(tmp_path / "o2.tsv"))
+
+
+def test_site_list_reader_native_equals_python(tmp_path, monkeypatch):
+    """step2's editing / PoN lists (BaseCellCalling.step2.py:197-221): the native reader and the Python loop give the same
+    key set; a list the reference's loop fails on (and so empties) is empty either way."""
+    from longsom_b200.cli import step2
+    rng = np.random.default_rng(8)
+    good = str(tmp_path / "sites.tsv")
+    with open(good, "w", newline="") as f:
+        f.write("#chrom\tpos\tinfo\n")
+        for i in range(20000):
+            ch = "chr%s" % rng.choice(["1", "2", "10", "X", "Un_gl000220"])
+            pos = int(rng.integers(-5, 1 << 33)) if i % 97 == 0 else int(rng.integers(0, 250_000_000))
+            end = "\r\n" if i % 3 == 0 else "\n"
+            f.write(("%s\t%d\tx\ty" % (ch, pos) if i % 2 else "%s\t%d" % (ch, pos)) + end)
+            if i == 5000:
+                f.write("# a comment in the middle\n")
+
+    def keys(path, native):
+        monkeypatch.setenv("LONGSOM_STEP2_NATIVE", "1" if native else "0")
+        ids = {}
+        k = step2.site_list_keys(path, lambda names: [ids.setdefault(n, len(ids)) for n in names])
+        inv = {v: n for n, v in ids.items()}
+        return sorted((inv[int(x) >> 32], int(x) & 0xffffffff) for x in k.tolist())
+    a, b = keys(good, True), keys(good, False)
+    assert a == b and len(a) > 19000
+    for name, bad_line in (("one column", "chr1\n"), ("text position", "chr1\tabc\n"), ("empty line", "\n")):
+        bad = str(tmp_path / "bad.tsv")
+        open(bad, "w").write(open(good).read() + bad_line)
+        assert keys(bad, True) == [] and keys(bad, False) == [], name
+    assert keys(str(tmp_path / "missing.tsv"), True) == [] and keys(str(tmp_path / "missing.tsv"), False) == []
