@@ -69,6 +69,8 @@ struct Chunk {
   size_t tail_lo = 0;                 // first byte of raw not covered by a complete record
   std::vector<const uint8_t *> recs;  // records (pointers into raw, past block_size)
   std::vector<const char *> cbp;      // their CB:Z texts (or nullptr)
+  std::vector<uint64_t> cbh;          // ... and the hashes of those texts
+  std::vector<uint32_t> ncig, lseq;   // n_cigar_op / l_seq of every record (read once, in parallel)
   std::vector<uint32_t> cig_off;
   std::vector<uint64_t> base_off;
   std::vector<int32_t> cb;
@@ -90,8 +92,7 @@ struct BarcodeTable {
     for (; *s; ++s) h = (h ^ (uint8_t)*s) * 1099511628211ull;
     return h;
   }
-  int32_t intern(const char *s) {
-    const uint64_t h = fnv(s);
+  int32_t intern(const char *s, uint64_t h) {
     size_t m = slot.size() - 1, i = (size_t)h & m;
     for (;; i = (i + 1) & m) {
       const int32_t id = slot[i];
@@ -125,7 +126,7 @@ struct Stream {
   std::string err;
   FILE *f = nullptr;
   int threads = 1;
-  double t_read = 0, t_inflate = 0, t_index = 0, t_fill = 0, t_wait = 0;  // LS_BAM_TIMING
+  double t_read = 0, t_inflate = 0, t_index = 0, t_tags = 0, t_intern = 0, t_fill = 0, t_wait = 0;  // LS_BAM_TIMING
   bool header_done = false, eof = false;
   std::vector<std::string> contig_names;
   std::vector<int32_t> contig_lens;
@@ -408,6 +409,9 @@ void produce(Stream *s, Chunk &dst, const Chunk &prev, size_t target) {
   dst.base_off.resize((size_t)n + 1);
   dst.cb.resize((size_t)n);
   dst.cbp.resize((size_t)n);
+  dst.cbh.resize((size_t)n);
+  dst.ncig.resize((size_t)n);
+  dst.lseq.resize((size_t)n);
   // per record, in parallel: field check and the CB tag's text (each record's aux block is a cache miss)
   std::atomic<int64_t> nx(0);
   std::atomic<int> bad(0);
@@ -420,12 +424,16 @@ void produce(Stream *s, Chunk &dst, const Chunk &prev, size_t target) {
         const uint64_t bs = rd32(r - 4);
         const uint64_t l_name = r[8], n_cig = rd16(r + 12), l_seq = rd32(r + 16);
         const uint64_t fixed = 32 + l_name + 4 * n_cig + (l_seq + 1) / 2 + l_seq;
+        dst.ncig[(size_t)i] = (uint32_t)n_cig;
+        dst.lseq[(size_t)i] = (uint32_t)l_seq;
         if (fixed > bs) {
           bad = 1;
           dst.cbp[(size_t)i] = nullptr;
           continue;
         }
-        dst.cbp[(size_t)i] = find_cb(r + fixed, r + bs);
+        const char *cbs = find_cb(r + fixed, r + bs);
+        dst.cbp[(size_t)i] = cbs;
+        dst.cbh[(size_t)i] = cbs ? BarcodeTable::fnv(cbs) : 0;
       }
     }
   };
@@ -434,6 +442,8 @@ void produce(Stream *s, Chunk &dst, const Chunk &prev, size_t target) {
     for (int t = 0; t < s->threads; ++t) th.emplace_back(scan);
     for (auto &t : th) t.join();
   }
+  const double t_x2 = now_s();
+  s->t_tags += t_x2 - t_x1;
   if (bad) {
     dst.err = "corrupt BAM record (fields exceed block_size)";
     dst.n = -1;
@@ -441,14 +451,13 @@ void produce(Stream *s, Chunk &dst, const Chunk &prev, size_t target) {
   }
   uint64_t co = 0, bo = 0;
   for (int64_t i = 0; i < n; ++i) {
-    const uint8_t *r = dst.recs[(size_t)i];
-    const uint64_t n_cig = rd16(r + 12), l_seq = rd32(r + 16);
+    const uint64_t n_cig = dst.ncig[(size_t)i], l_seq = dst.lseq[(size_t)i];
     dst.cig_off[(size_t)i] = (uint32_t)co;
     dst.base_off[(size_t)i] = bo;
     co += n_cig;
     bo += (l_seq + 15u) & ~(uint64_t)15u;
     const char *cbs = dst.cbp[(size_t)i];
-    dst.cb[(size_t)i] = cbs ? s->bar.intern(cbs) : -1;
+    dst.cb[(size_t)i] = cbs ? s->bar.intern(cbs, dst.cbh[(size_t)i]) : -1;
   }
   if (co >= 0xffffffffull) {
     dst.err = "more than 2^32 CIGAR operations in one chunk";
@@ -461,7 +470,7 @@ void produce(Stream *s, Chunk &dst, const Chunk &prev, size_t target) {
   dst.n_bases = (int64_t)bo;
   dst.n = n;
   dst.n_barcodes = (int32_t)s->bar.names.size();
-  s->t_index += now_s() - t_x1;
+  s->t_intern += now_s() - t_x2;
 }
 
 }  // namespace
@@ -505,9 +514,9 @@ void ls_bams_close(void *h) {
   if (!s) return;
   if (s->pf_running) s->pf.join();
   if (getenv("LS_BAM_TIMING"))
-    fprintf(stderr, "[ls_bamstream] file read %.2f s, inflate %.2f s, record index + barcodes %.2f s (all three on the prefetch "
-                    "thread), fill %.2f s, caller waited %.2f s for prefetched chunks\n",
-            s->t_read, s->t_inflate, s->t_index, s->t_fill, s->t_wait);
+    fprintf(stderr, "[ls_bamstream] file read %.2f s, inflate %.2f s, record boundaries %.2f s, CB tags %.2f s, barcode ids + offsets "
+                    "%.2f s (all on the prefetch thread), fill %.2f s, caller waited %.2f s for prefetched chunks\n",
+            s->t_read, s->t_inflate, s->t_index, s->t_tags, s->t_intern, s->t_fill, s->t_wait);
   if (s->f) fclose(s->f);
   delete s;
 }
