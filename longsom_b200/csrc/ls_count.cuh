@@ -1,7 +1,8 @@
 // K1 pileup-count kernel (one LANE per 32-column unit) + the unit expansion and part bookkeeping around it.
 // Included by ls_pileup.cu.
 //
-// After the (tile, cell) sort, `classify_kernel` + scans + `expand_kernel` turn the sorted segments into UNIT STREAMS
+// After the (tile, cell) sort, `classify_kernel` + scans + `expand_single_kernel` / `expand_runs_kernel` turn the sorted
+// segments into UNIT STREAMS
 // in HBM.  A unit is one piece (CIGAR op clipped to the tile) clipped to one of the tile's sixteen 32-column windows:
 // where its query bases start in qual[] / seq4[], the window, the columns [lo, hi) it covers, strand, and whether it
 // is a run of deletion columns (which all carry one quality).  Three streams, each in sorted-segment order:
@@ -14,7 +15,11 @@
 // one part; deep tiles (chrM, hotspot genes: >1e5 reads per locus) are split so that no CTA owns more than ~4e5
 // pileup entries.  Same-cell runs never straddle parts (a run belongs to the part that holds its first segment), so
 // NC / CC stay exact and every output word is additive across parts; multi-part tiles add into their HBM slot and
-// the last part to finish applies the reference's gates.
+// the last part to finish applies the reference's gates.  `part_build_kernel` writes one 64-byte PartDesc per CTA (tile
+// bounds, reference offset, the part's slices of the streams and of the group directory): a CTA starts with one load.
+// The same-cell runs (M) are counted first, the single-segment units (S) last, claimed one 32-unit batch at a time: the
+// fine-grained stream fills in behind the long groups, so the warps reach the tile's barrier together.  Single-part
+// tiles leave the kernel as finished 26-word site records (passing sites packed per 32-column window).
 //
 // Inside a part (CTA of K1_WARPS warps, tile accumulators in shared memory) every lane owns whole units:
 //   * the lane loads the aligned 40-byte block of qualities and 24-byte block of 4-bit bases around its unit and
