@@ -457,19 +457,7 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
             continue
         break
     body_bytes = os.path.getsize(infile) - body_start
-    native = None
-    if _native_ok(P) and cell_types_idx is not None and body_bytes > 0:
-        from concurrent.futures import ThreadPoolExecutor
-        nthr = 1 if body_bytes < (4 << 20) else min(16, _available_cpus())
-        try:
-            def parse(rng):
-                with open(infile, 'rb') as f:
-                    f.seek(rng[0])
-                    return _NativeRange(f.read(rng[1] - rng[0]), cell_types_idx, P)
-            with ThreadPoolExecutor(nthr) as ex:
-                native = list(ex.map(parse, _line_aligned_ranges(infile, body_start, nthr)))
-        except ValueError:
-            native = None    # a row the native parser refuses: the Python passes (and their exceptions) take the table
+    native = _native_ok(P) and cell_types_idx is not None and body_bytes > 0
     if procs is None:
         procs = int(os.environ.get("LONGSOM_PROCS", "0") or 0)   # an explicit setting is honoured as is
         if procs <= 0:
@@ -495,39 +483,64 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
         # == round(np.float64, 4) of the reference, element-wise
         return np.round(p1, 4), np.round(p2, 4)
 
-    if native is not None:
-        # native row passes: parse the ranges on threads (the library releases the GIL), one K2 call for all their
-        # queries, format on threads, write in order
+    if native:
+        # Native row passes, in waves of byte ranges so that the memory in flight does not grow with the table: every
+        # wave is parsed on threads (the library releases the GIL), its queries go through K2 in one call, it is
+        # formatted on threads and appended to the output.  A wave the strict parser refuses discards what has been
+        # written and leaves the whole table to the Python passes below (whose exceptions are the reference's).
         from concurrent.futures import ThreadPoolExecutor
+        nthr = 1 if body_bytes < (4 << 20) else min(16, _available_cpus())
+        chunk = int(float(os.environ.get("LONGSOM_STEP1_CHUNK_MB", "64")) * (1 << 20))
+        n_ranges = max(nthr, -(-body_bytes // max(chunk, 1 << 16)))
+        ranges = _line_aligned_ranges(infile, body_start, int(n_ranges))
         fa = bamio.Fasta(fasta) if fasta is not None else None
+        tmp_out = outfile + ".native.%d.tmp" % os.getpid()
+        n_rows = n_queries = 0
+        ok = False
+
+        def parse(rng):
+            with open(infile, 'rb') as f:
+                f.seek(rng[0])
+                return _NativeRange(f.read(rng[1] - rng[0]), cell_types_idx, P)
         try:
-            qs = [r.q for r in native]
-            r1, r2 = tails(tuple(np.concatenate([q[j] for q in qs]) if qs else np.zeros(0, np.int32) for j in range(4)))
-            o1 = np.concatenate([[0], np.cumsum([len(q[0]) for q in qs])]).astype(np.int64)
-            o2 = np.concatenate([[0], np.cumsum([len(q[2]) for q in qs])]).astype(np.int64)
-            if fa is not None:     # contigs are loaded once, before the threads share the reader
-                for r in native:
-                    for ci in range(r.lib.ls_s1_n_chroms(r.h)):
-                        try:
-                            fa.contig(r.lib.ls_s1_chrom(r.h, ci).decode())
-                        except Exception:
-                            pass
-            with ThreadPoolExecutor(max(1, len(native))) as ex:
-                texts = list(ex.map(lambda kr: kr[1].format(r1[o1[kr[0]]:o1[kr[0] + 1]], r2[o2[kr[0]]:o2[kr[0] + 1]], fa, P),
-                                    enumerate(native)))
-            with open(outfile, 'wb') as out:
+            with open(tmp_out, 'wb') as out, ThreadPoolExecutor(nthr) as ex:
                 out.write("".join(out_lines).encode())
-                for t in texts:
-                    out.write(t)
-            return sum(r.n_rows for r in native), len(r1) + len(r2)
+                for w0 in range(0, len(ranges), nthr):
+                    wave = []
+                    try:
+                        for r in ex.map(parse, ranges[w0:w0 + nthr]):   # (a refusal surfaces here as ValueError)
+                            wave.append(r)
+                        qs = [r.q for r in wave]
+                        r1, r2 = tails(tuple(np.concatenate([q[j] for q in qs]) for j in range(4)))
+                        o1 = np.concatenate([[0], np.cumsum([len(q[0]) for q in qs])]).astype(np.int64)
+                        o2 = np.concatenate([[0], np.cumsum([len(q[2]) for q in qs])]).astype(np.int64)
+                        if fa is not None:     # contigs are loaded once, before the threads share the reader
+                            for r in wave:
+                                for ci in range(r.lib.ls_s1_n_chroms(r.h)):
+                                    try:
+                                        fa.contig(r.lib.ls_s1_chrom(r.h, ci).decode())
+                                    except Exception:
+                                        pass
+                        texts = list(ex.map(lambda kr: kr[1].format(r1[o1[kr[0]]:o1[kr[0] + 1]], r2[o2[kr[0]]:o2[kr[0] + 1]], fa, P),
+                                            enumerate(wave)))
+                        for t in texts:
+                            out.write(t)
+                        n_rows += sum(r.n_rows for r in wave)
+                        n_queries += len(r1) + len(r2)
+                    finally:
+                        for r in wave:
+                            r.close()
+            os.replace(tmp_out, outfile)
+            ok = True
         except ValueError:
             pass   # fall through to the Python passes
         finally:
-            for r in native:
-                r.close()
             if fa is not None:
                 fa.close()
-        procs = 1 if procs is None or procs <= 1 else procs
+            if not ok and os.path.exists(tmp_out):
+                os.remove(tmp_out)
+        if ok:
+            return n_rows, n_queries
 
     if procs <= 1:
         fa = bamio.Fasta(fasta) if fasta is not None else None

@@ -154,3 +154,16 @@ def test_rows_the_reference_fails_on_fail_the_same_way(tmp_path):
                 _run(bad, str(tmp_path / "o.tsv"), None, native=native)
             errs.append(type(e.value))
         assert errs[0] == errs[1], name
+
+
+def test_native_waves_give_the_same_table(tmp_path, monkeypatch):
+    """Small byte ranges (LONGSOM_STEP1_CHUNK_MB): many waves, each with its own K2 call, appended in order."""
+    merged = str(tmp_path / "rand.tsv")
+    _random_table(merged, 5000, 21)
+    py, nat = str(tmp_path / "py.tsv"), str(tmp_path / "nat.tsv")
+    _run(merged, py, None, native=False)
+    monkeypatch.setenv("LONGSOM_STEP1_CHUNK_MB", "0.07")
+    _used_native(monkeypatch)
+    _run(merged, nat, None, native=True)
+    assert open(nat, "rb").read() == open(py, "rb").read()
+    assert not [f for f in os.listdir(str(tmp_path)) if f.endswith(".tmp")]
