@@ -173,3 +173,16 @@ def test_own_inflater_matches_zlib(built):
         junk = rng.integers(0, 256, int(rng.integers(0, 200)), dtype=np.uint8).tobytes()
         inflate(junk, int(rng.integers(0, 70000)))   # must not crash or write out of bounds
     assert n_streams == 400
+
+
+def test_numa_binding_helpers(built):
+    """bind_near_gpu: the cpulist parser, and a silent no-op where there is no device / no NUMA information."""
+    from longsom_b200.pipeline import _parse_cpulist, bind_near_gpu
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    before = os.sched_getaffinity(0) if hasattr(os, "sched_getaffinity") else None
+    import torch
+    if not torch.cuda.is_available():
+        assert bind_near_gpu(0) is None
+        if before is not None:
+            assert os.sched_getaffinity(0) == before
