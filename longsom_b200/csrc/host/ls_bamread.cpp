@@ -16,6 +16,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "ls_inflate.h"
@@ -411,8 +413,15 @@ inline char *put_vec6(char *p, const uint32_t *v) {
 
 extern "C" int ls_write_counter_rows(const char *path, const char *chrom, const int32_t *pos, const uint8_t *ref,
                                      const uint32_t *counts, int64_t n, int threads, int append) {
-  FILE *f = fopen(path, append ? "ab" : "wb");
-  if (!f) return -1;
+  // open(2) + pwrite(2): the threads that format a batch of rows also write it, each at its own offset (a single
+  // writer is bound by the page-cache allocation of the file, ~0.5 GB/s; the formatting itself does 1.7e7 rows/s)
+  const int fd = open(path, O_WRONLY | O_CREAT | (append ? 0 : O_TRUNC), 0666);
+  if (fd < 0) return -1;
+  off_t file_off = append ? lseek(fd, 0, SEEK_END) : 0;
+  if (file_off < 0) {
+    close(fd);
+    return -1;
+  }
   if (threads < 1) threads = 1;
   const size_t clen = strlen(chrom);
   const int64_t CH = 1 << 16;
@@ -420,14 +429,16 @@ extern "C" int ls_write_counter_rows(const char *path, const char *chrom, const 
   int rc = 0;
   for (int64_t c0 = 0; c0 < nch; c0 += threads) {
     const int nt = (int)std::min<int64_t>(threads, nch - c0);
-    std::vector<std::string> bufs(nt);
+    // (plain arrays: a std::string would zero-fill its ~420 reserved bytes per row before the ~115 that get written)
+    std::vector<std::unique_ptr<char[]>> bufs((size_t)nt);
+    std::vector<size_t> lens((size_t)nt, 0);
     std::vector<std::thread> th;
     for (int t = 0; t < nt; ++t) {
       th.emplace_back([&, t]() {
         const int64_t lo = (c0 + t) * CH, hi = std::min(n, lo + CH);
-        std::string &out = bufs[t];
-        out.resize((size_t)(hi - lo) * (clen + 420));
-        char *p = &out[0];
+        bufs[(size_t)t].reset(new char[(size_t)(hi - lo) * (clen + 420) + 16]);
+        char *const base = bufs[(size_t)t].get();
+        char *p = base;
         for (int64_t i = lo; i < hi; ++i) {
           const uint32_t *r = counts + i * 26;
           memcpy(p, chrom, clen);
@@ -451,13 +462,37 @@ extern "C" int ls_write_counter_rows(const char *path, const char *chrom, const 
           p = put_vec6(p, r + 14);  // BCr
           p[-1] = '\n';
         }
-        out.resize((size_t)(p - &out[0]));
+        lens[(size_t)t] = (size_t)(p - base);
       });
     }
     for (auto &t : th) t.join();
-    for (int t = 0; t < nt; ++t)
-      if (fwrite(bufs[t].data(), 1, bufs[t].size(), f) != bufs[t].size()) rc = -2;
+    th.clear();
+    std::vector<off_t> offs((size_t)nt);
+    for (int t = 0; t < nt; ++t) {
+      offs[(size_t)t] = file_off;
+      file_off += (off_t)lens[(size_t)t];
+    }
+    std::atomic<int> bad(0);
+    for (int t = 0; t < nt; ++t) {
+      th.emplace_back([&, t]() {
+        const char *b = bufs[(size_t)t].get();
+        size_t left = lens[(size_t)t];
+        off_t o = offs[(size_t)t];
+        while (left > 0) {
+          const ssize_t w = pwrite(fd, b, left, o);
+          if (w <= 0) {
+            bad = 1;
+            return;
+          }
+          b += w;
+          o += w;
+          left -= (size_t)w;
+        }
+      });
+    }
+    for (auto &t : th) t.join();
+    if (bad) rc = -2;
   }
-  fclose(f);
+  if (close(fd) != 0 && rc == 0) rc = -2;
   return rc;
 }
