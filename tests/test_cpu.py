@@ -186,3 +186,23 @@ def test_numa_binding_helpers(built):
         assert bind_near_gpu(0) is None
         if before is not None:
             assert os.sched_getaffinity(0) == before
+
+
+def test_early_cuda_warm_is_light_and_harmless(built):
+    """_early.warm() must not pull the numeric stack in (its point is to run BESIDE those imports) and must swallow the
+    absence of a device: the Engine created afterwards is what reports it."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from longsom_b200 import _early\n"
+            "t = _early.warm()\n"
+            "assert 'numpy' not in sys.modules and 'pandas' not in sys.modules, sorted(sys.modules)\n"
+            "t.join(60)\n"
+            "assert not t.is_alive()\n"
+            "import os; os.environ['LONGSOM_EARLY_CUDA'] = '0'\n"
+            "assert _early.warm() is None\n"
+            "os.environ['LONGSOM_GPUS'] = '3,1'; assert _early.first_device() == 3\n"
+            "os.environ['LONGSOM_GPUS'] = '4'; assert _early.first_device() == 0\n"
+            "print('ok')\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == "ok", r.stderr[-2000:]

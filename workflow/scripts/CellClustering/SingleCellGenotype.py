@@ -6,6 +6,9 @@ import os
 import sys
 
 sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..")))
+if __name__ == '__main__':
+    from longsom_b200 import _early  # noqa: E402
+    _early.warm()  # the CUDA context comes up while the numeric stack below is imported
 from longsom_b200.cli.genotype import main  # noqa: E402
 
 if __name__ == '__main__':
