@@ -541,6 +541,8 @@ def variant_calling_step1(infile, outfile, fasta, alpha1, beta1, alpha2, beta2, 
                 os.remove(tmp_out)
         if ok:
             return n_rows, n_queries
+        if "engine" in warm:
+            procs = 1   # a wave has already created the CUDA context: the Python passes must not fork below it
 
     if procs <= 1:
         fa = bamio.Fasta(fasta) if fasta is not None else None
